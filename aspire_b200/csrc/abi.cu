@@ -1,0 +1,69 @@
+// C-ABI glue: error state, version, options, and the composed otAspire entry point.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace asp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return ASP_ERR_CUDA;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+extern int g_ot_kernel;
+
+}  // namespace asp
+
+extern "C" int asp_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" const char* asp_last_error(void) { return asp::g_err; }
+
+extern "C" int asp_sm_count(void) {
+    int dev = 0, n = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    ASP_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    return n;
+}
+
+extern "C" int asp_set_option(const char* key, int value) {
+    ASP_REQUIRE(key, "asp_set_option: NULL key");
+    if (strcmp(key, "ot_kernel") == 0) {
+        ASP_REQUIRE(value >= 0 && value <= 2, "asp_set_option: ot_kernel must be 0 (auto), 1 (warp) or 2 (thread)");
+        asp::g_ot_kernel = value;
+        return ASP_OK;
+    }
+    asp::set_error("asp_set_option: unknown key '%s'", key);
+    return ASP_ERR_INVALID;
+}
+
+extern "C" int asp_ot_sinkhorn(const float* q, const int32_t* q_lens, int q_broadcast, const float* c,
+                               const int32_t* c_lens, int B, int Sq, int Sc, int D, const float* eps_host, int n_eps,
+                               float temp, float* cost_workspace, const asp_ot_outputs* out, asp_stream_t stream) {
+    ASP_REQUIRE(cost_workspace, "asp_ot_sinkhorn: cost_workspace is NULL (needs B*Sq*Sc floats)");
+    int rc = asp_pair_cost(q, q_lens, q_broadcast, c, c_lens, B, Sq, Sc, D, cost_workspace, stream);
+    if (rc) return rc;
+    return asp_ot_sinkhorn_from_cost(cost_workspace, q_lens, q_broadcast, c_lens, B, Sq, Sc, eps_host, n_eps, temp,
+                                     out, stream);
+}

@@ -1,0 +1,80 @@
+// Shared device/host helpers for the aspire_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/aspire_b200.h"
+
+namespace asp {
+
+// ---- error plumbing (thread-local message, returned through asp_last_error) -------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define ASP_REQUIRE(cond, ...)                       \
+    do {                                             \
+        if (!(cond)) {                               \
+            ::asp::set_error(__VA_ARGS__);           \
+            return ASP_ERR_INVALID;                  \
+        }                                            \
+    } while (0)
+
+#define ASP_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return ::asp::cuda_fail(e__, #call);    \
+    } while (0)
+
+#define ASP_LAUNCH_CHECK(name)                                               \
+    do {                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                \
+        if (e__ != cudaSuccess) return ::asp::cuda_fail(e__, "launch " name); \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+int sm_count();
+
+// Epsilon schedule passed by value in kernel parameter space (uniform, read through the constant bank).
+struct EpsSched {
+    int n;
+    float eps[ASP_MAX_EPS];
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kPadNeg = -1.0e9f;        // pair_distances.py:39 mask constant
+constexpr float kLogZeroWeight = -100000.0f;  // geomloss log_weights() value for zero-mass points
+
+// ---- device math ------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, s));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// Streaming 128-bit load that does not allocate in L1 (data read exactly once).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+}  // namespace asp

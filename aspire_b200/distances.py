@@ -1,0 +1,190 @@
+"""Pair-scoring functions of Aspire, backed by the sm_100a kernels (host-side mirror of the reference API).
+
+Mirrors, name for name and argument for argument:
+  * ``AllPairMaskedWasserstein`` / ``compute_distance``  -- src/learning/facetid_models/pair_distances.py:14-92
+    (release copy examples/ex_aspire_consent_multimatch.py:111-189)                       [otAspire]
+  * ``allpair_masked_dist_l2max``                         -- pair_distances.py:138-186     [tsAspire]
+  * ``rep_len_tup``                                       -- disent_models.py:16 (namedtuple RepLen(embed, abs_lens))
+plus array-level entry points (``ot_scores``, ``l2max_scores``) that the batched scorers and the bench use.
+
+Inputs may live on the CPU (as in the reference, which never leaves the CPU in its release scripts) or on a
+CUDA device; results come back on the device of ``query.embed``.  All arithmetic runs in the CUDA library --
+there is no CPU implementation in this package.
+"""
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import _abi
+
+rep_len_tup = namedtuple("RepLen", ["embed", "abs_lens"])
+RepLen = rep_len_tup
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _abi.AspireB200Error("aspire_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def epsilon_schedule(diameter, blur, scaling, p=1):
+    """geomloss 0.2.4 ``epsilon_schedule`` in float64 (reached from pair_distances.py:68-72,88-91).
+
+    [diam^p] + [exp(e) for e in arange(p ln diam, p ln blur, p ln scaling)] + [blur^p]
+    """
+    steps = np.arange(p * np.log(diameter), p * np.log(blur), p * np.log(scaling))
+    return [float(diameter) ** p] + [float(np.exp(e)) for e in steps] + [float(blur) ** p]
+
+
+def _as_bsd(embed, dev):
+    """Reference layout [B, D, S] (pair_distances.py:28-31) -> contiguous fp32 [B, S, D] on the GPU."""
+    if embed.dim() != 3:
+        raise AssertionError("embed must be batch_size x encoding_dim x max_sents")
+    t = embed.permute(0, 2, 1)
+    return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def _lens_tensor(lens, dev):
+    if isinstance(lens, torch.Tensor):
+        return lens.to(device=dev, dtype=torch.int32).contiguous()
+    return torch.tensor(list(lens), dtype=torch.int32).to(dev, non_blocking=True)
+
+
+def bbox_diameter(x_rows, y_rows):
+    """geomloss ``max_diameter`` over the rows of two fp32 CUDA tensors [..., D] (pad rows included)."""
+    D = x_rows.shape[-1]
+    dev = x_rows.device
+    ws = torch.empty(2 * D + 1, dtype=torch.float32, device=dev)
+    L = _abi.lib()
+    _abi.check(L.asp_bbox_diameter(_abi.ptr(x_rows), x_rows.numel() // D, _abi.ptr(y_rows), y_rows.numel() // D, D,
+                                   _abi.ptr(ws), ctypes.c_void_p(ws.data_ptr() + 8 * D), _abi.stream_of(dev)),
+               "asp_bbox_diameter")
+    return float(ws[2 * D].item())
+
+
+_OT_FIELDS = ("dual", "primal", "f", "g", "alpha", "beta", "neg_cost", "plan", "weighted")
+
+
+def ot_scores(q, q_lens, c, c_lens, eps_list, temp=1.0, want=("dual",), broadcast_query=False, cost_workspace=None):
+    """Masked Sinkhorn OT on contiguous fp32 CUDA tensors.
+
+    q [B,Sq,D] (or [1,Sq,D] with ``broadcast_query``), c [B,Sc,D]; lens int32 CUDA tensors.
+    ``eps_list``: the epsilon schedule (python floats / float64).  Returns a dict of the requested outputs.
+    """
+    _abi.require_cuda(q, c, q_lens, c_lens)
+    B, Sc, D = c.shape
+    Sq = q.shape[1]
+    if broadcast_query:
+        assert q.shape[0] == 1
+    else:
+        assert q.shape[0] == B
+    assert q.is_contiguous() and c.is_contiguous() and q.dtype == c.dtype == torch.float32
+    dev = c.device
+    shapes = {"dual": (B,), "primal": (B,), "f": (B, Sq), "g": (B, Sc), "alpha": (B, Sq), "beta": (B, Sc),
+              "neg_cost": (B, Sq, Sc), "plan": (B, Sq, Sc), "weighted": (B, Sq, Sc)}
+    res = {k: torch.empty(shapes[k], dtype=torch.float32, device=dev) for k in want}
+    outs = _abi.AspOtOutputs(**{k: (res[k].data_ptr() if k in res else None) for k in _OT_FIELDS})
+    if cost_workspace is None:
+        cost_workspace = torch.empty((B, Sq, Sc), dtype=torch.float32, device=dev)
+    eps32 = np.asarray(eps_list, dtype=np.float32)
+    L = _abi.lib()
+    _abi.check(L.asp_ot_sinkhorn(_abi.ptr(q), _abi.ptr(q_lens), int(broadcast_query), _abi.ptr(c), _abi.ptr(c_lens),
+                                 B, Sq, Sc, D, eps32.ctypes.data_as(_abi.c_float_p), len(eps32), float(temp),
+                                 _abi.ptr(cost_workspace), ctypes.byref(outs), _abi.stream_of(dev)),
+               "asp_ot_sinkhorn")
+    return res
+
+
+def l2max_scores(q, q_lens, c, c_lens, broadcast_query=False, want_pair_sims=False):
+    """tsAspire on contiguous fp32 CUDA tensors: (best [B], flat argmax int32 [B], pair_sims or None)."""
+    _abi.require_cuda(q, c, q_lens, c_lens)
+    B, Sc, D = c.shape
+    Sq = q.shape[1]
+    dev = c.device
+    best = torch.empty(B, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, dtype=torch.int32, device=dev)
+    sims = torch.empty((B, Sq, Sc), dtype=torch.float32, device=dev) if want_pair_sims else None
+    L = _abi.lib()
+    _abi.check(L.asp_l2max(_abi.ptr(q), _abi.ptr(q_lens), int(broadcast_query), _abi.ptr(c), _abi.ptr(c_lens),
+                           B, Sq, Sc, D, _abi.ptr(best), _abi.ptr(idx), _abi.ptr(sims), _abi.stream_of(dev)),
+               "asp_l2max")
+    return best, idx, sims
+
+
+class AllPairMaskedWasserstein:
+    """Drop-in for pair_distances.AllPairMaskedWasserstein (same hparam keys and defaults, :15-19).
+
+    Extension key ``geoml_diameter``: fix the bounding-box diameter instead of deriving it from the call's
+    batch as geomloss does (makes scores independent of how a pool is batched / sharded).
+    """
+
+    def __init__(self, model_hparams):
+        self.geoml_blur = model_hparams.get('geoml_blur', 0.05)
+        self.geoml_scaling = model_hparams.get('geoml_scaling', 0.9)
+        self.geoml_reach = model_hparams.get('geoml_reach', None)
+        self.sent_sm_temp = model_hparams.get('sent_sm_temp', 1.0)
+        self.geoml_diameter = model_hparams.get('geoml_diameter', None)
+        if self.geoml_reach is not None:
+            raise NotImplementedError("unbalanced OT (geoml_reach) is not used by any released Aspire config")
+        self.last_schedule = None
+
+    def compute_distance(self, query, cand, return_pair_sims=False):
+        """
+        :param query: namedtuple(embed: batch_size x encoding_dim x q_max_sents; abs_lens: list(int))
+        :param cand: namedtuple(embed: batch_size x encoding_dim x c_max_sents; abs_lens: list(int))
+        :return: return_pair_sims=False -> OT_eps distances [B] (>= 0);
+                 True -> (sum P*(-C) [B], [query_distr, cand_distr, pair_sims, transport_plan, masked_sims])
+        """
+        out_dev = query.embed.device
+        dev = query.embed.device if query.embed.is_cuda else _device()
+        qef_batch_size, _, qmax_sents = query.embed.size()
+        cef_batch_size, encoding_dim, cmax_sents = cand.embed.size()
+        assert (qef_batch_size == cef_batch_size)
+        assert len(query.abs_lens) == qef_batch_size and len(cand.abs_lens) == cef_batch_size
+        q = _as_bsd(query.embed, dev)
+        c = _as_bsd(cand.embed, dev)
+        ql, cl = _lens_tensor(query.abs_lens, dev), _lens_tensor(cand.abs_lens, dev)
+        diameter = self.geoml_diameter
+        if diameter is None:
+            diameter = bbox_diameter(q, c)  # whole call batch incl. pad rows, like geomloss
+        eps_list = epsilon_schedule(diameter, self.geoml_blur, self.geoml_scaling)
+        self.last_schedule = (diameter, len(eps_list))
+        if not return_pair_sims:
+            res = ot_scores(q, ql, c, cl, eps_list, temp=self.sent_sm_temp, want=("dual",))
+            return res["dual"].to(out_dev)
+        res = ot_scores(q, ql, c, cl, eps_list, temp=self.sent_sm_temp,
+                        want=("primal", "alpha", "beta", "neg_cost", "plan", "weighted"))
+        extras = [res[k].to(out_dev) for k in ("alpha", "beta", "neg_cost", "plan", "weighted")]
+        return res["primal"].to(out_dev), extras
+
+
+def allpair_masked_dist_l2max(query, cand, return_pair_sims=False):
+    """Drop-in for pair_distances.allpair_masked_dist_l2max (:138-186).
+
+    return_pair_sims=True -> (batch_sims [B] = max -dist, pair_sims [B,Sq,Sc] with -1e9 on padding);
+    False -> positive distances -max (what the triplet loss minimises).
+    """
+    out_dev = query.embed.device
+    dev = query.embed.device if query.embed.is_cuda else _device()
+    qef_batch_size, _, qmax_sents = query.embed.size()
+    cef_batch_size, encoding_dim, cmax_sents = cand.embed.size()
+    assert (qef_batch_size == cef_batch_size)
+    q = _as_bsd(query.embed, dev)
+    c = _as_bsd(cand.embed, dev)
+    ql, cl = _lens_tensor(query.abs_lens, dev), _lens_tensor(cand.abs_lens, dev)
+    best, _idx, sims = l2max_scores(q, ql, c, cl, want_pair_sims=return_pair_sims)
+    if return_pair_sims:
+        return best.to(out_dev), sims.to(out_dev)
+    return (-1 * best).to(out_dev)
+
+
+def allpair_masked_argmax_l2max(query, cand):
+    """The flat argmax ``i*cmax_sents + j`` the reference computes at pair_distances.py:176 and drops."""
+    dev = query.embed.device if query.embed.is_cuda else _device()
+    q = _as_bsd(query.embed, dev)
+    c = _as_bsd(cand.embed, dev)
+    ql, cl = _lens_tensor(query.abs_lens, dev), _lens_tensor(cand.abs_lens, dev)
+    best, idx, _ = l2max_scores(q, ql, c, cl)
+    return best.to(query.embed.device), idx.to(device=query.embed.device, dtype=torch.int64)

@@ -1,0 +1,95 @@
+"""GPU parity: tsAspire (masked max of -L2 distance + flat argmax) through the C ABI vs oracle / golden."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aspire_ref as ar
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+OT_FILES = sorted(glob.glob(os.path.join(GOLDEN, "ot_*.npz")))
+
+
+@pytest.mark.parametrize("fn", OT_FILES, ids=[os.path.basename(f) for f in OT_FILES])
+def test_l2max_vs_golden(fn):
+    from aspire_b200 import allpair_masked_dist_l2max, allpair_masked_argmax_l2max, rep_len_tup
+    z = np.load(fn)
+    q, c = torch.from_numpy(z["q"]).cuda(), torch.from_numpy(z["c"]).cuda()
+    ql, cl = z["q_lens"].tolist(), z["c_lens"].tolist()
+    qt = rep_len_tup(embed=q.permute(0, 2, 1), abs_lens=ql)
+    ct = rep_len_tup(embed=c.permute(0, 2, 1), abs_lens=cl)
+    sims, pair = allpair_masked_dist_l2max(query=qt, cand=ct, return_pair_sims=True)
+    np.testing.assert_allclose(sims.cpu().numpy(), z["l2max_best"], rtol=1e-5, atol=2e-5)
+    ref_pair = z["l2max_sims"]
+    got = pair.cpu().numpy()
+    assert np.array_equal(got <= -1e8, ref_pair <= -1e8)  # same padding pattern, -1e9 exactly
+    assert np.all(got[ref_pair <= -1e8] == np.float32(-1e9))
+    np.testing.assert_allclose(got[ref_pair > -1e8], ref_pair[ref_pair > -1e8], rtol=1e-5, atol=2e-5)
+    dist = allpair_masked_dist_l2max(query=qt, cand=ct)
+    np.testing.assert_allclose(dist.cpu().numpy(), z["l2max_dist"], rtol=1e-5, atol=2e-5)
+    # argmax: exact, except where the fp64 top-2 gap is a true near-tie (< 1e-5)
+    _, idx = allpair_masked_argmax_l2max(query=qt, cand=ct)
+    idx = idx.cpu().numpy()
+    d64 = torch.cdist(torch.from_numpy(z["q"]).double(), torch.from_numpy(z["c"]).double()).numpy()
+    for b in range(len(ql)):
+        if idx[b] == z["l2max_idx"][b]:
+            continue
+        blk = np.sort(d64[b, :ql[b], :cl[b]].reshape(-1))
+        assert blk.size > 1 and blk[1] - blk[0] < 1e-5, f"argmax mismatch on pair {b} without a near-tie"
+
+
+def test_l2max_cpu_inputs_roundtrip():
+    from aspire_b200 import allpair_masked_dist_l2max, rep_len_tup
+    g = torch.Generator().manual_seed(0)
+    q = 0.3 * torch.randn(3, 4, 32, generator=g)
+    c = 0.3 * torch.randn(3, 6, 32, generator=g)
+    qt = rep_len_tup(embed=q.permute(0, 2, 1), abs_lens=[4, 2, 1])
+    ct = rep_len_tup(embed=c.permute(0, 2, 1), abs_lens=[6, 6, 3])
+    sims, pair = allpair_masked_dist_l2max(qt, ct, return_pair_sims=True)
+    assert not sims.is_cuda and pair.shape == (3, 4, 6)
+    best, idx, ref_pair = ar.l2max(q, [4, 2, 1], c, [6, 6, 3])
+    np.testing.assert_allclose(sims.numpy(), best.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_first_occurrence_on_exact_ties():
+    """Duplicate candidate sentences give exactly equal distances: the flat argmax is the first one."""
+    from aspire_b200 import l2max_scores
+    g = torch.Generator().manual_seed(1)
+    q = 0.3 * torch.randn(8, 6, 256, generator=g)
+    c = 0.3 * torch.randn(8, 9, 256, generator=g)
+    c[:, 7] = c[:, 2]
+    c[:, 5] = c[:, 2]
+    q[:, 4] = q[:, 1]
+    best, idx, _ = l2max_scores(q.cuda(), torch.full((8,), 6).int().cuda(), c.cuda(), torch.full((8,), 9).int().cuda())
+    rb, ri, _ = ar.l2max(q, [6] * 8, c, [9] * 8)
+    d64 = torch.cdist(q.double(), c.double())
+    for b in range(8):
+        i, j = divmod(int(idx[b]), 9)
+        # the winner must be the first flat index among the exact-duplicate group of the fp64 minimum
+        mi, mj = divmod(int(torch.argmin(d64[b].reshape(-1))), 9)
+        dup_i = {1, 4} if mi in (1, 4) else {mi}
+        dup_j = {2, 5, 7} if mj in (2, 5, 7) else {mj}
+        assert (i, j) == (min(dup_i), min(dup_j))
+
+
+def test_large_batch_property():
+    """BASELINE-size property: score == -min over the valid block of exact fp64 distances (sampled), 1xN mode."""
+    from aspire_b200 import l2max_scores
+    g = torch.Generator().manual_seed(2345)
+    N = 20000
+    q = (0.3 * torch.randn(1, 10, 768, generator=g)).cuda()
+    c = (0.3 * torch.randn(N, 10, 768, generator=g)).cuda()
+    cl = torch.randint(1, 11, (N,), generator=g).int().cuda()
+    best, idx, _ = l2max_scores(q, torch.tensor([10]).int().cuda(), c, cl, broadcast_query=True)
+    sel = torch.arange(0, N, 97)
+    d = torch.cdist(q[0].double().cpu()[None].expand(len(sel), -1, -1), c[sel].double().cpu())
+    for n, b in enumerate(sel.tolist()):
+        blk = d[n, :, :cl[b]]
+        assert abs(-blk.min().item() - best[b].item()) < 2e-5
+        i, j = divmod(int(idx[b]), 10)
+        assert abs(blk[i, j].item() - blk.min().item()) < 1e-5
