@@ -65,8 +65,9 @@ def lib():
     L.asp_topk_merge.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
-        if name not in ("asp_last_error",):
+        if name not in ("asp_last_error", "asp_launch_count"):
             fn.restype = ci
+    L.asp_launch_count.restype = cll
     _lib = L
     return L
 
@@ -90,6 +91,10 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise AspireB200Error("aspire_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+def launch_count():
+    return int(lib().asp_launch_count())
 
 
 def set_option(key, value):

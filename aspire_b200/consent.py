@@ -1,0 +1,162 @@
+"""Contextual sentence encoder front-end: batch preparation (host) + AspireConSent (device).
+
+Mirrors the release API of the reference, keyword for keyword:
+  * ``prepare_bert_sentences(batch_doc_sents, tokenizer)``  -- examples/ex_aspire_consent.py:107-181
+    (= src/learning/batchers.py:555-630)
+  * ``prepare_abstracts(batch_abs, pt_lm_tokenizer)``       -- examples/ex_aspire_consent.py:185-212
+    (= src/learning/batchers.py:525-553)
+  * ``AspireConSent(hf_model_name).forward(bert_batch, abs_lens, sent_tok_idxs)`` -- :25-101
+
+The pooling step (K1) runs in the CUDA library (``asp_span_mean_pool``): sentence spans are contiguous token
+ranges, so the kernel takes ``(start, end)`` pairs instead of the reference's dense [B,L,768] float64 masks.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import _abi
+
+MAX_WORDPIECES = 500  # examples/ex_aspire_consent.py:120
+
+
+def prepare_bert_sentences(batch_doc_sents, tokenizer):
+    """Tokenise documents given as lists of "sentences" (element 0 is the title + ' [SEP] ').
+
+    Per document the word-pieces of all sentences are concatenated into ONE sequence
+    ``[CLS] w... [SEP]`` (no separator between abstract sentences); the token positions of every sentence
+    are recorded (+1 for the leading [CLS]); at most 500 word-pieces are kept -- the sentence that crosses
+    the budget is cut to fit and later ones are dropped; the title's positions are not returned.
+
+    :return: (bert_batch{'tokid_tt','seg_tt','attnmask_tt': int64 [B,Lmax], 'seq_lens': list},
+              batch_tokenized_text: list(list(str)), batch_sent_token_idxs: list(list(list(int))))
+    """
+    docs_ids, docs_text, docs_spans = [], [], []
+    for doc_sents in batch_doc_sents:
+        ids, text, spans = [], [], []
+        used = 0
+        for sent in doc_sents:
+            pieces = tokenizer.tokenize(sent)
+            piece_ids = tokenizer.convert_tokens_to_ids(pieces)
+            room = MAX_WORDPIECES - used
+            take = min(len(pieces), room)
+            if take > 0 or len(pieces) == 0:
+                # positions are shifted by one for the [CLS] prepended below
+                spans.append(list(range(used + 1, used + 1 + take)))
+                text.extend(pieces[:take])
+                ids.extend(piece_ids[:take])
+            if len(pieces) > room:
+                break  # budget exhausted: this sentence was cut (or skipped when nothing fitted)
+            used += take
+        docs_text.append(text)
+        docs_spans.append(spans[1:])  # the title is encoded but never pooled
+        docs_ids.append(tokenizer.build_inputs_with_special_tokens(token_ids_0=ids))
+    seq_lens = [len(x) for x in docs_ids]
+    width = max(seq_lens) if seq_lens else 0
+    pad = tokenizer.pad_token_id
+    tok = [x + [pad] * (width - len(x)) for x in docs_ids]
+    seg = [[0] * n + [pad] * (width - n) for n in seq_lens]
+    att = [[1] * n + [pad] * (width - n) for n in seq_lens]
+    bert_batch = {
+        'tokid_tt': torch.tensor(tok),
+        'seg_tt': torch.tensor(seg),
+        'attnmask_tt': torch.tensor(att),
+        'seq_lens': seq_lens,
+    }
+    return bert_batch, docs_text, docs_spans
+
+
+def prepare_abstracts(batch_abs, pt_lm_tokenizer):
+    """
+    :param batch_abs: list(dict) with 'TITLE' (str) and 'ABSTRACT' (list of sentence strings).
+    :return: (bert_batch, abs_lens: list(int), sent_token_idxs: list(list(list(int))))
+    """
+    seqs = [[ex['TITLE'] + ' [SEP] '] + list(ex['ABSTRACT']) for ex in batch_abs]
+    bert_batch, _tokenized, sent_token_idxs = prepare_bert_sentences(batch_doc_sents=seqs,
+                                                                     tokenizer=pt_lm_tokenizer)
+    abs_lens = [len(s) for s in sent_token_idxs]
+    for n in abs_lens:
+        assert (n > 0)  # an abstract whose title alone fills the budget (reference :210)
+    return bert_batch, abs_lens, sent_token_idxs
+
+
+def spans_from_token_idxs(sent_tok_idxs, max_sents):
+    """list[B][S][tokens] -> int32 [B, max_sents, 2] half-open (start, end); (-1,-1) for missing sentences."""
+    B = len(sent_tok_idxs)
+    out = -np.ones((B, max_sents, 2), dtype=np.int32)
+    for b, sents in enumerate(sent_tok_idxs):
+        for s, toks in enumerate(sents[:max_sents]):
+            if len(toks) == 0:
+                continue
+            start, end = int(toks[0]), int(toks[-1]) + 1
+            if end - start != len(toks):
+                raise NotImplementedError("span_mean_pool needs contiguous token ranges per sentence")
+            out[b, s] = (start, end)
+    return torch.from_numpy(out)
+
+
+def span_mean_pool(hidden, spans):
+    """K1 on the GPU: hidden fp32 CUDA [B,L,D], spans int32 CUDA [B,Smax,2] -> (cls [B,D], sent_reps [B,Smax,D])."""
+    _abi.require_cuda(hidden, spans)
+    B, L, D = hidden.shape
+    smax = spans.shape[1]
+    hidden = hidden.contiguous()
+    spans = spans.contiguous()
+    reps = torch.empty((B, smax, D), dtype=torch.float32, device=hidden.device)
+    cls = torch.empty((B, D), dtype=torch.float32, device=hidden.device)
+    _abi.check(_abi.lib().asp_span_mean_pool(_abi.ptr(hidden), _abi.ptr(spans), B, L, D, smax, _abi.ptr(reps),
+                                             _abi.ptr(cls), _abi.stream_of(hidden.device)), "asp_span_mean_pool")
+    return cls, reps
+
+
+class AspireConSent(nn.Module):
+    """Drop-in for examples/ex_aspire_consent.py:25-101 (and the multimatch copy :30-106).
+
+    ``bert_encoder`` keeps the reference's attribute name so released state dicts load unchanged
+    (SURVEY appendix A.11).  The encoder and the pooling kernel run on the current CUDA device; outputs are
+    returned on the device of ``bert_batch['tokid_tt']`` (CPU in the reference's scripts).
+    """
+
+    def __init__(self, hf_model_name):
+        torch.nn.Module.__init__(self)
+        from transformers import AutoModel
+        self.bert_encoding_dim = 768
+        self.bert_layer_count = 12 + 1
+        self.bert_encoder = AutoModel.from_pretrained(hf_model_name)
+        self.bert_encoder.config.output_hidden_states = True
+
+    def forward(self, bert_batch, abs_lens, sent_tok_idxs):
+        """
+        :return: doc_cls_reps [B, 768], sent_reps [B, max(abs_lens), 768] (zero rows past abs_lens[b]).
+        """
+        doc_cls_reps, sent_reps = self.consent_reps_bert(bert_batch=bert_batch, num_sents=abs_lens,
+                                                         batch_senttok_idxs=sent_tok_idxs)
+        if len(sent_reps.size()) == 2:
+            sent_reps = sent_reps.unsqueeze(0)
+        if len(doc_cls_reps.size()) == 1:
+            doc_cls_reps = doc_cls_reps.unsqueeze(0)
+        return doc_cls_reps, sent_reps
+
+    def _device(self):
+        if not torch.cuda.is_available():
+            raise _abi.AspireB200Error("AspireConSent needs a CUDA device; there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if next(self.bert_encoder.parameters()).device != dev:
+            self.bert_encoder.to(dev)
+        return dev
+
+    def encode_hidden(self, tokid_tt, seg_tt, attnmask_tt):
+        """BERT forward -> last_hidden_state fp32 [B,L,768] on the GPU (K0)."""
+        out = self.bert_encoder(tokid_tt, token_type_ids=seg_tt, attention_mask=attnmask_tt)
+        return out.last_hidden_state.float()
+
+    def consent_reps_bert(self, bert_batch, batch_senttok_idxs, num_sents):
+        out_dev = bert_batch['tokid_tt'].device
+        dev = self._device()
+        max_sents = max(num_sents)
+        tokid_tt, seg_tt, attnmask_tt = (bert_batch[k].to(dev, non_blocking=True)
+                                         for k in ('tokid_tt', 'seg_tt', 'attnmask_tt'))
+        spans = spans_from_token_idxs(batch_senttok_idxs, max_sents).to(dev, non_blocking=True)
+        hidden = self.encode_hidden(tokid_tt, seg_tt, attnmask_tt)
+        doc_cls_reps, sent_reps = span_mean_pool(hidden, spans)
+        doc_cls_reps = doc_cls_reps.squeeze()  # reference :76 ([768] when B == 1; forward() re-expands)
+        return doc_cls_reps.to(out_dev), sent_reps.to(out_dev)

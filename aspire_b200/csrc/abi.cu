@@ -1,6 +1,7 @@
 // C-ABI glue: error state, version, options, and the composed otAspire entry point.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace asp {
@@ -34,6 +35,9 @@ int sm_count() {
 
 extern int g_ot_kernel;
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 }  // namespace asp
 
 extern "C" int asp_version(void) { return 100; /* 0.1.0 */ }
@@ -46,6 +50,8 @@ extern "C" int asp_sm_count(void) {
     ASP_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     return n;
 }
+
+extern "C" long long asp_launch_count(void) { return asp::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int asp_set_option(const char* key, int value) {
     ASP_REQUIRE(key, "asp_set_option: NULL key");
@@ -61,6 +67,7 @@ extern "C" int asp_set_option(const char* key, int value) {
 extern "C" int asp_ot_sinkhorn(const float* q, const int32_t* q_lens, int q_broadcast, const float* c,
                                const int32_t* c_lens, int B, int Sq, int Sc, int D, const float* eps_host, int n_eps,
                                float temp, float* cost_workspace, const asp_ot_outputs* out, asp_stream_t stream) {
+    if (B == 0) return ASP_OK;
     ASP_REQUIRE(cost_workspace, "asp_ot_sinkhorn: cost_workspace is NULL (needs B*Sq*Sc floats)");
     int rc = asp_pair_cost(q, q_lens, q_broadcast, c, c_lens, B, Sq, Sc, D, cost_workspace, stream);
     if (rc) return rc;

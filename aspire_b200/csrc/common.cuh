@@ -10,6 +10,7 @@ namespace asp {
 // ---- error plumbing (thread-local message, returned through asp_last_error) -------------------------
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();  // every kernel launch of this library is counted (asp_launch_count)
 
 #define ASP_REQUIRE(cond, ...)                       \
     do {                                             \
@@ -29,6 +30,7 @@ int cuda_fail(cudaError_t e, const char* what);
     do {                                                                     \
         cudaError_t e__ = cudaGetLastError();                                \
         if (e__ != cudaSuccess) return ::asp::cuda_fail(e__, "launch " name); \
+        ::asp::count_launch();                                               \
     } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -1,0 +1,259 @@
+"""Plugin boundary of the evaluation code: ``SimilarityModel`` and the otAspire / tsAspire models behind it.
+
+Mirrors src/evaluation/utils/models.py:
+  * ``SimilarityModel``  (:23-167)  -- same constructor, abstract ``encode`` / ``get_similarity``, cache helpers
+  * ``AspireModel``      (:169-209) -- otAspire: ``encode`` = prepare_abstracts + AspireConSent.forward,
+                                        ``get_similarity(x, y)`` = -OT_eps(x, y)
+  * ``get_model``        (:738-768) -- factory for the model names on this path
+and adds the batched entry point the reference lacks: ``score_pool(query_enc, cand_encs)`` scores one query
+against a whole candidate pool in one kernel launch (the reference's evaluate.py:72-74 loop calls
+``get_similarity`` once per pair; pp_gen_nearest.py:182-202 batches 64 at a time through caching_score).
+"""
+import logging
+import os
+from abc import ABCMeta, abstractmethod
+from typing import Dict, List, Union
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _abi
+from .consent import AspireConSent, prepare_abstracts
+from .distances import (AllPairMaskedWasserstein, bbox_diameter, epsilon_schedule, l2max_scores, ot_scores,
+                        rep_len_tup)
+
+
+class EncodingsCache(dict):
+    """{paper_id: encoding} with the three h5py.File members the reference touches (utils/models.py:76-95,112-114).
+
+    h5py is not a dependency here; the cache persists as one ``.npz`` when a filename is given.
+    """
+
+    def __init__(self, filename=None):
+        super().__init__()
+        self.filename = filename
+        if filename and os.path.exists(filename):
+            with np.load(filename, allow_pickle=False) as z:
+                for k in z.files:
+                    self[k] = z[k]
+
+    def create_dataset(self, name, data):
+        self[name] = data.detach().cpu().numpy() if isinstance(data, Tensor) else np.asarray(data)
+
+    def close(self):
+        if self.filename:
+            np.savez(self.filename if self.filename.endswith(".npz") else self.filename + ".npz", **self)
+
+
+def batchify(dataset: Dict, batch_size: int):
+    """src/evaluation/utils/utils.py:10-27 -- (pids, papers) groups of ``batch_size`` in dict order."""
+    items = list(dataset.items())
+    for s in range(0, len(items), batch_size):
+        chunk = items[s:s + batch_size]
+        yield [p for p, _ in chunk], [d for _, d in chunk]
+
+
+class SimilarityModel(metaclass=ABCMeta):
+    """Abstract paper-similarity model: implement ``encode`` and ``get_similarity`` (higher == closer)."""
+    ENCODING_TYPES = ('abstract', 'sentence', 'sentence-entity')
+
+    def __init__(self, name: str, encoding_type: str, batch_size: int = 8):
+        self.name = name
+        assert encoding_type in SimilarityModel.ENCODING_TYPES, \
+            'Model output representation must be "abstract", "sentence" or "sentence-entity"'
+        self.encoding_type = encoding_type
+        self.batch_size = batch_size
+        self.cache = None
+
+    @abstractmethod
+    def encode(self, batch_papers: List[Dict]):
+        raise NotImplementedError()
+
+    @abstractmethod
+    def get_similarity(self, x: Union[Tensor, np.ndarray], y: Union[Tensor, np.ndarray]):
+        raise NotImplementedError()
+
+    def set_encodings_cache(self, cache_filename: str):
+        self.cache = EncodingsCache(cache_filename)
+
+    def cache_encodings(self, batch_pids: List[str], batch_papers: List[dict]):
+        assert self.cache is not None, "Cannot cache encodings, cache is not set"
+        encodings = self.encode(batch_papers)
+        for pid, enc in zip(batch_pids, encodings):
+            self.cache.create_dataset(name=pid, data=enc)
+        return encodings
+
+    def get_encoding(self, pids: List[str], dataset) -> Dict:
+        uncached = [p for p in pids if p not in self.cache] if self.cache is not None else list(pids)
+        out = {p: torch.from_numpy(np.array(self.cache.get(p))) for p in set(pids).difference(uncached)}
+        for batch_pids, batch_papers in batchify({p: dataset.get(p) for p in uncached}, self.batch_size):
+            encs = self.cache_encodings(batch_pids, batch_papers) if self.cache is not None \
+                else self.encode(batch_papers)
+            out.update({p: encs[i] for i, p in enumerate(batch_pids)})
+        return out
+
+    def get_faceted_encoding(self, unfaceted_encoding, facet: str, input_data: Dict):
+        """Keep only the sentence (and entity) rows whose predicted facet label matches (utils/models.py:127-163)."""
+        if self.encoding_type == 'abstract':
+            return unfaceted_encoding
+        labels = ['background' if lab == 'objective_label' else lab[:-len('_label')] for lab in input_data['FACETS']]
+        sent_ids = [i for i, k in enumerate(labels) if facet == k]
+        if self.encoding_type == 'sentence':
+            return unfaceted_encoding[sent_ids]
+        ner_ids, cursor = [], len(labels)
+        for i, sent_ners in enumerate(input_data['ENTITIES']):
+            if i in sent_ids:
+                ner_ids += list(range(cursor, cursor + len(sent_ners)))
+            cursor += len(sent_ners)
+        return unfaceted_encoding[sent_ids + ner_ids]
+
+    def __del__(self):
+        if getattr(self, 'cache', None) is not None:
+            self.cache.close()
+
+
+def pack_pool(cand_encs, device, max_sents=None):
+    """list of [S_j, D] encodings (torch / numpy) -> (fp32 CUDA [N, Smax, D] zero padded, int32 lens [N])."""
+    lens = [int(e.shape[0]) for e in cand_encs]
+    smax = max_sents or max(lens)
+    D = int(cand_encs[0].shape[1])
+    host = torch.zeros((len(cand_encs), smax, D), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    for j, e in enumerate(cand_encs):
+        host[j, :lens[j]] = torch.as_tensor(np.asarray(e) if not isinstance(e, Tensor) else e.detach().cpu(),
+                                            dtype=torch.float32)
+    return host.to(device, non_blocking=True), torch.tensor(lens, dtype=torch.int32).to(device, non_blocking=True)
+
+
+def score_pool_tensors(query, cands, cand_lens, diameter=None, model_hparams=None, score_aggregation='l2wasserstein'):
+    """One query against a packed pool held in HOST memory: H2D, score on the GPU, D2H of the scores.
+
+    query [Sq,D] or [1,Sq,D]; cands [N,Sc,D] (zero padded; pin it for full PCIe rate); cand_lens int32 [N].
+    Returns {'scores': float32 CPU [N] (higher == closer: -OT_eps, or max -dist for 'l2max'),
+             'device_scores': the same on the GPU}.  The call returns after the scores have landed on the host.
+    """
+    hp = dict(model_hparams or {})
+    dev = torch.device("cuda", torch.cuda.current_device())
+    q = query if query.dim() == 3 else query[None]
+    q = q.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+    c = cands.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+    c_lens = cand_lens.to(dev, dtype=torch.int32, non_blocking=True)
+    q_lens = torch.tensor([q.shape[1]], dtype=torch.int32, device=dev)
+    if score_aggregation == 'l2max':
+        sims, _idx, _ = l2max_scores(q, q_lens, c, c_lens, broadcast_query=True)
+    else:
+        if diameter is None:
+            diameter = hp.get('geoml_diameter') or bbox_diameter(q, c)
+        eps = epsilon_schedule(diameter, hp.get('geoml_blur', 0.05), hp.get('geoml_scaling', 0.9))
+        sims = -ot_scores(q, q_lens, c, c_lens, eps, temp=hp.get('sent_sm_temp', 1.0), broadcast_query=True)["dual"]
+    host = torch.empty(sims.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(sims, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return {'scores': host, 'device_scores': sims}
+
+
+class AspireModel(SimilarityModel):
+    """otAspire (``aspire_compsci`` / ``aspire_biomed``); ``score_aggregation='l2max'`` gives tsAspire scoring."""
+
+    MODEL_PATHS = {
+        'compsci': 'allenai/aspire-contextualsentence-multim-compsci',
+        'biomed': 'allenai/aspire-contextualsentence-multim-biomed',
+    }
+
+    def __init__(self, score_aggregation='l2wasserstein', model_hparams=None, **kwargs):
+        super(AspireModel, self).__init__(**kwargs)
+        from transformers import AutoTokenizer
+        model_path = AspireModel.MODEL_PATHS[self.name.split('_')[-1]]
+        self.model = AspireConSent(model_path)
+        self.model.eval()
+        self.tokenizer = AutoTokenizer.from_pretrained(model_path)
+        self.score_aggregation = score_aggregation
+        self.model_hparams = dict(model_hparams or {})
+
+    def get_similarity(self, x, y):
+        """-OT_eps between two [S,768] encodings, one pair per call (utils/models.py:190-197)."""
+        x, y = torch.as_tensor(x), torch.as_tensor(y)
+        xt = rep_len_tup(embed=x[None, :].permute(0, 2, 1), abs_lens=[len(x)])
+        yt = rep_len_tup(embed=y[None, :].permute(0, 2, 1), abs_lens=[len(y)])
+        if self.score_aggregation == 'l2max':
+            from .distances import allpair_masked_dist_l2max
+            return allpair_masked_dist_l2max(query=xt, cand=yt, return_pair_sims=True)[0].item()
+        ot_dist = AllPairMaskedWasserstein(self.model_hparams).compute_distance(query=xt, cand=yt).item()
+        return -ot_dist
+
+    def encode(self, batch_papers: List[Dict]):
+        bert_batch, abs_lens, sent_token_idxs = prepare_abstracts(batch_abs=batch_papers,
+                                                                  pt_lm_tokenizer=self.tokenizer)
+        with torch.no_grad():
+            _, batch_reps_sent = self.model.forward(bert_batch=bert_batch, abs_lens=abs_lens,
+                                                    sent_tok_idxs=sent_token_idxs)
+        return [batch_reps_sent[i, :abs_lens[i]] for i in range(len(abs_lens))]
+
+    def score_pool(self, query_enc, cand_encs, diameter=None, return_primal=False):
+        """Similarities (higher == closer) of ONE query against a pool, one launch on the current CUDA device.
+
+        otAspire: -OT_eps (dual), or sum P*(-C) with ``return_primal`` (the caching_score quantity).  The epsilon
+        schedule comes from ``diameter`` if given, else from the bounding box of this call's points
+        (query + zero-padded pool), which is what geomloss sees in caching_score (disent_models.py:274-297).
+        Returns a float32 CPU tensor [N].
+        """
+        dev = torch.device("cuda", torch.cuda.current_device())
+        c, c_lens = pack_pool(cand_encs, dev)
+        q = torch.as_tensor(np.asarray(query_enc) if not isinstance(query_enc, Tensor) else query_enc,
+                            dtype=torch.float32).to(dev)[None].contiguous()
+        q_lens = torch.tensor([q.shape[1]], dtype=torch.int32, device=dev)
+        if self.score_aggregation == 'l2max':
+            best, _idx, _ = l2max_scores(q, q_lens, c, c_lens, broadcast_query=True)
+            return best.cpu()
+        hp = self.model_hparams
+        blur, scaling = hp.get('geoml_blur', 0.05), hp.get('geoml_scaling', 0.9)
+        if diameter is None:
+            diameter = hp.get('geoml_diameter') or bbox_diameter(q, c)
+        eps = epsilon_schedule(diameter, blur, scaling)
+        want = "primal" if return_primal else "dual"
+        res = ot_scores(q, q_lens, c, c_lens, eps, temp=hp.get('sent_sm_temp', 1.0), want=(want,),
+                        broadcast_query=True)
+        return (res[want] if return_primal else -res[want]).cpu()
+
+
+def get_model(model_name, trained_model_path=None) -> SimilarityModel:
+    """Factory (utils/models.py:738-768) for the model names on the fine-grained scoring path."""
+    if model_name in {'aspire_compsci', 'aspire_biomed'}:
+        return AspireModel(name=model_name, encoding_type='sentence')
+    if model_name in {'tsaspire_compsci', 'tsaspire_biomed'}:
+        return AspireModel(name=model_name, encoding_type='sentence', score_aggregation='l2max')
+    raise NotImplementedError(f"No Implementation for model {model_name}")
+
+
+def caching_score(query_encode_ret_dict, cand_encode_ret_dicts, score_agg_type='l2wasserstein',
+                  model_hparams=None):
+    """Batched 1 x B scorer with the calling convention of WordSentAlignBiEnc.caching_score
+    (src/learning/facetid_models/disent_models.py:256-342; sent_loss_prop=1, abs_loss_prop=0).
+
+    :param query_encode_ret_dict: {'sent_reps': np [Sq,D], 'doc_cls_reps': np [D]}
+    :param cand_encode_ret_dicts: list of such dicts
+    :return: {'batch_scores': np [B], 'pair_scores': list of un-padded per-pair outputs}
+        l2wasserstein -> pair_scores[i] = [alpha[:ql], beta[:cl], -C[:ql,:cl], plan[:ql,:cl], plan*-C[:ql,:cl]]
+        l2max         -> pair_scores[i] = -dist[:ql,:cl]
+    """
+    hp = dict(model_hparams or {})
+    dev = torch.device("cuda", torch.cuda.current_device())
+    c, c_lens = pack_pool([d['sent_reps'] for d in cand_encode_ret_dicts], dev)
+    q = torch.as_tensor(np.asarray(query_encode_ret_dict['sent_reps']), dtype=torch.float32).to(dev)[None].contiguous()
+    qn = q.shape[1]
+    q_lens = torch.tensor([qn], dtype=torch.int32, device=dev)
+    lens = c_lens.cpu().tolist()
+    if score_agg_type == 'l2max':
+        best, _idx, sims = l2max_scores(q, q_lens, c, c_lens, broadcast_query=True, want_pair_sims=True)
+        sims = sims.cpu().numpy()
+        return {'batch_scores': best.cpu().numpy(), 'pair_scores': [sims[i, :qn, :n] for i, n in enumerate(lens)]}
+    if score_agg_type != 'l2wasserstein':
+        raise ValueError(f'Unknown aggregation: {score_agg_type}')
+    diameter = hp.get('geoml_diameter') or bbox_diameter(q, c)
+    eps = epsilon_schedule(diameter, hp.get('geoml_blur', 0.05), hp.get('geoml_scaling', 0.9))
+    res = ot_scores(q, q_lens, c, c_lens, eps, temp=hp.get('sent_sm_temp', 1.0), broadcast_query=True,
+                    want=("primal", "alpha", "beta", "neg_cost", "plan", "weighted"))
+    host = {k: v.cpu().numpy() for k, v in res.items()}
+    pairs = [[host["alpha"][i, :qn], host["beta"][i, :n], host["neg_cost"][i, :qn, :n], host["plan"][i, :qn, :n],
+              host["weighted"][i, :qn, :n]] for i, n in enumerate(lens)]
+    return {'batch_scores': host["primal"], 'pair_scores': pairs}

@@ -42,6 +42,8 @@ int asp_version(void);
 const char* asp_last_error(void);
 /* Number of SMs of the current device (used by callers to size persistent grids); <0 on error. */
 int asp_sm_count(void);
+/* Kernels launched by this library since load (all threads); used by bench.py's gpu_launches. */
+long long asp_launch_count(void);
 /* Tuning/testing knobs.  "ot_kernel": 0 auto, 1 force warp-per-pair, 2 force thread-per-pair. */
 int asp_set_option(const char* key, int value);
 

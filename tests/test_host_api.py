@@ -1,0 +1,148 @@
+"""CPU: host-side logic of the drop-in boundary -- batch preparation, API surface, sharding arithmetic."""
+import inspect
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shims
+
+from conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def prep_golden():
+    with open(os.path.join(GOLDEN, "prepare_abstracts.json")) as fh:
+        return json.load(fh)
+
+
+def _batch(prep_golden):
+    from oracle.make_golden import README_ABSTRACTS
+    return README_ABSTRACTS + [prep_golden["long_doc"]]
+
+
+def test_prepare_abstracts_matches_reference_output(prep_golden):
+    from aspire_b200.consent import prepare_abstracts
+    bert_batch, abs_lens, sent_tok_idxs = prepare_abstracts(batch_abs=_batch(prep_golden),
+                                                            pt_lm_tokenizer=ref_shims.ToyTokenizer())
+    assert abs_lens == prep_golden["abs_lens"]
+    assert bert_batch["seq_lens"] == prep_golden["seq_lens"]
+    assert bert_batch["tokid_tt"].tolist() == prep_golden["tokid"]
+    assert bert_batch["seg_tt"].tolist() == prep_golden["seg"]
+    assert bert_batch["attnmask_tt"].tolist() == prep_golden["attn"]
+    assert bert_batch["tokid_tt"].dtype == torch.int64
+    spans = [[[s[0], s[-1] + 1] for s in doc] for doc in sent_tok_idxs]
+    assert spans == prep_golden["spans"]
+    for doc in sent_tok_idxs:
+        for s in doc:
+            assert s == list(range(s[0], s[-1] + 1))  # contiguous
+    # truncation: 500 word-pieces + [CLS]/[SEP]; the crossing sentence is cut, later ones dropped
+    assert max(bert_batch["seq_lens"]) == 502
+    assert abs_lens[2] < 12 and sent_tok_idxs[2][-1][-1] == 500
+
+
+def test_prepare_abstracts_title_fills_budget_asserts():
+    from aspire_b200.consent import prepare_abstracts
+    doc = {"TITLE": "t " * 600, "ABSTRACT": ["never reached"]}
+    with pytest.raises(AssertionError):
+        prepare_abstracts(batch_abs=[doc], pt_lm_tokenizer=ref_shims.ToyTokenizer())
+
+
+def test_spans_from_token_idxs():
+    from aspire_b200.consent import spans_from_token_idxs
+    sp = spans_from_token_idxs([[[3, 4, 5], [6]], [[2, 3]]], 3)
+    assert sp.dtype == torch.int32 and sp.shape == (2, 3, 2)
+    assert sp.tolist() == [[[3, 6], [6, 7], [-1, -1]], [[2, 4], [-1, -1], [-1, -1]]]
+    with pytest.raises(NotImplementedError):
+        spans_from_token_idxs([[[3, 5]]], 1)
+
+
+def test_api_surface_matches_reference_signatures():
+    """Keyword names are part of the API (README.md:88-92, utils/models.py:201-207, notebook cell 14)."""
+    import aspire_b200
+    from aspire_b200 import consent, distances, similarity
+    assert list(inspect.signature(consent.prepare_abstracts).parameters) == ["batch_abs", "pt_lm_tokenizer"]
+    assert list(inspect.signature(consent.prepare_bert_sentences).parameters) == ["batch_doc_sents", "tokenizer"]
+    assert list(inspect.signature(consent.AspireConSent.forward).parameters) == \
+        ["self", "bert_batch", "abs_lens", "sent_tok_idxs"]
+    assert list(inspect.signature(distances.AllPairMaskedWasserstein.compute_distance).parameters) == \
+        ["self", "query", "cand", "return_pair_sims"]
+    assert list(inspect.signature(distances.allpair_masked_dist_l2max).parameters) == \
+        ["query", "cand", "return_pair_sims"]
+    assert distances.rep_len_tup._fields == ("embed", "abs_lens")
+    w = distances.AllPairMaskedWasserstein({})
+    assert (w.geoml_blur, w.geoml_scaling, w.geoml_reach, w.sent_sm_temp) == (0.05, 0.9, None, 1.0)
+    assert set(similarity.SimilarityModel.__abstractmethods__) == {"encode", "get_similarity"}
+    with pytest.raises(NotImplementedError):
+        similarity.get_model("no_such_model")
+    with pytest.raises(AssertionError):
+        type("M", (similarity.SimilarityModel,), {"encode": lambda s, b: None,
+                                                  "get_similarity": lambda s, x, y: 0})(name="m", encoding_type="x")
+    # both import spellings of the reference resolve to the drop-in
+    from examples.ex_aspire_consent import AspireConSent as A1
+    from examples.ex_aspire_consent_multimatch import AllPairMaskedWasserstein as W1
+    assert A1 is consent.AspireConSent and W1 is distances.AllPairMaskedWasserstein
+
+
+def test_epsilon_schedule_equals_oracle():
+    from aspire_b200 import epsilon_schedule
+    from oracle import geomloss_ref as gr
+    for diam, blur, sc in [(43.117, 0.05, 0.9), (166.4, 0.05, 0.9), (12.8, 0.1, 0.9), (52.4, 1.0, 0.8), (0.03, 0.05, 0.9)]:
+        assert epsilon_schedule(diam, blur, sc) == gr.epsilon_schedule(1, diam, blur, sc)
+
+
+def test_faceted_encoding_and_cache(tmp_path):
+    from aspire_b200.similarity import SimilarityModel
+
+    class Dummy(SimilarityModel):
+        def encode(self, batch_papers):
+            return [torch.full((len(p["ABSTRACT"]), 4), float(len(p["TITLE"]))) for p in batch_papers]
+
+        def get_similarity(self, x, y):
+            return -float((x.mean() - y.mean()).abs())
+
+    m = Dummy(name="d", encoding_type="sentence", batch_size=2)
+    enc = torch.arange(12.).view(4, 3)
+    paper = {"FACETS": ["objective_label", "method_label", "result_label", "method_label"]}
+    assert m.get_faceted_encoding(enc, "method", paper).tolist() == enc[[1, 3]].tolist()
+    assert m.get_faceted_encoding(enc, "background", paper).tolist() == enc[[0]].tolist()
+    m2 = Dummy(name="d", encoding_type="sentence-entity")
+    paper2 = dict(paper, ENTITIES=[["a"], ["b", "c"], [], ["d"]])
+    enc2 = torch.arange(8.).view(8, 1)
+    assert m2.get_faceted_encoding(enc2, "method", paper2).view(-1).tolist() == [1., 3., 5., 6., 7.]
+
+    class DS:
+        data = {"p%d" % i: {"TITLE": "t" * (i + 1), "ABSTRACT": ["s"] * (i + 1)} for i in range(5)}
+
+        def get(self, pid):
+            return self.data[pid]
+    fn = str(tmp_path / "enc.npz")
+    m.set_encodings_cache(fn)
+    encs = m.get_encoding(["p0", "p3", "p4"], DS())
+    assert set(encs) == {"p0", "p3", "p4"} and encs["p3"].shape == (4, 4)
+    m.cache.close()
+    m3 = Dummy(name="d", encoding_type="sentence")
+    m3.set_encodings_cache(fn)
+    assert set(m3.cache.keys()) == {"p0", "p3", "p4"}
+    again = m3.get_encoding(["p3"], DS())
+    assert torch.equal(again["p3"], encs["p3"])
+
+
+def test_shard_bounds_cover_pool():
+    from aspire_b200.ranking import shard_bounds
+    for n, w in [(1000000, 8), (1003, 8), (5, 8), (100000, 3)]:
+        cuts = [shard_bounds(n, w, r) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+        sizes = [e - s for s, e in cuts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_merge_order():
+    from aspire_b200.ranking import host_merge
+    s = torch.tensor([[1.0, 3.0, 3.0, -1.0, 2.0, 0.0]])
+    i = torch.tensor([[10, 7, 4, -1, 5, 6]])
+    ms, mi = host_merge(s, i, 3)
+    assert mi.tolist() == [[4, 7, 5]] and ms.tolist() == [[3.0, 3.0, 2.0]]

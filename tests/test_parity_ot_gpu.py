@@ -76,7 +76,7 @@ def test_compute_distance_vs_golden(fn, kernel):
                                                                                return_pair_sims=True)
         np.testing.assert_allclose(alpha.cpu().numpy(), z["alpha"], rtol=2e-4, atol=1e-7)
         np.testing.assert_allclose(beta.cpu().numpy(), z["beta"], rtol=2e-4, atol=1e-7)
-        np.testing.assert_allclose(negc.cpu().numpy(), z["negc"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(negc.cpu().numpy(), z["negc"], rtol=2e-6, atol=2e-5)
         # padding of every per-pair output is exactly zero
         for b, (a_, b_) in enumerate(zip(ql, cl)):
             for t in (negc, plan, weighted):
@@ -152,7 +152,10 @@ def test_broadcast_query_matches_replicated(kernel):
 
 
 def test_kernels_agree_random_ragged():
-    """Property: the two solvers (stabilised warp kernel, shared-exponential thread kernel) agree to 1e-5."""
+    """Property: the two solvers (stabilised warp kernel, shared-exponential thread kernel) agree.
+
+    dual: 2e-5 relative.  primal: the plan exponent (f+g-C)/blur amplifies fp32 rounding of the potentials
+    (ulp(4) = 4.8e-7) by 1/blur, so the bound scales as 2e-5 + 2e-6/blur (2.2e-4 at blur=0.01)."""
     from aspire_b200 import ot_scores, epsilon_schedule, _abi
     g = torch.Generator().manual_seed(11)
     B = 5000
@@ -170,7 +173,8 @@ def test_kernels_agree_random_ragged():
         a, b_ = outs[-2], outs[-1]
         for key in ("dual", "primal"):
             assert torch.isfinite(a[key]).all() and torch.isfinite(b_[key]).all()
-            assert rel_err(a[key].cpu().numpy(), b_[key].cpu().numpy()).max() <= 2e-5, (blur, temp, key)
+            tol = 2e-5 if key == "dual" else 2e-5 + 2e-6 / blur
+            assert rel_err(a[key].cpu().numpy(), b_[key].cpu().numpy()).max() <= tol, (blur, temp, key)
 
 
 def test_config5_variable_length_fixed_50_steps():
