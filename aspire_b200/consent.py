@@ -136,18 +136,45 @@ class AspireConSent(nn.Module):
             doc_cls_reps = doc_cls_reps.unsqueeze(0)
         return doc_cls_reps, sent_reps
 
+    # "bf16x3": fp32-equivalent split-bf16 tensor-core math (default, parity with the reference's fp32 forward);
+    # "bf16": plain bf16 operands (fastest); "hf": run the HF module on the GPU instead of the sm_100a kernels
+    # (library path, kept only as an A/B aid for debugging).
+    encoder_precision = "bf16x3"
+
     def _device(self):
         if not torch.cuda.is_available():
             raise _abi.AspireB200Error("AspireConSent needs a CUDA device; there is no CPU fallback")
-        dev = torch.device("cuda", torch.cuda.current_device())
-        if next(self.bert_encoder.parameters()).device != dev:
-            self.bert_encoder.to(dev)
-        return dev
+        return torch.device("cuda", torch.cuda.current_device())
 
-    def encode_hidden(self, tokid_tt, seg_tt, attnmask_tt):
+    def native_encoder(self):
+        """The repacked weights for ``asp_bert_forward`` (built on first use; call ``reset_native_encoder`` after
+        loading a new state dict)."""
+        dev = self._device()
+        enc = getattr(self, "_native", None)
+        if enc is None or enc.device != dev:
+            from .encoder import B200BertEncoder
+            enc = B200BertEncoder(self.bert_encoder, device=dev)
+            object.__setattr__(self, "_native", enc)
+        return enc
+
+    def reset_native_encoder(self):
+        object.__setattr__(self, "_native", None)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.reset_native_encoder()
+        return super().load_state_dict(*args, **kwargs)
+
+    def encode_hidden(self, tokid_tt, seg_tt, attnmask_tt, seq_lens=None):
         """BERT forward -> last_hidden_state fp32 [B,L,768] on the GPU (K0)."""
-        out = self.bert_encoder(tokid_tt, token_type_ids=seg_tt, attention_mask=attnmask_tt)
-        return out.last_hidden_state.float()
+        if self.encoder_precision == "hf":
+            dev = self._device()
+            if next(self.bert_encoder.parameters()).device != dev:
+                self.bert_encoder.to(dev)
+            out = self.bert_encoder(tokid_tt, token_type_ids=seg_tt, attention_mask=attnmask_tt)
+            return out.last_hidden_state.float()
+        if seq_lens is None:
+            seq_lens = attnmask_tt.sum(dim=1)
+        return self.native_encoder().forward(tokid_tt, seq_lens, type_ids=seg_tt, precision=self.encoder_precision)
 
     def consent_reps_bert(self, bert_batch, batch_senttok_idxs, num_sents):
         out_dev = bert_batch['tokid_tt'].device
@@ -156,7 +183,7 @@ class AspireConSent(nn.Module):
         tokid_tt, seg_tt, attnmask_tt = (bert_batch[k].to(dev, non_blocking=True)
                                          for k in ('tokid_tt', 'seg_tt', 'attnmask_tt'))
         spans = spans_from_token_idxs(batch_senttok_idxs, max_sents).to(dev, non_blocking=True)
-        hidden = self.encode_hidden(tokid_tt, seg_tt, attnmask_tt)
+        hidden = self.encode_hidden(tokid_tt, seg_tt, attnmask_tt, seq_lens=bert_batch.get('seq_lens'))
         doc_cls_reps, sent_reps = span_mean_pool(hidden, spans)
         doc_cls_reps = doc_cls_reps.squeeze()  # reference :76 ([768] when B == 1; forward() re-expands)
         return doc_cls_reps.to(out_dev), sent_reps.to(out_dev)

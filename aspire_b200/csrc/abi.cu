@@ -33,8 +33,6 @@ int sm_count() {
     return cached;
 }
 
-extern int g_ot_kernel;
-
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

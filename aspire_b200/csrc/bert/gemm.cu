@@ -1,0 +1,263 @@
+// K0 GEMMs: out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias) on the 5th-generation tensor cores.
+//
+// Replaces the nn.Linear calls inside HF BertModel as reached from AspireConSent.consent_reps_bert
+// (examples/ex_aspire_consent.py:72): Q/K/V, attention output, and the two feed-forward projections of each of the
+// 12 layers.  W keeps the PyTorch Linear layout [out_features, in_features], so both operands are K-major.
+//
+// One CTA (128 threads) computes a 128 x BLOCK_N output tile:
+//   * warp 0 / lane 0  -- TMA producer: cp.async.bulk.tensor 128x64 (A) and BLOCK_Nx64 (W) bf16 boxes, 128B swizzle,
+//                         into a STAGES-deep shared-memory ring, completion on mbarriers (expect_tx);
+//   * warp 1 / lane 0  -- MMA issuer: 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16) per stage,
+//                         fp32 accumulator in TMEM; tcgen05.commit releases the stage and finally signals the epilogue;
+//   * warp 2           -- allocates / frees the TMEM columns;
+//   * all 4 warps      -- epilogue: tcgen05.ld (32 lanes x 32 columns per warp), bias / GELU / residual, stores.
+// Two CTAs are resident per SM (3 stages x 32 KB each), so one tile's epilogue overlaps the other's main loop.
+//
+// fp32-equivalent mode ("bf16x3"): every fp32 operand x is carried as hi = bf16(x), lo = bf16(x - hi); the main loop
+// then runs three passes per K block into the SAME accumulator: hi.hi + hi.lo + lo.hi (the lo.lo term is below fp32
+// resolution).  The producer simply picks the tensor map of the pass; nothing else changes.
+#include "../common.cuh"
+#include "tc05.cuh"
+
+namespace asp {
+
+using namespace tc;
+
+enum { EPI_BF16 = 0, EPI_GELU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32 = 3 };
+
+struct GemmArgs {
+    int M, N, K, nterms;
+    const float* bias;
+    const float* residual;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    float* out_f32;
+};
+
+constexpr int kGemmStages = 3;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+
+template <int BLOCK_N>
+struct GemmSmem {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kBarOff = kGemmStages * kStage;
+    static constexpr int kTotal = kBarOff + 128 + 1024;  // barriers + slack for the 1024-byte alignment
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(128)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
+               const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo, const GemmArgs g) {
+    using S = GemmSmem<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+    uint64_t* empty = full + kGemmStages;
+    uint64_t* accum = empty + kGemmStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kBlockM, n0 = blockIdx.x * BLOCK_N;
+    const int total = (g.K / kBlockK) * g.nterms;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&ta_hi);
+        tma_prefetch_desc(&tb_hi);
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, BLOCK_N);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        for (int it = 0; it < total; ++it) {
+            const int s = it % kGemmStages, ph = (it / kGemmStages) & 1;
+            const int kb = it / g.nterms, term = it - kb * g.nterms;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], S::kStage);
+            uint8_t* sa = smem + s * S::kStage;
+            tma_load_2d(sa, term == 2 ? &ta_lo : &ta_hi, &full[s], kb * kBlockK, m0);
+            tma_load_2d(sa + S::kABytes, term == 1 ? &tb_lo : &tb_hi, &full[s], kb * kBlockK, n0);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+        for (int it = 0; it < total; ++it) {
+            const int s = it % kGemmStages, ph = (it / kGemmStages) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after_sync();
+            const uint32_t sa = smem_u32(smem + s * S::kStage);
+            const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + S::kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)  // 16 bf16 = 32 bytes = +2 in the (>>4) start-address field
+                umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            umma_commit(&empty[s]);
+        }
+        umma_commit(accum);
+    }
+    __syncwarp();
+
+    // ---------------- epilogue (all warps): TMEM lane = tile row, TMEM column = tile column ----------------
+    mbar_wait(accum, 0);
+    tc_fence_after_sync();
+    const int row = m0 + warp * 32 + lane;
+    const bool row_ok = row < g.M;
+    const size_t row_off = (size_t)row * g.N + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        if (g.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c0 + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+        }
+        if (row_ok) {  // no early 'continue': every lane must reach the next tcgen05.ld converged
+        if (EPI == EPI_GELU_BF16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+            float4* o = reinterpret_cast<float4*>(g.out_f32 + row_off + c0);
+            const float4* r = (EPI == EPI_RESID_F32) ? reinterpret_cast<const float4*>(g.residual + row_off + c0) : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if (EPI == EPI_RESID_F32) {
+                    const float4 rr = __ldg(r + i / 4);
+                    x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                }
+                o[i / 4] = x;
+            }
+        } else {
+            uint4* oh = reinterpret_cast<uint4*>(g.out_hi + row_off + c0);
+            uint4* ol = g.out_lo ? reinterpret_cast<uint4*>(g.out_lo + row_off + c0) : nullptr;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                __nv_bfloat162 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = v[i + 2 * j], b = v[i + 2 * j + 1];
+                    h[j] = __floats2bfloat162_rn(a, b);
+                    l[j] = __floats2bfloat162_rn(a - __low2float(h[j]), b - __high2float(h[j]));
+                }
+                oh[i / 8] = *reinterpret_cast<uint4*>(h);
+                if (ol) ol[i / 8] = *reinterpret_cast<uint4*>(l);
+            }
+        }
+        }
+        __syncwarp();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Row-major bf16 matrix [rows, cols] (cols contiguous) -> tensor map with a [box_rows x 64] box and 128B swizzle.
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ASP_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with code %d (ptr %p rows %llu cols %llu)", (int)r, ptr,
+                  (unsigned long long)rows, (unsigned long long)cols);
+        return ASP_ERR_CUDA;
+    }
+    return ASP_OK;
+}
+
+template <int BLOCK_N, int EPI>
+static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
+                       const GemmArgs& g, cudaStream_t stream) {
+    using S = GemmSmem<BLOCK_N>;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        ASP_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        attr_dev = dev;
+    }
+    dim3 grid(g.N / BLOCK_N, (g.M + kBlockM - 1) / kBlockM);
+    gemm_tn_kernel<BLOCK_N, EPI><<<grid, 128, S::kTotal, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
+    ASP_LAUNCH_CHECK("gemm_tn_kernel");
+    return ASP_OK;
+}
+
+int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                 const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo, float* out_f32,
+                 cudaStream_t stream) {
+    constexpr int BN = 128;
+    ASP_REQUIRE(a_hi && w_hi, "gemm: NULL operand");
+    ASP_REQUIRE(M >= 1 && N >= BN && (N % BN) == 0 && K >= kBlockK && (K % kBlockK) == 0,
+                "gemm: need N %% %d == 0 and K %% %d == 0 (got M=%d N=%d K=%d)", BN, kBlockK, M, N, K);
+    ASP_REQUIRE((a_lo == nullptr) == (w_lo == nullptr), "gemm: give both lo operands (bf16x3) or neither (bf16)");
+    ASP_REQUIRE(aligned16(a_hi) && aligned16(w_hi) && aligned16(a_lo) && aligned16(w_lo), "gemm: operands must be 16-byte aligned");
+    if (epilogue == EPI_RESID_F32) ASP_REQUIRE(residual && out_f32, "gemm: residual epilogue needs residual and out_f32");
+    if (epilogue == EPI_F32) ASP_REQUIRE(out_f32, "gemm: fp32 epilogue needs out_f32");
+    if (epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16) ASP_REQUIRE(out_hi, "gemm: bf16 epilogue needs out_hi");
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    int rc;
+    if ((rc = make_tmap_bf16(&ta_hi, a_hi, M, K, kBlockM))) return rc;
+    if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, BN))) return rc;
+    if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;
+    if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, BN))) return rc;
+    GemmArgs g{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32};
+    switch (epilogue) {
+        case EPI_BF16: return launch_gemm<BN, EPI_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_GELU_BF16: return launch_gemm<BN, EPI_GELU_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_RESID_F32: return launch_gemm<BN, EPI_RESID_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_F32: return launch_gemm<BN, EPI_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+    }
+    set_error("gemm: unknown epilogue %d", epilogue);
+    return ASP_ERR_INVALID;
+}
+
+}  // namespace asp
+
+extern "C" int asp_gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo,
+                                float* out_f32, asp_stream_t stream) {
+    return asp::gemm_bf16_tn(a_hi, a_lo, w_hi, w_lo, bias, residual, M, N, K, epilogue, out_hi, out_lo, out_f32,
+                             (cudaStream_t)stream);
+}

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/aspire_b200.h"
 
 namespace asp {
@@ -35,6 +36,7 @@ void count_launch();  // every kernel launch of this library is counted (asp_lau
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int sm_count();
+extern int g_ot_kernel;  // asp_set_option("ot_kernel")
 
 // Epsilon schedule passed by value in kernel parameter space (uniform, read through the constant bank).
 struct EpsSched {
@@ -46,6 +48,17 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kPadNeg = -1.0e9f;        // pair_distances.py:39 mask constant
 constexpr float kLogZeroWeight = -100000.0f;  // geomloss log_weights() value for zero-mass points
+
+// ---- cross-file launch helpers (q_group = consecutive candidates sharing one query; 1 = paired) ----------
+struct OtOut;
+int check_pair_args(const float* q, const int32_t* q_lens, const float* c, const int32_t* c_lens, int B, int Sq, int Sc,
+                    int D);
+int pair_cost_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens, int B,
+                     int Sq, int Sc, int D, float* cost, cudaStream_t stream);
+int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_group, const int32_t* c_lens, int B, int Sq, int Sc,
+                    const EpsSched& sched, float temp, const OtOut& out, cudaStream_t stream);
+int make_sched(const float* eps_host, int n_eps, EpsSched* s);
+OtOut to_out(const asp_ot_outputs* o);
 
 // ---- device math ------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2(float x) {

@@ -16,13 +16,9 @@
 //   sinkhorn_thread_kernel -- one THREAD per pair for small tiles (Sq,Sc <= TS): the whole cost tile and
 //                             both potentials live in registers, one shared exponential per (i,j) and
 //                             step feeds both half-updates, no shuffles / shared memory in the loop.
-#include "common.cuh"
+#include "ot_pair.cuh"
 
 namespace asp {
-
-struct OtOut {
-    float *dual, *primal, *f, *g, *alpha, *beta, *neg_cost, *plan, *weighted;
-};
 
 // ---------------------------------------------------------------------------------------------------
 // Generic warp-per-pair kernel.  Shared memory per warp: C tile [Sq][ldc] + hf[Sq] + hg[Sc] + la[Sq] + lb[Sc].
@@ -31,7 +27,7 @@ struct OtOut {
 // ---------------------------------------------------------------------------------------------------
 template <int RPL>  // rows (and columns) per lane: S <= 32*RPL
 __global__ void __launch_bounds__(128)
-sinkhorn_warp_kernel(const float* __restrict__ cost, const int32_t* __restrict__ q_lens, int q_broadcast,
+sinkhorn_warp_kernel(const float* __restrict__ cost, const int32_t* __restrict__ q_lens, int q_group,
                      const int32_t* __restrict__ c_lens, int B, int Sq, int Sc, const EpsSched sched,
                      float inv_temp, OtOut out) {
     extern __shared__ float smem[];
@@ -45,7 +41,7 @@ sinkhorn_warp_kernel(const float* __restrict__ cost, const int32_t* __restrict__
     float* lb = la + Sq;        // log2(beta_j)
 
     for (int b = blockIdx.x * nwarps + warp; b < B; b += gridDim.x * nwarps) {
-        const int ql = min(max(q_lens[q_broadcast ? 0 : b], 0), Sq), cl = min(max(c_lens[b], 0), Sc);
+        const int ql = min(max(q_lens[b / q_group], 0), Sq), cl = min(max(c_lens[b], 0), Sc);
         const float* Cg = cost + (size_t)b * Sq * Sc;
         __syncwarp();
         for (int e = lane; e < ql * cl; e += 32) {
@@ -221,210 +217,22 @@ sinkhorn_warp_kernel(const float* __restrict__ cost, const int32_t* __restrict__
 }
 
 
-// ---------------------------------------------------------------------------------------------------
-// Thread-per-pair kernel for small tiles (Sq <= TQ, Sc <= TC).
-//
-// State per thread: C[TQ][TC], log2 weights, f, g -- all in registers.  One step at epsilon (t = log2e/eps):
-//     u_i = la_i + f_i t,  v_j = lb_j + g_j t,  E_ij = 2^(u_i + v_j - C_ij t)      (ONE exponential per entry)
-//     R_i = sum_j E_ij,    S_j = sum_i E_ij
-//     f~_i = f_i - eps ln2 (log2 R_i - la_i),   g~_j = g_j - eps ln2 (log2 S_j - lb_j)
-// which is algebraically the two geomloss softmins taken from the OLD (f, g); E is the current plan estimate
-// (entries <= ~1 near feasibility), so no max-subtraction is needed.  A row/column whose sum leaves the
-// fp32 range (0, inf, nan) is recomputed with the max-stabilised form, so the result stays defined wherever
-// the reference's is.  init = un-averaged step from f=g=0 at eps[0]; loop = averaged steps; final =
-// un-averaged step at eps[n-1].
-// ---------------------------------------------------------------------------------------------------
-template <int TQ, int TC>
-struct PairState {
-    float C[TQ][TC];
-    float la[TQ], lb[TC], f[TQ], g[TC];
-};
-
-template <int TQ, int TC>
-__device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql, int cl, float eps, float weight) {
-    // weight = 1 (un-averaged) or 0.5 (averaged): new = old - weight * eps ln2 (log2 sum - logw)
-    const float t = kLog2e / eps;
-    const float scale = weight * eps * kLn2;
-    float u[TQ], v[TC], S[TC];
-#pragma unroll
-    for (int i = 0; i < TQ; ++i) u[i] = fmaf(st.f[i], t, st.la[i]);
-#pragma unroll
-    for (int j = 0; j < TC; ++j) {
-        v[j] = fmaf(st.g[j], t, st.lb[j]);
-        S[j] = 0.f;
-    }
-    const float nt = -t;
-    bool bad = false;
-    float fnew[TQ];
-#pragma unroll
-    for (int i = 0; i < TQ; ++i) {
-        float R = 0.f;
-#pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            const float e = ex2(fmaf(st.C[i][j], nt, u[i] + v[j]));
-            R += e;
-            S[j] += e;
-        }
-        const float l = lg2(R);
-        fnew[i] = st.f[i] - scale * (l - st.la[i]);
-        bad |= (i < ql) && !(fabsf(l) < 1e30f);
-    }
-    float gnew[TC];
-#pragma unroll
-    for (int j = 0; j < TC; ++j) {
-        const float l = lg2(S[j]);
-        gnew[j] = st.g[j] - scale * (l - st.lb[j]);
-        bad |= (j < cl) && !(fabsf(l) < 1e30f);
-    }
-    if (__builtin_expect(bad, 0)) {
-        // max-stabilised recomputation of both half-steps from the old potentials (rare).  Padded rows/columns
-        // carry log-weight -1e5 and vanish from every sum, exactly as in the reference.
-#pragma unroll
-        for (int i = 0; i < TQ; ++i) {
-            float m = -INFINITY, s = 0.f;
-#pragma unroll
-            for (int j = 0; j < TC; ++j) m = fmaxf(m, fmaf(st.C[i][j], nt, v[j]));
-#pragma unroll
-            for (int j = 0; j < TC; ++j) s += ex2(fmaf(st.C[i][j], nt, v[j]) - m);
-            const float ft = -eps * kLn2 * (m + lg2(s));
-            fnew[i] = st.f[i] + weight * (ft - st.f[i]);
-        }
-#pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            float m = -INFINITY, s = 0.f;
-#pragma unroll
-            for (int i = 0; i < TQ; ++i) m = fmaxf(m, fmaf(st.C[i][j], nt, u[i]));
-#pragma unroll
-            for (int i = 0; i < TQ; ++i) s += ex2(fmaf(st.C[i][j], nt, u[i]) - m);
-            const float gt = -eps * kLn2 * (m + lg2(s));
-            gnew[j] = st.g[j] + weight * (gt - st.g[j]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < TQ; ++i) st.f[i] = (i < ql) ? fnew[i] : 0.f;
-#pragma unroll
-    for (int j = 0; j < TC; ++j) st.g[j] = (j < cl) ? gnew[j] : 0.f;
-}
-
+// Thread-per-pair kernel for small tiles: the solver itself lives in ot_pair.cuh (shared with ot_fused.cu).
 template <int TQ, int TC>
 __global__ void __launch_bounds__(128)
-sinkhorn_thread_kernel(const float* __restrict__ cost, const int32_t* __restrict__ q_lens, int q_broadcast,
+sinkhorn_thread_kernel(const float* __restrict__ cost, const int32_t* __restrict__ q_lens, int q_group,
                        const int32_t* __restrict__ c_lens, int B, int Sq, int Sc, const EpsSched sched,
                        float inv_temp, OtOut out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const int ql = min(max(q_lens[q_broadcast ? 0 : b], 0), Sq), cl = min(max(c_lens[b], 0), Sc);
-    PairState<TQ, TC> st;
+    const int ql = min(max(q_lens[b / q_group], 0), Sq), cl = min(max(c_lens[b], 0), Sc);
     const float* Cg = cost + (size_t)b * Sq * Sc;
-    const float kBig = 1.0e30f;
-#pragma unroll
-    for (int i = 0; i < TQ; ++i)
-#pragma unroll
-        for (int j = 0; j < TC; ++j) st.C[i][j] = (i < ql && j < cl) ? Cg[i * Sc + j] : kBig;
-
-    // marginals: log_softmax over valid sentences of (-min dist)/T, exp, then log again as geomloss does
-    float alpha[TQ], beta[TC];
-    {
-        float x[TQ], mx = -INFINITY, s = 0.f;
-#pragma unroll
-        for (int i = 0; i < TQ; ++i) {
-            float best = kBig;
-#pragma unroll
-            for (int j = 0; j < TC; ++j) best = fminf(best, st.C[i][j]);
-            x[i] = -best * inv_temp;
-            if (i < ql) mx = fmaxf(mx, x[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < TQ; ++i) s += (i < ql) ? expf(x[i] - mx) : 0.f;
-        const float lse = mx + logf(s);
-#pragma unroll
-        for (int i = 0; i < TQ; ++i) {
-            alpha[i] = (i < ql) ? expf(x[i] - lse) : 0.f;
-            st.la[i] = (alpha[i] > 0.f) ? log2f(alpha[i]) : kLogZeroWeight * kLog2e;
-        }
-    }
-    {
-        float x[TC], mx = -INFINITY, s = 0.f;
-#pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            float best = kBig;
-#pragma unroll
-            for (int i = 0; i < TQ; ++i) best = fminf(best, st.C[i][j]);
-            x[j] = -best * inv_temp;
-            if (j < cl) mx = fmaxf(mx, x[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < TC; ++j) s += (j < cl) ? expf(x[j] - mx) : 0.f;
-        const float lse = mx + logf(s);
-#pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            beta[j] = (j < cl) ? expf(x[j] - lse) : 0.f;
-            st.lb[j] = (beta[j] > 0.f) ? log2f(beta[j]) : kLogZeroWeight * kLog2e;
-        }
-    }
-    // padded entries: any finite cost works (their weight is 2^-144269 = 0); keep them small and finite
-#pragma unroll
-    for (int i = 0; i < TQ; ++i)
-#pragma unroll
-        for (int j = 0; j < TC; ++j)
-            if (!(i < ql && j < cl)) st.C[i][j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < TQ; ++i) st.f[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < TC; ++j) st.g[j] = 0.f;
-
-    if (ql > 0 && cl > 0) {
-        sinkhorn_step<TQ, TC>(st, ql, cl, sched.eps[0], 1.0f);
-#pragma unroll 1
-        for (int k = 0; k < sched.n; ++k) sinkhorn_step<TQ, TC>(st, ql, cl, sched.eps[k], 0.5f);
-        sinkhorn_step<TQ, TC>(st, ql, cl, sched.eps[sched.n - 1], 1.0f);
-    }
-
-    float dual = 0.f;
-#pragma unroll
-    for (int i = 0; i < TQ; ++i) dual = fmaf(alpha[i], st.f[i], dual);
-#pragma unroll
-    for (int j = 0; j < TC; ++j) dual = fmaf(beta[j], st.g[j], dual);
-    if (out.dual) out.dual[b] = dual;
-#pragma unroll
-    for (int i = 0; i < TQ; ++i)
-        if (i < Sq) {
-            if (out.f) out.f[(size_t)b * Sq + i] = st.f[i];
-            if (out.alpha) out.alpha[(size_t)b * Sq + i] = alpha[i];
-        }
-#pragma unroll
-    for (int j = 0; j < TC; ++j)
-        if (j < Sc) {
-            if (out.g) out.g[(size_t)b * Sc + j] = st.g[j];
-            if (out.beta) out.beta[(size_t)b * Sc + j] = beta[j];
-        }
-    if (out.primal || out.plan || out.weighted || out.neg_cost) {
-        const float tf = kLog2e / sched.eps[sched.n - 1];
-        float primal = 0.f;
-#pragma unroll
-        for (int i = 0; i < TQ; ++i)
-#pragma unroll
-            for (int j = 0; j < TC; ++j) {
-                if (i < Sq && j < Sc) {
-                    const bool valid = (i < ql && j < cl);
-                    const float cij = st.C[i][j];
-                    const float p = valid ? ex2((st.f[i] + st.g[j] - cij) * tf) * (alpha[i] * beta[j]) : 0.f;
-                    const float negc = valid ? -cij : 0.f;
-                    const float w = p * negc;
-                    primal += w;
-                    const size_t o = (size_t)b * Sq * Sc + i * Sc + j;
-                    if (out.neg_cost) out.neg_cost[o] = negc;
-                    if (out.plan) out.plan[o] = p;
-                    if (out.weighted) out.weighted[o] = w;
-                }
-            }
-        if (out.primal) out.primal[b] = primal;
-    }
+    solve_pair_thread<TQ, TC>([&](int i, int j) { return Cg[i * Sc + j]; }, ql, cl, b, Sq, Sc, sched, inv_temp, out);
 }
 
 int g_ot_kernel = 0;  // 0 auto, 1 force warp-per-pair, 2 force thread-per-pair (asp_set_option "ot_kernel")
 
-static int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_broadcast, const int32_t* c_lens, int B,
+int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_group, const int32_t* c_lens, int B,
                            int Sq, int Sc, const EpsSched& sched, float temp, const OtOut& out, cudaStream_t stream) {
     const int smax = Sq > Sc ? Sq : Sc;
     const bool thread_ok = (Sq <= 10 && Sc <= 10);
@@ -435,7 +243,7 @@ static int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_broad
     // one thread per pair only pays once there are enough pairs to fill the machine
     if (thread_ok && (g_ot_kernel == 2 || (g_ot_kernel == 0 && B >= 64 * sm_count()))) {
         const int threads = 128, blocks = (B + threads - 1) / threads;
-        sinkhorn_thread_kernel<10, 10><<<blocks, threads, 0, stream>>>(cost, q_lens, q_broadcast, c_lens, B, Sq, Sc,
+        sinkhorn_thread_kernel<10, 10><<<blocks, threads, 0, stream>>>(cost, q_lens, q_group, c_lens, B, Sq, Sc,
                                                                      sched, 1.0f / temp, out);
         ASP_LAUNCH_CHECK("sinkhorn_thread_kernel");
         return ASP_OK;
@@ -451,7 +259,7 @@ static int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_broad
         if (smem > 48 * 1024)                                                                                    \
             ASP_CUDA(cudaFuncSetAttribute(sinkhorn_warp_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                           smem));                                                                \
-        sinkhorn_warp_kernel<RPL><<<blocks, warps * 32, smem, stream>>>(cost, q_lens, q_broadcast, c_lens, B, Sq, \
+        sinkhorn_warp_kernel<RPL><<<blocks, warps * 32, smem, stream>>>(cost, q_lens, q_group, c_lens, B, Sq,   \
                                                                         Sc, sched, inv_temp, out);               \
     } while (0)
     if (smax <= 32) ASP_LAUNCH_WARP(1);
@@ -462,7 +270,7 @@ static int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_broad
     return ASP_OK;
 }
 
-static int make_sched(const float* eps_host, int n_eps, EpsSched* s) {
+int make_sched(const float* eps_host, int n_eps, EpsSched* s) {
     ASP_REQUIRE(eps_host && n_eps >= 1, "ot: eps schedule missing");
     if (n_eps > ASP_MAX_EPS) {
         set_error("ot: schedule of %d entries exceeds ASP_MAX_EPS=%d", n_eps, ASP_MAX_EPS);
@@ -476,7 +284,7 @@ static int make_sched(const float* eps_host, int n_eps, EpsSched* s) {
     return ASP_OK;
 }
 
-static OtOut to_out(const asp_ot_outputs* o) {
+OtOut to_out(const asp_ot_outputs* o) {
     OtOut r{o->dual, o->primal, o->f, o->g, o->alpha, o->beta, o->neg_cost, o->plan, o->weighted};
     return r;
 }
@@ -497,6 +305,6 @@ extern "C" int asp_ot_sinkhorn_from_cost(const float* cost, const int32_t* q_len
     int rc = asp::make_sched(eps_host, n_eps, &sched);
     if (rc) return rc;
     if (B == 0) return ASP_OK;
-    return asp::launch_sinkhorn(cost, q_lens, q_broadcast, c_lens, B, Sq, Sc, sched, temp, asp::to_out(out),
+    return asp::launch_sinkhorn(cost, q_lens, q_broadcast ? B : 1, c_lens, B, Sq, Sc, sched, temp, asp::to_out(out),
                                 (cudaStream_t)stream);
 }

@@ -6,69 +6,9 @@
 // partial squared norms, and a transpose-reduce over the warp (NV-ish shuffles instead of 5*NV) leaves
 // each finished sum in exactly one lane.  Reference arithmetic replaced: torch.cdist
 // (pair_distances.py:49-50,167) / geomloss distances() = sqrt(clamp_min(|x|^2-2x.y+|y|^2, 1e-8)).
-#include "common.cuh"
+#include "gram.cuh"
 
 namespace asp {
-
-template <int TI, int TJ>
-struct GramTile {
-    static constexpr int kEntries = TI * TJ;
-    static constexpr int kVals = kEntries + TI + TJ;           // dots, |q_i|^2, |c_j|^2
-    static constexpr int NV = ((kVals + 31) / 32) * 32;        // padded for the transpose-reduce
-};
-
-__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
-    acc = fmaf(a.x, b.x, acc);
-    acc = fmaf(a.y, b.y, acc);
-    acc = fmaf(a.z, b.z, acc);
-    acc = fmaf(a.w, b.w, acc);
-    return acc;
-}
-
-// Accumulate this lane's share (k = 4*lane + 128*m) of a TI x TJ tile.
-template <int TI, int TJ>
-__device__ __forceinline__ void gram_accumulate(const float* __restrict__ q, int nq, const float* __restrict__ c,
-                                                int nc, int D, int lane, float (&v)[GramTile<TI, TJ>::NV]) {
-    using T = GramTile<TI, TJ>;
-    const int d4 = D >> 2;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k4 = lane; k4 < d4; k4 += 32) {
-        float4 cv[TJ];
-#pragma unroll
-        for (int j = 0; j < TJ; ++j)
-            cv[j] = (j < nc) ? ldg_stream(reinterpret_cast<const float4*>(c + (size_t)j * D) + k4) : zero4;
-#pragma unroll
-        for (int i = 0; i < TI; ++i) {
-            const float4 qv = (i < nq) ? __ldg(reinterpret_cast<const float4*>(q + (size_t)i * D) + k4) : zero4;
-#pragma unroll
-            for (int j = 0; j < TJ; ++j) v[i * TJ + j] = dot4(qv, cv[j], v[i * TJ + j]);
-            v[T::kEntries + i] = dot4(qv, qv, v[T::kEntries + i]);
-        }
-#pragma unroll
-        for (int j = 0; j < TJ; ++j) v[T::kEntries + TI + j] = dot4(cv[j], cv[j], v[T::kEntries + TI + j]);
-    }
-}
-
-// Sum v[] over the 32 lanes.  After the call lane l holds, in v[m], the total of original slot
-// 32*m + bitrev5(l).  Cost: NV*(1/2+1/4+...) ~ NV shuffles.
-template <int NV>
-__device__ __forceinline__ void transpose_reduce(float (&v)[NV], int lane) {
-    int n = NV;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        const bool upper = (lane & s) != 0;
-        n >>= 1;
-#pragma unroll
-        for (int m = 0; m < NV / 2; ++m) {
-            if (m < n) {
-                const float a = v[2 * m], b = v[2 * m + 1];
-                const float send = upper ? a : b;
-                const float keep = upper ? b : a;
-                v[m] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-            }
-        }
-    }
-}
 
 enum { MODE_COST = 0, MODE_L2MAX = 1 };
 
@@ -91,7 +31,7 @@ __device__ __forceinline__ void gram_tile_to_smem(const float* q, int nq, const 
 
 template <int TI, int TJ, int MODE, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-pair_cost_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_lens, int q_broadcast,
+pair_cost_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_lens, int q_group,
                  const float* __restrict__ c, const int32_t* __restrict__ c_lens, int B, int Sq, int Sc, int D,
                  float* __restrict__ cost, float* __restrict__ best, int32_t* __restrict__ flat_idx) {
     using T = GramTile<TI, TJ>;
@@ -99,7 +39,7 @@ pair_cost_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_lens
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* red = red_all[warp];
     for (int b = blockIdx.x * WARPS + warp; b < B; b += gridDim.x * WARPS) {
-        const int qb = q_broadcast ? 0 : b;
+        const int qb = b / q_group;
         const int ql = min(max(q_lens[qb], 0), Sq), cl = min(max(c_lens[b], 0), Sc);
         const float* qbase = q + (size_t)qb * Sq * D;
         const float* cbase = c + (size_t)b * Sc * D;
@@ -160,29 +100,34 @@ pair_cost_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_lens
 }
 
 template <int MODE>
-static int launch_pair_cost(const float* q, const int32_t* q_lens, int q_broadcast, const float* c,
+int launch_pair_cost(const float* q, const int32_t* q_lens, int q_group, const float* c,
                             const int32_t* c_lens, int B, int Sq, int Sc, int D, float* cost, float* best,
                             int32_t* flat_idx, cudaStream_t stream) {
     constexpr int WARPS = 4;
     const int blocks = (B + WARPS - 1) / WARPS;
     if (Sq <= 10 && Sc <= 10) {
-        pair_cost_kernel<10, 10, MODE, WARPS><<<blocks, WARPS * 32, 0, stream>>>(q, q_lens, q_broadcast, c, c_lens,
+        pair_cost_kernel<10, 10, MODE, WARPS><<<blocks, WARPS * 32, 0, stream>>>(q, q_lens, q_group, c, c_lens,
                                                                               B, Sq, Sc, D, cost, best, flat_idx);
     } else {
-        pair_cost_kernel<8, 8, MODE, WARPS><<<blocks, WARPS * 32, 0, stream>>>(q, q_lens, q_broadcast, c, c_lens, B,
+        pair_cost_kernel<8, 8, MODE, WARPS><<<blocks, WARPS * 32, 0, stream>>>(q, q_lens, q_group, c, c_lens, B,
                                                                             Sq, Sc, D, cost, best, flat_idx);
     }
     ASP_LAUNCH_CHECK("pair_cost_kernel");
     return ASP_OK;
 }
 
-static int check_pair_args(const float* q, const int32_t* q_lens, const float* c, const int32_t* c_lens, int B,
+int check_pair_args(const float* q, const int32_t* q_lens, const float* c, const int32_t* c_lens, int B,
                            int Sq, int Sc, int D) {
     ASP_REQUIRE(q && c && q_lens && c_lens, "pair kernels: NULL input pointer");
     ASP_REQUIRE(B >= 0 && Sq >= 1 && Sc >= 1, "pair kernels: bad shape B=%d Sq=%d Sc=%d", B, Sq, Sc);
     ASP_REQUIRE(D >= 4 && (D % 4) == 0, "pair kernels: D=%d must be a positive multiple of 4", D);
     ASP_REQUIRE(aligned16(q) && aligned16(c), "pair kernels: q/c must be 16-byte aligned");
     return ASP_OK;
+}
+
+int pair_cost_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens, int B,
+                     int Sq, int Sc, int D, float* cost, cudaStream_t stream) {
+    return launch_pair_cost<MODE_COST>(q, q_lens, q_group, c, c_lens, B, Sq, Sc, D, cost, nullptr, nullptr, stream);
 }
 
 }  // namespace asp
@@ -194,7 +139,7 @@ extern "C" int asp_pair_cost(const float* q, const int32_t* q_lens, int q_broadc
     if (rc) return rc;
     ASP_REQUIRE(cost, "asp_pair_cost: cost is NULL");
     if (B == 0) return ASP_OK;
-    return asp::launch_pair_cost<asp::MODE_COST>(q, q_lens, q_broadcast, c, c_lens, B, Sq, Sc, D, cost, nullptr,
+    return asp::launch_pair_cost<asp::MODE_COST>(q, q_lens, q_broadcast ? B : 1, c, c_lens, B, Sq, Sc, D, cost, nullptr,
                                                  nullptr, (cudaStream_t)stream);
 }
 
@@ -205,6 +150,6 @@ extern "C" int asp_l2max(const float* q, const int32_t* q_lens, int q_broadcast,
     if (rc) return rc;
     ASP_REQUIRE(best, "asp_l2max: best is NULL");
     if (B == 0) return ASP_OK;
-    return asp::launch_pair_cost<asp::MODE_L2MAX>(q, q_lens, q_broadcast, c, c_lens, B, Sq, Sc, D, pair_sims, best,
+    return asp::launch_pair_cost<asp::MODE_L2MAX>(q, q_lens, q_broadcast ? B : 1, c, c_lens, B, Sq, Sc, D, pair_sims, best,
                                                   flat_idx, (cudaStream_t)stream);
 }

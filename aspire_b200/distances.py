@@ -67,33 +67,40 @@ def bbox_diameter(x_rows, y_rows):
 _OT_FIELDS = ("dual", "primal", "f", "g", "alpha", "beta", "neg_cost", "plan", "weighted")
 
 
-def ot_scores(q, q_lens, c, c_lens, eps_list, temp=1.0, want=("dual",), broadcast_query=False, cost_workspace=None):
-    """Masked Sinkhorn OT on contiguous fp32 CUDA tensors.
+def ot_scores(q, q_lens, c, c_lens, eps_list, temp=1.0, want=("dual",), broadcast_query=False, cost_workspace=None,
+              q_group=None, out=None):
+    """Masked Sinkhorn OT on contiguous fp32 CUDA tensors through the fused entry point ``asp_ot_score``.
 
-    q [B,Sq,D] (or [1,Sq,D] with ``broadcast_query``), c [B,Sc,D]; lens int32 CUDA tensors.
-    ``eps_list``: the epsilon schedule (python floats / float64).  Returns a dict of the requested outputs.
+    c [B,Sc,D]; q [B,Sq,D] (paired, default), [1,Sq,D] with ``broadcast_query``, or [ceil(B/q_group),Sq,D] with
+    ``q_group`` = number of consecutive candidates sharing one query (several query pools in one launch).
+    lens: int32 CUDA tensors.  ``eps_list``: the epsilon schedule (python floats / float64).
+    ``out``: optional dict of preallocated output tensors (reused across calls).  Returns a dict of outputs.
     """
     _abi.require_cuda(q, c, q_lens, c_lens)
     B, Sc, D = c.shape
     Sq = q.shape[1]
-    if broadcast_query:
-        assert q.shape[0] == 1
-    else:
-        assert q.shape[0] == B
+    if q_group is None:
+        q_group = max(B, 1) if broadcast_query else 1
+    assert q_group >= 1 and q.shape[0] == max(-(-B // q_group), 1 if broadcast_query else 0), \
+        "query batch does not match candidates / q_group"
+    assert q_lens.numel() == q.shape[0] and c_lens.numel() == B
     assert q.is_contiguous() and c.is_contiguous() and q.dtype == c.dtype == torch.float32
     dev = c.device
     shapes = {"dual": (B,), "primal": (B,), "f": (B, Sq), "g": (B, Sc), "alpha": (B, Sq), "beta": (B, Sc),
               "neg_cost": (B, Sq, Sc), "plan": (B, Sq, Sc), "weighted": (B, Sq, Sc)}
-    res = {k: torch.empty(shapes[k], dtype=torch.float32, device=dev) for k in want}
+    res = {k: (out[k] if out is not None and k in out else torch.empty(shapes[k], dtype=torch.float32, device=dev))
+           for k in want}
     outs = _abi.AspOtOutputs(**{k: (res[k].data_ptr() if k in res else None) for k in _OT_FIELDS})
-    if cost_workspace is None:
-        cost_workspace = torch.empty((B, Sq, Sc), dtype=torch.float32, device=dev)
-    eps32 = np.asarray(eps_list, dtype=np.float32)
     L = _abi.lib()
-    _abi.check(L.asp_ot_sinkhorn(_abi.ptr(q), _abi.ptr(q_lens), int(broadcast_query), _abi.ptr(c), _abi.ptr(c_lens),
-                                 B, Sq, Sc, D, eps32.ctypes.data_as(_abi.c_float_p), len(eps32), float(temp),
-                                 _abi.ptr(cost_workspace), ctypes.byref(outs), _abi.stream_of(dev)),
-               "asp_ot_sinkhorn")
+    need = int(L.asp_ot_score_workspace_bytes(B, Sq, Sc, D))
+    if need and (cost_workspace is None or cost_workspace.numel() * cost_workspace.element_size() < need):
+        cost_workspace = torch.empty(need // 4, dtype=torch.float32, device=dev)
+    ws_bytes = 0 if cost_workspace is None else cost_workspace.numel() * cost_workspace.element_size()
+    eps32 = np.asarray(eps_list, dtype=np.float32)
+    _abi.check(L.asp_ot_score(_abi.ptr(q), _abi.ptr(q_lens), int(q_group), _abi.ptr(c), _abi.ptr(c_lens),
+                              B, Sq, Sc, D, eps32.ctypes.data_as(_abi.c_float_p), len(eps32), float(temp),
+                              ctypes.byref(outs), _abi.ptr(cost_workspace), ws_bytes, _abi.stream_of(dev)),
+               "asp_ot_score")
     return res
 
 

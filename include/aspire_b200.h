@@ -44,7 +44,7 @@ const char* asp_last_error(void);
 int asp_sm_count(void);
 /* Kernels launched by this library since load (all threads); used by bench.py's gpu_launches. */
 long long asp_launch_count(void);
-/* Tuning/testing knobs.  "ot_kernel": 0 auto, 1 force warp-per-pair, 2 force thread-per-pair. */
+/* Tuning/testing knobs.  "ot_kernel": 0 auto, 1 force warp-per-pair (never fuse), 2 force thread-per-pair. */
 int asp_set_option(const char* key, int value);
 
 /* ---- K1: per-sentence token-span mean pooling -------------------------------------------------
@@ -56,6 +56,55 @@ int asp_set_option(const char* key, int value);
  */
 int asp_span_mean_pool(const float* hidden, const int32_t* spans, int B, int L, int D, int Smax,
                        float* sent_reps, float* cls_reps, asp_stream_t stream);
+
+/* ---- K0: tensor-core GEMM of the encoder (tcgen05 / TMEM / TMA) --------------------------------------------
+ * Replaces the nn.Linear layers of HF BertModel as called from AspireConSent.consent_reps_bert
+ * (examples/ex_aspire_consent.py:72).  out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]); A and W are bf16,
+ * row-major with K contiguous (W = the PyTorch Linear weight as stored), fp32 accumulation in TMEM.
+ * a_lo / w_lo: NULL -> plain bf16 operands.  Both given -> "bf16x3": operands are (hi, lo) bf16 pairs of fp32
+ *   values and the kernel accumulates hi.hi + hi.lo + lo.hi (fp32-equivalent products).
+ * epilogue: 0 = bf16 out (out_hi, and out_lo = bf16 of the rounding residual when non-NULL)
+ *           1 = exact-erf GELU, then as 0        2 = + residual[M,N] (fp32) -> out_f32        3 = fp32 -> out_f32
+ * Requirements: N % 128 == 0, K % 64 == 0, 16-byte aligned pointers.
+ */
+int asp_gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                     const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo,
+                     float* out_f32, asp_stream_t stream);
+
+/* ---- K0: BERT-base encoder forward ---------------------------------------------------------------------
+ * Replaces `self.bert_encoder(tokid_tt, token_type_ids=seg_tt, attention_mask=attnmask_tt)` of
+ * AspireConSent.consent_reps_bert (examples/ex_aspire_consent.py:72; = disent_models.py:505) and yields its
+ * `last_hidden_state`.  Architecture = HF BertModel (post-LN, exact-erf GELU, LayerNorm eps from the config).
+ * All weight pointers are DEVICE pointers; the structs themselves live in HOST memory.
+ *   *_hi : bf16 [out,in] = the nn.Linear weight rounded to bf16;  *_lo : bf16 of (weight - hi) or NULL.
+ *   wqkv = rows of query | key | value weights stacked ([3*hidden, hidden]); bqkv likewise.
+ */
+typedef struct asp_bert_layer {
+    const void *wqkv_hi, *wqkv_lo; const float* bqkv;
+    const void *wo_hi, *wo_lo;     const float* bo;
+    const float *ln1_g, *ln1_b;
+    const void *w1_hi, *w1_lo;     const float* b1;
+    const void *w2_hi, *w2_lo;     const float* b2;
+    const float *ln2_g, *ln2_b;
+} asp_bert_layer;
+
+typedef struct asp_bert_weights {
+    int hidden, heads, layers, intermediate, vocab, max_pos;
+    float ln_eps;
+    const float *word_emb, *pos_emb, *type_emb;  /* fp32 [vocab,hidden], [max_pos,hidden], [2,hidden] */
+    const float *emb_ln_g, *emb_ln_b;
+    const asp_bert_layer* layer;                 /* host array of `layers` entries */
+} asp_bert_weights;
+
+/* Bytes of device scratch asp_bert_forward needs for a [B,L] batch. */
+size_t asp_bert_workspace_bytes(const asp_bert_weights* w, int B, int L, int precise);
+/* ids / type_ids (may be NULL = all 0): int32 [B,L] right-padded; seq_lens int32 [B] = number of real tokens
+ * (attention mask = 1 on the first seq_lens[b] positions, as prepare_bert_sentences builds it, :169-173).
+ * precise = 0: bf16 tensor-core operands; 1: bf16x3 split operands (fp32-equivalent, needs the *_lo weights).
+ * hidden_out: fp32 [B,L,hidden] (every position, pads included, like HF). */
+int asp_bert_forward(const asp_bert_weights* w, const int32_t* ids, const int32_t* type_ids, const int32_t* seq_lens,
+                     int B, int L, int precise, float* hidden_out, void* workspace, size_t workspace_bytes,
+                     asp_stream_t stream);
 
 /* ---- K2: pairwise sentence-sentence L2 cost matrix --------------------------------------------
  * Replaces torch.cdist at src/learning/facetid_models/pair_distances.py:49-50,167 and geomloss's
@@ -109,6 +158,21 @@ typedef struct asp_ot_outputs {
 int asp_ot_sinkhorn(const float* q, const int32_t* q_lens, int q_broadcast, const float* c,
                     const int32_t* c_lens, int B, int Sq, int Sc, int D, const float* eps_host, int n_eps,
                     float temp, float* cost_workspace, const asp_ot_outputs* out, asp_stream_t stream);
+
+/* ---- K2+K4 FUSED: otAspire scores straight from the sentence representations (headline entry point) ----
+ * Same arithmetic and outputs as asp_ot_sinkhorn, replacing pair_distances.py:21-92 (+ geomloss) in one
+ * launch; the cost tensor never touches HBM when Sq,Sc <= 10 (asp_ot_score_workspace_bytes() == 0).
+ * q_group: number of CONSECUTIVE candidates that share one query: pair b uses query b / q_group
+ *   (q [ceil(B/q_group),Sq,D], q_lens [ceil(B/q_group)]).  q_group = 1 is the reference's paired call
+ *   (compute_distance, pair_distances.py:46); q_group = B is caching_score's "one query replicated B times"
+ *   (disent_models.py:274-281) without the replication; anything between scores several query pools at once.
+ * workspace: caller-owned device scratch of at least asp_ot_score_workspace_bytes(B,Sq,Sc,D) bytes (may be
+ *   NULL when that is 0).
+ */
+size_t asp_ot_score_workspace_bytes(int B, int Sq, int Sc, int D);
+int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
+                 int B, int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp,
+                 const asp_ot_outputs* out, void* workspace, size_t workspace_bytes, asp_stream_t stream);
 
 /* Same solver on a precomputed cost tensor [B,Sq,Sc] (as written by asp_pair_cost). */
 int asp_ot_sinkhorn_from_cost(const float* cost, const int32_t* q_lens, int q_broadcast, const int32_t* c_lens,

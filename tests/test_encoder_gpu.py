@@ -1,0 +1,82 @@
+"""GPU parity of the sm_100a BERT encoder (asp_bert_forward) and of AspireConSent.forward built on it.
+
+Reference = the plain PyTorch fp32 forward of the same HF ``BertModel`` (what the reference calls at
+examples/ex_aspire_consent.py:72), weights seeded (no checkpoints exist offline).
+Tolerances on last_hidden_state (post-LayerNorm values, O(1)):
+  bf16x3 (default, fp32-equivalent split operands): max |err| <= 2e-4
+  bf16   (plain bf16 tensor-core operands)        : relative L2 error <= 3e-2, cosine >= 0.999
+and on the end-to-end README example against the golden output of the UNMODIFIED reference
+(tests/golden/readme_encoder_2layer.npz): sentence reps <= 2e-4, tsAspire score <= 1e-3 absolute.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shims
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _hf_reference(model, ids, lens):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = model.cuda().float()
+    B, L = ids.shape
+    mask = (torch.arange(L)[None, :] < torch.as_tensor(lens)[:, None]).long().cuda()
+    with torch.no_grad():
+        out = model(ids.cuda(), token_type_ids=torch.zeros_like(ids).cuda(), attention_mask=mask).last_hidden_state
+    return out.float()
+
+
+@pytest.mark.parametrize("layers,B,L,lens", [(2, 3, 70, [70, 33, 5]), (12, 2, 300, [300, 121]), (12, 5, 129, [129, 64, 65, 2, 128])])
+def test_encoder_matches_hf_fp32(layers, B, L, lens):
+    from aspire_b200.encoder import B200BertEncoder
+    model = ref_shims.seeded_bert(seed=3, num_hidden_layers=layers)
+    g = torch.Generator().manual_seed(layers * 100 + L)
+    ids = torch.randint(1000, 31000, (B, L), generator=g)
+    for b, n in enumerate(lens):
+        ids[b, n:] = 0
+    ref = _hf_reference(model, ids, lens)
+    enc = B200BertEncoder(model)
+    valid = (torch.arange(L)[None, :] < torch.tensor(lens)[:, None]).cuda()
+    got = enc.forward(ids, lens, precision="bf16x3")
+    torch.cuda.synchronize()
+    err = (got - ref).abs()
+    assert torch.isfinite(got).all()
+    assert err[valid].max().item() <= 2e-4, f"bf16x3 max err (valid tokens) {err[valid].max().item():.3e}"
+    assert err.max().item() <= 2e-4, f"bf16x3 max err (pad positions too) {err.max().item():.3e}"
+    fast = enc.forward(ids, lens, precision="bf16")
+    torch.cuda.synchronize()
+    rel = ((fast - ref)[valid].norm() / ref[valid].norm()).item()
+    cos = torch.nn.functional.cosine_similarity(fast[valid], ref[valid], dim=-1).min().item()
+    assert rel <= 3e-2 and cos >= 0.999, f"bf16 rel L2 {rel:.3e}, min cosine {cos:.5f}"
+
+
+def test_readme_example_end_to_end_vs_reference_golden():
+    """BASELINE config 1 on the GPU: prepare_abstracts -> AspireConSent.forward -> tsAspire score."""
+    import transformers
+    from oracle.make_golden import README_ABSTRACTS
+    from aspire_b200 import allpair_masked_dist_l2max, rep_len_tup
+    from aspire_b200.consent import AspireConSent, prepare_abstracts
+    z = np.load(os.path.join(GOLDEN, "readme_encoder_2layer.npz"))
+    orig = transformers.AutoModel.from_pretrained
+    transformers.AutoModel.from_pretrained = staticmethod(lambda name, *a, **k: ref_shims.seeded_bert(0, num_hidden_layers=2))
+    try:
+        model = AspireConSent("allenai/aspire-contextualsentence-singlem-compsci")
+    finally:
+        transformers.AutoModel.from_pretrained = orig
+    bb, al, sti = prepare_abstracts(batch_abs=README_ABSTRACTS, pt_lm_tokenizer=ref_shims.ToyTokenizer())
+    with torch.no_grad():
+        cls, reps = model.forward(bert_batch=bb, abs_lens=al, sent_tok_idxs=sti)
+    assert not reps.is_cuda and tuple(reps.shape) == tuple(z["reps"].shape) and tuple(cls.shape) == tuple(z["cls"].shape)
+    assert al == z["abs_lens"].tolist()
+    assert np.abs(reps.numpy() - z["reps"]).max() <= 2e-4
+    assert np.abs(cls.numpy() - z["cls"]).max() <= 2e-4
+    assert (reps[0, al[0]:] == 0).all() and (reps[1, al[1]:] == 0).all()
+    qt = rep_len_tup(embed=reps[0:1].permute(0, 2, 1), abs_lens=[al[0]])
+    ct = rep_len_tup(embed=reps[1:2].permute(0, 2, 1), abs_lens=[al[1]])
+    score, _ = allpair_masked_dist_l2max(query=qt, cand=ct, return_pair_sims=True)
+    assert abs(score.item() - float(z["ts_score"].reshape(-1)[0])) <= 1e-3

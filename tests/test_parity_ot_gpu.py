@@ -151,6 +151,34 @@ def test_broadcast_query_matches_replicated(kernel):
         _abi.set_option("ot_kernel", 0)
 
 
+def test_query_groups_match_per_query_calls():
+    """q_group: several query pools in ONE launch == one broadcast call per query (bit-identical), ragged pools,
+    a last group that is not full, and parity with the oracle."""
+    from aspire_b200 import ot_scores, epsilon_schedule
+    g = torch.Generator().manual_seed(21)
+    NQ, G = 5, 77
+    B = NQ * G - 30  # last query has only 47 candidates
+    q = (0.3 * torch.randn(NQ, 10, 768, generator=g)).cuda()
+    c = (0.3 * torch.randn(B, 10, 768, generator=g)).cuda()
+    ql = torch.randint(1, 11, (NQ,), generator=g).int().cuda()
+    cl = torch.randint(1, 11, (B,), generator=g).int().cuda()
+    eps = epsilon_schedule(60.0, 0.05, 0.9)
+    allq = ot_scores(q, ql, c, cl, eps, want=("dual", "primal"), q_group=G)
+    for i in range(NQ):
+        s, e = i * G, min((i + 1) * G, B)
+        one = ot_scores(q[i:i + 1].contiguous(), ql[i:i + 1].contiguous(), c[s:e].contiguous(), cl[s:e].contiguous(), eps,
+                        want=("dual", "primal"), broadcast_query=True)
+        assert torch.equal(one["dual"], allq["dual"][s:e]) and torch.equal(one["primal"], allq["primal"][s:e])
+    qi = torch.arange(B) // G
+    qc, qlc = q.cpu()[qi].clone(), ql.cpu()[qi].tolist()
+    cc = c.cpu().clone()
+    for b in range(B):
+        qc[b, qlc[b]:] = 0
+        cc[b, int(cl[b]):] = 0
+    ref = ar.ot_distance(qc, qlc, cc, cl.cpu().tolist(), diameter=60.0)
+    assert rel_err(allq["dual"].cpu().numpy(), ref.numpy()).max() <= 1e-4
+
+
 def test_kernels_agree_random_ragged():
     """Property: the two solvers (stabilised warp kernel, shared-exponential thread kernel) agree.
 
