@@ -1,16 +1,5 @@
 // Per-THREAD masked Sinkhorn solver for small tiles (Sq <= TQ, Sc <= TC), shared by the stand-alone
 // thread-per-pair kernel (ot_sinkhorn.cu) and the fused cost+OT kernel (ot_fused.cu).
-#pragma once
-#include "common.cuh"
-
-namespace asp {
-
-struct OtOut {
-    float *dual, *primal, *f, *g, *alpha, *beta, *neg_cost, *plan, *weighted;
-};
-
-// ---------------------------------------------------------------------------------------------------
-// Thread-per-pair kernel for small tiles (Sq <= TQ, Sc <= TC).
 //
 // State per thread: C[TQ][TC], log2 weights, f, g -- all in registers.  One step at epsilon (t = log2e/eps):
 //     u_i = la_i + f_i t,  v_j = lb_j + g_j t,  E_ij = 2^(u_i + v_j - C_ij t)      (ONE exponential per entry)
@@ -21,101 +10,136 @@ struct OtOut {
 // fp32 range (0, inf, nan) is recomputed with the max-stabilised form, so the result stays defined wherever
 // the reference's is.  init = un-averaged step from f=g=0 at eps[0]; loop = averaged steps; final =
 // un-averaged step at eps[n-1].
-// ---------------------------------------------------------------------------------------------------
+//
+// The column index is processed in PAIRS with the sm_100 packed fp32 instructions (FFMA2 / FADD2 through
+// __ffma2_rn / __fadd2_rn): per two entries the step issues 4 packed ALU instructions + 2 MUFU.EX2 instead of
+// 8 scalar ALU + 2 MUFU, which matters because the loop is issue-bound next to the MUFU pipe.
+#pragma once
+#include "common.cuh"
+
+namespace asp {
+
+struct OtOut {
+    float *dual, *primal, *f, *g, *alpha, *beta, *neg_cost, *plan, *weighted;
+};
+
 template <int TQ, int TC>
 struct PairState {
-    float C[TQ][TC];
-    float la[TQ], lb[TC], f[TQ], g[TC];
+    static_assert(TC % 2 == 0, "columns are processed in pairs");
+    float2 C[TQ][TC / 2];
+    float la[TQ], f[TQ];
+    float2 lb[TC / 2], g[TC / 2];
 };
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 
 template <int TQ, int TC>
 __device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql, int cl, float eps, float weight) {
     // weight = 1 (un-averaged) or 0.5 (averaged): new = old - weight * eps ln2 (log2 sum - logw)
+    constexpr int TP = TC / 2;
     const float t = kLog2e / eps;
     const float scale = weight * eps * kLn2;
-    float u[TQ], v[TC], S[TC];
+    const float2 t2 = dup2(t), nt2 = dup2(-t), nscale2 = dup2(-scale);
+    float u[TQ];
+    float2 v[TP], S[TP];
 #pragma unroll
     for (int i = 0; i < TQ; ++i) u[i] = fmaf(st.f[i], t, st.la[i]);
 #pragma unroll
-    for (int j = 0; j < TC; ++j) {
-        v[j] = fmaf(st.g[j], t, st.lb[j]);
-        S[j] = 0.f;
+    for (int j = 0; j < TP; ++j) {
+        v[j] = __ffma2_rn(st.g[j], t2, st.lb[j]);
+        S[j] = f2(0.f, 0.f);
     }
-    const float nt = -t;
     bool bad = false;
     float fnew[TQ];
 #pragma unroll
     for (int i = 0; i < TQ; ++i) {
-        float R = 0.f;
+        const float2 uu = dup2(u[i]);
+        float2 R = f2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            const float e = ex2(fmaf(st.C[i][j], nt, u[i] + v[j]));
-            R += e;
-            S[j] += e;
+        for (int j = 0; j < TP; ++j) {
+            const float2 x = __ffma2_rn(st.C[i][j], nt2, __fadd2_rn(uu, v[j]));
+            const float2 e = f2(ex2(x.x), ex2(x.y));
+            R = __fadd2_rn(R, e);
+            S[j] = __fadd2_rn(S[j], e);
         }
-        const float l = lg2(R);
-        fnew[i] = st.f[i] - scale * (l - st.la[i]);
+        const float l = lg2(R.x + R.y);
+        fnew[i] = fmaf(-scale, l - st.la[i], st.f[i]);
         bad |= (i < ql) && !(fabsf(l) < 1e30f);
     }
-    float gnew[TC];
+    float2 gnew[TP];
 #pragma unroll
-    for (int j = 0; j < TC; ++j) {
-        const float l = lg2(S[j]);
-        gnew[j] = st.g[j] - scale * (l - st.lb[j]);
-        bad |= (j < cl) && !(fabsf(l) < 1e30f);
+    for (int j = 0; j < TP; ++j) {
+        const float2 l = f2(lg2(S[j].x), lg2(S[j].y));
+        gnew[j] = __ffma2_rn(nscale2, __fadd2_rn(l, f2(-st.lb[j].x, -st.lb[j].y)), st.g[j]);
+        bad |= (2 * j < cl) && !(fabsf(l.x) < 1e30f);
+        bad |= (2 * j + 1 < cl) && !(fabsf(l.y) < 1e30f);
     }
     if (__builtin_expect(bad, 0)) {
         // max-stabilised recomputation of both half-steps from the old potentials (rare).  Padded rows/columns
         // carry log-weight -1e5 and vanish from every sum, exactly as in the reference.
+        const float nt = -t;
 #pragma unroll
         for (int i = 0; i < TQ; ++i) {
             float m = -INFINITY, s = 0.f;
 #pragma unroll
-            for (int j = 0; j < TC; ++j) m = fmaxf(m, fmaf(st.C[i][j], nt, v[j]));
+            for (int j = 0; j < TP; ++j)
+                m = fmaxf(m, fmaxf(fmaf(st.C[i][j].x, nt, v[j].x), fmaf(st.C[i][j].y, nt, v[j].y)));
 #pragma unroll
-            for (int j = 0; j < TC; ++j) s += ex2(fmaf(st.C[i][j], nt, v[j]) - m);
+            for (int j = 0; j < TP; ++j)
+                s += ex2(fmaf(st.C[i][j].x, nt, v[j].x) - m) + ex2(fmaf(st.C[i][j].y, nt, v[j].y) - m);
             const float ft = -eps * kLn2 * (m + lg2(s));
             fnew[i] = st.f[i] + weight * (ft - st.f[i]);
         }
 #pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            float m = -INFINITY, s = 0.f;
+        for (int j = 0; j < TP; ++j) {
+            float mx = -INFINITY, my = -INFINITY, sx = 0.f, sy = 0.f;
 #pragma unroll
-            for (int i = 0; i < TQ; ++i) m = fmaxf(m, fmaf(st.C[i][j], nt, u[i]));
+            for (int i = 0; i < TQ; ++i) {
+                mx = fmaxf(mx, fmaf(st.C[i][j].x, nt, u[i]));
+                my = fmaxf(my, fmaf(st.C[i][j].y, nt, u[i]));
+            }
 #pragma unroll
-            for (int i = 0; i < TQ; ++i) s += ex2(fmaf(st.C[i][j], nt, u[i]) - m);
-            const float gt = -eps * kLn2 * (m + lg2(s));
-            gnew[j] = st.g[j] + weight * (gt - st.g[j]);
+            for (int i = 0; i < TQ; ++i) {
+                sx += ex2(fmaf(st.C[i][j].x, nt, u[i]) - mx);
+                sy += ex2(fmaf(st.C[i][j].y, nt, u[i]) - my);
+            }
+            const float gx = -eps * kLn2 * (mx + lg2(sx)), gy = -eps * kLn2 * (my + lg2(sy));
+            gnew[j] = f2(st.g[j].x + weight * (gx - st.g[j].x), st.g[j].y + weight * (gy - st.g[j].y));
         }
     }
 #pragma unroll
     for (int i = 0; i < TQ; ++i) st.f[i] = (i < ql) ? fnew[i] : 0.f;
 #pragma unroll
-    for (int j = 0; j < TC; ++j) st.g[j] = (j < cl) ? gnew[j] : 0.f;
+    for (int j = 0; j < TP; ++j) st.g[j] = f2((2 * j < cl) ? gnew[j].x : 0.f, (2 * j + 1 < cl) ? gnew[j].y : 0.f);
 }
 
-
 // Solve one pair in the calling thread.  load_cost(i, j) returns C_ij for i < ql, j < cl (never called outside).
+// eps_sched[0..n_eps): the epsilon schedule (kernel-parameter / constant-bank or shared memory).
 // Writes every requested output of pair b.
 template <int TQ, int TC, typename LoadCost>
 __device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql, int cl, int b, int Sq, int Sc,
-                                                  const EpsSched& sched, float inv_temp, const OtOut& out) {
+                                                  const float* eps_sched, int n_eps, float inv_temp, const OtOut& out) {
+    constexpr int TP = TC / 2;
     PairState<TQ, TC> st;
     const float kBig = 1.0e30f;
 #pragma unroll
     for (int i = 0; i < TQ; ++i)
 #pragma unroll
-        for (int j = 0; j < TC; ++j) st.C[i][j] = (i < ql && j < cl) ? load_cost(i, j) : kBig;
+        for (int j = 0; j < TP; ++j)
+            st.C[i][j] = f2((i < ql && 2 * j < cl) ? load_cost(i, 2 * j) : kBig,
+                            (i < ql && 2 * j + 1 < cl) ? load_cost(i, 2 * j + 1) : kBig);
 
-    // marginals: log_softmax over valid sentences of (-min dist)/T, exp, then log again as geomloss does
-    float alpha[TQ], beta[TC];
+    // marginals (pair_distances.py:57-60): log_softmax over valid sentences of (-min dist)/T, exp, then log again as
+    // geomloss does (zero weights -> log-weight -1e5).  Only the log2 weights stay live; alpha/beta are
+    // re-materialised as 2^la at the end (keeps ~20 registers out of the hot loop).
     {
         float x[TQ], mx = -INFINITY, s = 0.f;
 #pragma unroll
         for (int i = 0; i < TQ; ++i) {
             float best = kBig;
 #pragma unroll
-            for (int j = 0; j < TC; ++j) best = fminf(best, st.C[i][j]);
+            for (int j = 0; j < TP; ++j) best = fminf(best, fminf(st.C[i][j].x, st.C[i][j].y));
             x[i] = -best * inv_temp;
             if (i < ql) mx = fmaxf(mx, x[i]);
         }
@@ -124,79 +148,102 @@ __device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql, in
         const float lse = mx + logf(s);
 #pragma unroll
         for (int i = 0; i < TQ; ++i) {
-            alpha[i] = (i < ql) ? expf(x[i] - lse) : 0.f;
-            st.la[i] = (alpha[i] > 0.f) ? log2f(alpha[i]) : kLogZeroWeight * kLog2e;
+            const float a = (i < ql) ? expf(x[i] - lse) : 0.f;
+            st.la[i] = (a > 0.f) ? log2f(a) : kLogZeroWeight * kLog2e;
         }
     }
     {
         float x[TC], mx = -INFINITY, s = 0.f;
 #pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            float best = kBig;
+        for (int j = 0; j < TP; ++j) {
+            float bx = kBig, by = kBig;
 #pragma unroll
-            for (int i = 0; i < TQ; ++i) best = fminf(best, st.C[i][j]);
-            x[j] = -best * inv_temp;
-            if (j < cl) mx = fmaxf(mx, x[j]);
+            for (int i = 0; i < TQ; ++i) {
+                bx = fminf(bx, st.C[i][j].x);
+                by = fminf(by, st.C[i][j].y);
+            }
+            x[2 * j] = -bx * inv_temp;
+            x[2 * j + 1] = -by * inv_temp;
+            if (2 * j < cl) mx = fmaxf(mx, x[2 * j]);
+            if (2 * j + 1 < cl) mx = fmaxf(mx, x[2 * j + 1]);
         }
 #pragma unroll
         for (int j = 0; j < TC; ++j) s += (j < cl) ? expf(x[j] - mx) : 0.f;
         const float lse = mx + logf(s);
 #pragma unroll
-        for (int j = 0; j < TC; ++j) {
-            beta[j] = (j < cl) ? expf(x[j] - lse) : 0.f;
-            st.lb[j] = (beta[j] > 0.f) ? log2f(beta[j]) : kLogZeroWeight * kLog2e;
+        for (int j = 0; j < TP; ++j) {
+            const float b0 = (2 * j < cl) ? expf(x[2 * j] - lse) : 0.f;
+            const float b1 = (2 * j + 1 < cl) ? expf(x[2 * j + 1] - lse) : 0.f;
+            st.lb[j] = f2((b0 > 0.f) ? log2f(b0) : kLogZeroWeight * kLog2e, (b1 > 0.f) ? log2f(b1) : kLogZeroWeight * kLog2e);
         }
     }
     // padded entries: any finite cost works (their weight is 2^-144269 = 0); keep them small and finite
 #pragma unroll
     for (int i = 0; i < TQ; ++i)
 #pragma unroll
-        for (int j = 0; j < TC; ++j)
-            if (!(i < ql && j < cl)) st.C[i][j] = 0.f;
+        for (int j = 0; j < TP; ++j) {
+            if (!(i < ql && 2 * j < cl)) st.C[i][j].x = 0.f;
+            if (!(i < ql && 2 * j + 1 < cl)) st.C[i][j].y = 0.f;
+        }
 #pragma unroll
     for (int i = 0; i < TQ; ++i) st.f[i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < TC; ++j) st.g[j] = 0.f;
+    for (int j = 0; j < TP; ++j) st.g[j] = f2(0.f, 0.f);
 
     if (ql > 0 && cl > 0) {
         // k = -1: initialisation (un-averaged step from f = g = 0 at eps[0]); k = 0..n-1: averaged steps;
         // k = n: final un-averaged extrapolation at eps[n-1].  One loop => one copy of the step in the binary.
 #pragma unroll 1
-        for (int k = -1; k <= sched.n; ++k) {
-            const bool plain = (k < 0) | (k == sched.n);
-            sinkhorn_step<TQ, TC>(st, ql, cl, sched.eps[min(max(k, 0), sched.n - 1)], plain ? 1.0f : 0.5f);
+        for (int k = -1; k <= n_eps; ++k) {
+            const bool plain = (k < 0) | (k == n_eps);
+            sinkhorn_step<TQ, TC>(st, ql, cl, eps_sched[min(max(k, 0), n_eps - 1)], plain ? 1.0f : 0.5f);
         }
     }
 
+    // weights back from their logs (exact zeros for padded sentences: 2^(-1e5 log2e) underflows to 0)
+    float alpha[TQ], beta[TC];
+#pragma unroll
+    for (int i = 0; i < TQ; ++i) alpha[i] = (i < ql) ? exp2f(st.la[i]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < TP; ++j) {
+        beta[2 * j] = (2 * j < cl) ? exp2f(st.lb[j].x) : 0.f;
+        beta[2 * j + 1] = (2 * j + 1 < cl) ? exp2f(st.lb[j].y) : 0.f;
+    }
     float dual = 0.f;
 #pragma unroll
     for (int i = 0; i < TQ; ++i) dual = fmaf(alpha[i], st.f[i], dual);
 #pragma unroll
-    for (int j = 0; j < TC; ++j) dual = fmaf(beta[j], st.g[j], dual);
+    for (int j = 0; j < TP; ++j) dual = fmaf(beta[2 * j + 1], st.g[j].y, fmaf(beta[2 * j], st.g[j].x, dual));
     if (out.dual) out.dual[b] = dual;
-#pragma unroll
-    for (int i = 0; i < TQ; ++i)
-        if (i < Sq) {
-            if (out.f) out.f[(size_t)b * Sq + i] = st.f[i];
-            if (out.alpha) out.alpha[(size_t)b * Sq + i] = alpha[i];
-        }
-#pragma unroll
-    for (int j = 0; j < TC; ++j)
-        if (j < Sc) {
-            if (out.g) out.g[(size_t)b * Sc + j] = st.g[j];
-            if (out.beta) out.beta[(size_t)b * Sc + j] = beta[j];
-        }
-    if (out.primal || out.plan || out.weighted || out.neg_cost) {
-        const float tf = kLog2e / sched.eps[sched.n - 1];
-        float primal = 0.f;
+    if (out.f || out.alpha) {
 #pragma unroll
         for (int i = 0; i < TQ; ++i)
+            if (i < Sq) {
+                if (out.f) out.f[(size_t)b * Sq + i] = st.f[i];
+                if (out.alpha) out.alpha[(size_t)b * Sq + i] = alpha[i];
+            }
+    }
+    if (out.g || out.beta) {
+#pragma unroll
+        for (int j = 0; j < TC; ++j)
+            if (j < Sc) {
+                if (out.g) out.g[(size_t)b * Sc + j] = (j & 1) ? st.g[j / 2].y : st.g[j / 2].x;
+                if (out.beta) out.beta[(size_t)b * Sc + j] = beta[j];
+            }
+    }
+    if (out.primal || out.plan || out.weighted || out.neg_cost) {
+        // plan (pair_distances.py:76-85): exp((f_i+g_j-C_ij)/blur) * alpha_i * beta_j, blur = eps_final
+        const float tf = kLog2e / eps_sched[n_eps - 1];
+        float primal = 0.f;
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
 #pragma unroll
             for (int j = 0; j < TC; ++j) {
                 if (i < Sq && j < Sc) {
                     const bool valid = (i < ql && j < cl);
-                    const float cij = st.C[i][j];
-                    const float p = valid ? ex2((st.f[i] + st.g[j] - cij) * tf) * (alpha[i] * beta[j]) : 0.f;
+                    const float cij = (j & 1) ? st.C[i][j / 2].y : st.C[i][j / 2].x;
+                    const float gj = (j & 1) ? st.g[j / 2].y : st.g[j / 2].x;
+                    const float p = valid ? ex2((st.f[i] + gj - cij) * tf) * (alpha[i] * beta[j]) : 0.f;
                     const float negc = valid ? -cij : 0.f;
                     const float w = p * negc;
                     primal += w;
@@ -206,9 +253,9 @@ __device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql, in
                     if (out.weighted) out.weighted[o] = w;
                 }
             }
+        }
         if (out.primal) out.primal[b] = primal;
     }
 }
-
 
 }  // namespace asp

@@ -227,7 +227,8 @@ sinkhorn_thread_kernel(const float* __restrict__ cost, const int32_t* __restrict
     if (b >= B) return;
     const int ql = min(max(q_lens[b / q_group], 0), Sq), cl = min(max(c_lens[b], 0), Sc);
     const float* Cg = cost + (size_t)b * Sq * Sc;
-    solve_pair_thread<TQ, TC>([&](int i, int j) { return Cg[i * Sc + j]; }, ql, cl, b, Sq, Sc, sched, inv_temp, out);
+    solve_pair_thread<TQ, TC>([&](int i, int j) { return Cg[i * Sc + j]; }, ql, cl, b, Sq, Sc, sched.eps, sched.n, inv_temp,
+                              out);
 }
 
 int g_ot_kernel = 0;  // 0 auto, 1 force warp-per-pair, 2 force thread-per-pair (asp_set_option "ot_kernel")

@@ -125,6 +125,92 @@ def pack_pool(cand_encs, device, max_sents=None):
     return host.to(device, non_blocking=True), torch.tensor(lens, dtype=torch.int32).to(device, non_blocking=True)
 
 
+_HOST_PIPE = {}
+
+
+def _host_pipeline(dev, chunk_pairs, sc, d):
+    """Per-device ping-pong staging buffers + copy stream for score_pools_host (created once, reused)."""
+    key = (dev.index, chunk_pairs, sc, d)
+    st = _HOST_PIPE.get(key)
+    if st is None:
+        st = {"bufs": [torch.empty((chunk_pairs, sc, d), dtype=torch.float32, device=dev) for _ in range(2)],
+              "copy": torch.cuda.Stream(device=dev),
+              "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)]}
+        _HOST_PIPE.clear()  # keep one configuration alive
+        _HOST_PIPE[key] = st
+    return st
+
+
+def score_pools_host(queries, q_lens, cands, cand_lens, pool_size, diameter=None, model_hparams=None,
+                     score_aggregation='l2wasserstein', chunk_queries=8):
+    """Several queries, each against its own pool, all held in HOST memory (the shape of an evaluation run whose
+    encodings cache lives on the host, utils/models.py:112-114).
+
+    queries [NQ,Sq,D]; cands [NQ*pool_size,Sc,D] zero padded, candidates of query i at rows i*pool_size...
+    (pin both for full PCIe rate); q_lens int32 [NQ]; cand_lens int32 [NQ*pool_size].
+    The pools are streamed to the GPU in chunks of ``chunk_queries`` queries on a copy stream, double buffered, so
+    the H2D copy of chunk k+1 overlaps the scoring of chunk k.  Returns {'scores': float32 pinned CPU tensor
+    (higher == closer: -OT_eps, or max -dist for 'l2max'), 'device_scores': the same on the GPU}; the call returns
+    after the scores have landed on the host.
+    """
+    hp = dict(model_hparams or {})
+    dev = torch.device("cuda", torch.cuda.current_device())
+    NQ, NP = queries.shape[0], cands.shape[0]
+    assert NP <= NQ * pool_size and cands.dim() == 3 and queries.dim() == 3
+    main = torch.cuda.current_stream(dev)
+    q = queries.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+    ql = q_lens.to(dev, dtype=torch.int32, non_blocking=True)
+    cl = cand_lens.to(dev, dtype=torch.int32, non_blocking=True)
+    if score_aggregation != 'l2max':
+        if diameter is None:
+            diameter = hp.get('geoml_diameter')
+        if diameter is None:
+            raise ValueError("score_pools_host streams the pools and cannot derive geomloss' bounding-box diameter; "
+                             "pass diameter= (or model_hparams['geoml_diameter'])")
+        eps = epsilon_schedule(diameter, hp.get('geoml_blur', 0.05), hp.get('geoml_scaling', 0.9))
+    chunk_queries = max(1, min(chunk_queries, NQ))
+    chunk_pairs = chunk_queries * pool_size
+    st = _host_pipeline(dev, chunk_pairs, cands.shape[1], cands.shape[2])
+    sims = torch.empty(NP, dtype=torch.float32, device=dev)
+    n_chunks = -(-NP // chunk_pairs)
+    for k in range(n_chunks):
+        lo, hi = k * chunk_pairs, min((k + 1) * chunk_pairs, NP)
+        buf = st["bufs"][k % 2][:hi - lo]
+        with torch.cuda.stream(st["copy"]):
+            if k >= 2:
+                st["copy"].wait_event(st["free"][k % 2])   # the kernel that read this buffer two chunks ago is done
+            buf.copy_(cands[lo:hi], non_blocking=True)
+            st["ready"][k % 2].record(st["copy"])
+        main.wait_event(st["ready"][k % 2])
+        q0 = lo // pool_size
+        nqk = -(-(hi - lo) // pool_size)
+        qk, qlk = q[q0:q0 + nqk], ql[q0:q0 + nqk]
+        if score_aggregation == 'l2max':
+            best = l2max_groups(qk, qlk, buf, cl[lo:hi], pool_size)
+            sims[lo:hi] = best
+        else:
+            ot_scores(qk, qlk, buf, cl[lo:hi], eps, temp=hp.get('sent_sm_temp', 1.0), q_group=pool_size,
+                      out={"dual": sims[lo:hi]})
+        st["free"][k % 2].record(main)
+    if score_aggregation != 'l2max':
+        sims.neg_()
+    host = torch.empty(sims.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(sims, non_blocking=True)
+    main.synchronize()
+    return {'scores': host, 'device_scores': sims}
+
+
+def l2max_groups(q, q_lens, c, c_lens, pool_size):
+    """tsAspire scores of several query pools: one launch per query (the l2max kernel takes one broadcast query)."""
+    out = torch.empty(c.shape[0], dtype=torch.float32, device=c.device)
+    for i in range(q.shape[0]):
+        lo, hi = i * pool_size, min((i + 1) * pool_size, c.shape[0])
+        if lo >= hi:
+            break
+        out[lo:hi] = l2max_scores(q[i:i + 1], q_lens[i:i + 1], c[lo:hi], c_lens[lo:hi], broadcast_query=True)[0]
+    return out
+
+
 def score_pool_tensors(query, cands, cand_lens, diameter=None, model_hparams=None, score_aggregation='l2wasserstein'):
     """One query against a packed pool held in HOST memory: H2D, score on the GPU, D2H of the scores.
 

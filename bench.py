@@ -1,21 +1,23 @@
 #!/usr/bin/env python
 """Headline benchmark: OT-scored doc-pairs/sec (10 sentences/doc, 768-d) -- BASELINE.json metric.
 
-A step = the hot path over one batch: ONE query scored against ITS pool of 1k candidates
-(BASELINE configs[1]) with otAspire (pair cost + softmax marginals + masked epsilon-scaling Sinkhorn, dual
-value).  Pools rotate over a resident corpus larger than L2, so every step streams its candidates from HBM.
+Workload = BASELINE configs[1] (otAspire OT scoring: 1 query x 1k candidates, 10 sents/doc, 768-d, blur 0.05,
+scaling 0.9, temp 1.0) batched the way an evaluation run presents it: a step scores ``--queries`` (default 64)
+queries, EACH against ITS OWN pool of 1k candidates, in ONE launch of the fused kernel (pair cost + softmax marginals
++ masked epsilon-scaling Sinkhorn, dual value) -- 64 000 pairs and 1.97 GB of candidate reps per step.  Steps rotate
+over ``--pools`` resident batches, each far larger than the 126 MB L2, so every step streams from HBM.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N>1 (launched by torchrun, one rank per GPU): weak scaling -- every rank holds its own shard of each pool
-(1k candidates per rank), scores the step's query against it, keeps a local top-100 with global ids, and the
-ranks exchange them with ONE NCCL all-gather + merge per step (the path's only collective).
+N>1 (launched by torchrun, one rank per GPU): weak scaling -- every rank holds its own shard of each query's pool
+(1k candidates per query per rank), scores it, keeps a per-query local top-100 with global ids, and the ranks
+exchange them with ONE NCCL all-gather + merge per step (the path's only collective).
 
 Prints ONE JSON line (rank 0).  ``value`` = device-resident throughput (CUDA events, max over ranks);
-``e2e`` = the same workload through the public host-buffer API (pinned H2D of the pool + D2H of the scores
-inside the timed region); ``roofline`` = HBM roofline of the dominant kernel; ``cpu_baseline`` = the oracle
-port of the reference's CPU path (torch, all host threads) on a bounded sample.
-``--impl reference`` times that CPU path as its own arm.
+``e2e`` = the same workload through the public host-buffer API (pinned H2D of the pools + D2H of the scores inside
+the timed region; PCIe-bound); ``roofline`` = HBM roofline of the dominant kernel; ``cpu_baseline`` = the oracle port
+of the reference's CPU path (torch, all host threads) on a bounded sample; ``latency_1x1k`` = one query x 1k
+candidates per launch (the un-batched shape of configs[1]).  ``--impl reference`` times the CPU path as its own arm.
 """
 import argparse
 import json
@@ -38,6 +40,7 @@ DIAMETER = 65.0          # explicit bounding-box diameter shared by all steps/ra
 TOPK = 100
 BYTES_PER_PAIR = SENTS * DIM * 4 + 12  # candidate reps once + lens + score = 30 732 B
 METRIC = "OT-scored doc-pairs/sec (10 sents, 768-d)"
+CPU_QUERIES = 8          # queries per step of the CPU arms (bounded sample of the same workload)
 
 
 def peaks():
@@ -92,23 +95,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_corpus(n_pools, device, seed):
-    """Synthetic abstracts: reps = 0.3*randn, all 10 sentences valid."""
+def make_corpus(n_batches, nq, device, seed):
+    """Synthetic abstracts: reps = 0.3*randn, all 10 sentences valid.
+    One batch = nq queries [nq,10,768] + their pools [nq*1000,10,768] (candidates of query i at rows i*1000...)."""
     g = torch.Generator(device=device).manual_seed(seed)
-    pools = [0.3 * torch.randn(POOL, SENTS, DIM, device=device, generator=g) for _ in range(n_pools)]
-    queries = [0.3 * torch.randn(1, SENTS, DIM, device=device, generator=g) for _ in range(n_pools)]
+    pools = [0.3 * torch.randn(nq * POOL, SENTS, DIM, device=device, generator=g) for _ in range(n_batches)]
+    queries = [0.3 * torch.randn(nq, SENTS, DIM, device=device, generator=g) for _ in range(n_batches)]
     return queries, pools
 
 
 # ------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_step(ar, q, c, lens_q, lens_c, threads):
-    """One step of the reference's CPU path (oracle port): compute_distance on [B,S,D] with the query replicated
-    B times, as caching_score does (disent_models.py:274-297), same explicit diameter as the GPU arm."""
+def cpu_reference_step(ar, q, c, threads):
+    """One step of the reference's CPU path (oracle port): for every query, compute_distance on [1000,S,D] with the
+    query replicated 1000 times, as caching_score does (disent_models.py:274-297); same explicit diameter as the
+    GPU arm.  q [nq,S,D], c [nq*1000,S,D]."""
     torch.set_num_threads(threads)
+    lens = [SENTS] * POOL
     t0 = time.perf_counter()
-    d = ar.ot_distance(q.expand(c.shape[0], -1, -1), lens_q, c, lens_c, blur=BLUR, scaling=SCALING, temp=TEMP,
-                       diameter=DIAMETER)
-    return time.perf_counter() - t0, d
+    out = []
+    for i in range(q.shape[0]):
+        out.append(ar.ot_distance(q[i:i + 1].expand(POOL, -1, -1), lens, c[i * POOL:(i + 1) * POOL], lens, blur=BLUR,
+                                  scaling=SCALING, temp=TEMP, diameter=DIAMETER))
+    return time.perf_counter() - t0, torch.cat(out)
 
 
 def run_reference(args):
@@ -118,33 +126,35 @@ def run_reference(args):
     from oracle import aspire_ref as ar
     threads = os.cpu_count() or 1
     g = torch.Generator().manual_seed(1234)
-    q = 0.3 * torch.randn(1, SENTS, DIM, generator=g)
-    pools = [0.3 * torch.randn(POOL, SENTS, DIM, generator=g) for _ in range(4)]
-    lq, lc = [SENTS] * POOL, [SENTS] * POOL
+    nq = CPU_QUERIES
+    qs = [0.3 * torch.randn(nq, SENTS, DIM, generator=g) for _ in range(2)]
+    pools = [0.3 * torch.randn(nq * POOL, SENTS, DIM, generator=g) for _ in range(2)]
     for i in range(args.warmup):
-        cpu_reference_step(ar, q, pools[i % 4], lq, lc, threads)
+        cpu_reference_step(ar, qs[i % 2], pools[i % 2], threads)
     total = 0.0
     for i in range(args.steps):
-        dt, _ = cpu_reference_step(ar, q, pools[i % 4], lq, lc, threads)
+        dt, _ = cpu_reference_step(ar, qs[i % 2], pools[i % 2], threads)
         total += dt
-    value = POOL * args.steps / total
+    value = nq * POOL * args.steps / total
+    cfg = workload_config(1, args.queries)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(1),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} steps x {POOL} pairs, oracle/aspire_ref.py (torch CPU restatement "
-                                       f"of pair_distances.py:21-92 + geomloss 0.2.4), one call per step"},
+                             "sample": f"each step = {nq} of the workload's queries x {POOL} candidates ({nq * POOL} pairs), "
+                                       f"oracle/aspire_ref.py (torch CPU restatement of pair_distances.py:21-92 + "
+                                       f"geomloss 0.2.4), one compute_distance call per query"},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
-    return {"workload": "otAspire OT scoring: 1 query x 1k candidates per step (per GPU), 10 sents/doc, 768-d, "
-                        "blur 0.05, scaling 0.9, temp 1.0 (BASELINE configs[1])",
-            "pairs_per_step": POOL * n_gpus, "n_eps": None, "diameter": DIAMETER,
-            "cache": "pools rotate over a resident corpus of 16 x 30.7 MB per GPU (> 126 MB L2)",
-            "parallelism": f"candidate-sharded x{n_gpus}, top-{TOPK} NCCL all-gather per step" if n_gpus > 1
+def workload_config(n_gpus, nq):
+    return {"workload": f"otAspire OT scoring (BASELINE configs[1]: 1 query x 1k candidates, 10 sents/doc, 768-d, "
+                        f"blur 0.05, scaling 0.9, temp 1.0), {nq} such queries per step in one fused launch (per GPU)",
+            "queries_per_step": nq * n_gpus, "pairs_per_step": nq * POOL * n_gpus, "n_eps": None, "diameter": DIAMETER,
+            "cache": f"steps rotate over resident batches of {nq * POOL * BYTES_PER_PAIR / 1e9:.2f} GB each (>> 126 MB L2)",
+            "parallelism": f"candidate-sharded x{n_gpus}, per-query top-{TOPK} NCCL all-gather per step" if n_gpus > 1
                            else "single GPU"}
 
 
@@ -152,10 +162,11 @@ def workload_config(n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--pools", type=int, default=16)
+    ap.add_argument("--queries", type=int, default=64, help="queries (x 1k candidates each) per step")
+    ap.add_argument("--pools", type=int, default=4, help="resident corpus batches the steps rotate over")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -176,22 +187,23 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _abi.lib()  # fail loudly if the CUDA library is missing
 
+    NQ = args.queries
+    NP = NQ * POOL  # pairs per step per GPU
     eps = epsilon_schedule(DIAMETER, BLUR, SCALING)
-    queries, pools = make_corpus(args.pools, dev, 1234 + rank)
-    if world > 1:  # the step's query is the same on every rank (rank 0's), broadcast once
+    queries, pools = make_corpus(args.pools, NQ, dev, 1234 + rank)
+    if world > 1:  # the step's queries are the same on every rank (rank 0's), broadcast once
         for q in queries:
             dist.broadcast(q, 0)
-    q_lens = torch.tensor([SENTS], dtype=torch.int32, device=dev)
-    c_lens = torch.full((POOL,), SENTS, dtype=torch.int32, device=dev)
-    cost_ws = torch.empty((POOL, SENTS, SENTS), dtype=torch.float32, device=dev)
+    q_lens = torch.full((NQ,), SENTS, dtype=torch.int32, device=dev)
+    c_lens = torch.full((NP,), SENTS, dtype=torch.int32, device=dev)
+    out = {"dual": torch.empty(NP, dtype=torch.float32, device=dev)}
     base_id = rank * POOL
 
     def step(i):
         p = i % args.pools
-        res = ot_scores(queries[p], q_lens, pools[p], c_lens, eps, temp=TEMP, want=("dual",), broadcast_query=True,
-                        cost_workspace=cost_ws)
+        res = ot_scores(queries[p], q_lens, pools[p], c_lens, eps, temp=TEMP, want=("dual",), q_group=POOL, out=out)
         if world > 1:
-            s, ids = topk((-res["dual"])[None], TOPK, base_id=base_id)
+            s, ids = topk((-res["dual"]).view(NQ, POOL), TOPK, base_id=base_id)
             return gather_topk(s, ids, TOPK)
         return res["dual"]
 
@@ -201,14 +213,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # clock ramp: ~0.3 s of untimed steps so the timed region runs at load clocks
-    t_end = time.time() + 0.3
+    # clock ramp: ~0.5 s of untimed steps so the timed region runs at load clocks
+    t_end = time.time() + 0.5
     i = 0
     while time.time() < t_end:
         step(i)
         i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
+        torch.cuda.synchronize()
     for i in range(args.warmup):
         step(i)
     sync_all()
@@ -228,43 +239,51 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
-    # ---- per-kernel timing of the same steps: which kernel dominates, and its HBM roofline ----------
-    L = _abi.lib()
-    st = _abi.stream_of(dev)
-    import ctypes
-    eps32 = np.asarray(eps, dtype=np.float32)
-    dual = torch.empty(POOL, device=dev)
-    outs = _abi.AspOtOutputs(dual=dual.data_ptr())
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    # ---- per-launch timing of the dominant kernel (CUDA events on its stream, same rotation of batches) ----
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     for i in range(args.steps):
         p = i % args.pools
         ev[i][0].record()
-        _abi.check(L.asp_pair_cost(_abi.ptr(queries[p]), _abi.ptr(q_lens), 1, _abi.ptr(pools[p]), _abi.ptr(c_lens), POOL,
-                                   SENTS, SENTS, DIM, _abi.ptr(cost_ws), st), "asp_pair_cost")
+        ot_scores(queries[p], q_lens, pools[p], c_lens, eps, temp=TEMP, want=("dual",), q_group=POOL, out=out)
         ev[i][1].record()
-        _abi.check(L.asp_ot_sinkhorn_from_cost(_abi.ptr(cost_ws), _abi.ptr(q_lens), 1, _abi.ptr(c_lens), POOL, SENTS, SENTS,
-                                               eps32.ctypes.data_as(_abi.c_float_p), len(eps32), TEMP,
-                                               ctypes.byref(outs), st), "asp_ot_sinkhorn_from_cost")
-        ev[i][2].record()
     torch.cuda.synchronize()
-    t_cost = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    t_sink = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    t_fused = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     clocks = sampler.stop() if sampler else None
 
+    # ---- latency of the un-batched shape: ONE query x 1k candidates per launch ----
+    lat_out = {"dual": torch.empty(POOL, dtype=torch.float32, device=dev)}
+    q1, ql1, cl1 = queries[0][:1].contiguous(), q_lens[:1].contiguous(), c_lens[:POOL].contiguous()
+    def one(i):
+        p = i % args.pools
+        off = (i % NQ) * POOL
+        ot_scores(q1, ql1, pools[p][off:off + POOL], cl1, eps, temp=TEMP, want=("dual",), broadcast_query=True, out=lat_out)
+    for i in range(20):
+        one(i)
+    torch.cuda.synchronize()
+    la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    la.record()
+    for i in range(200):
+        one(i)
+    lb.record()
+    torch.cuda.synchronize()
+    lat_ms = la.elapsed_time(lb) / 200
+
     # ---- e2e: host buffers in, host scores out, through the public API ------------------------------
-    from aspire_b200.similarity import score_pool_tensors
-    host_pools = [p.cpu().pin_memory() for p in pools[:4]]
-    host_q = [q.cpu().pin_memory() for q in queries[:4]]
-    host_lens = torch.full((POOL,), SENTS, dtype=torch.int32).pin_memory()
-    for i in range(3):
-        score_pool_tensors(host_q[i % 4], host_pools[i % 4], host_lens, diameter=DIAMETER)
+    from aspire_b200.similarity import score_pools_host
+    n_host = 2
+    host_pools = [pools[k].cpu().pin_memory() for k in range(n_host)]
+    host_q = [queries[k].cpu().pin_memory() for k in range(n_host)]
+    host_lens = torch.full((NP,), SENTS, dtype=torch.int32).pin_memory()
+    host_qlens = torch.full((NQ,), SENTS, dtype=torch.int32).pin_memory()
+    for i in range(2):
+        score_pools_host(host_q[i % n_host], host_qlens, host_pools[i % n_host], host_lens, POOL, diameter=DIAMETER)
     sync_all()
-    e2e_steps = max(10, min(args.steps, 100))
+    e2e_steps = max(3, min(args.steps, 20))
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        out = score_pool_tensors(host_q[i % 4], host_pools[i % 4], host_lens, diameter=DIAMETER)
+        res = score_pools_host(host_q[i % n_host], host_qlens, host_pools[i % n_host], host_lens, POOL, diameter=DIAMETER)
         if world > 1:
-            s, ids = topk(out["device_scores"][None], TOPK, base_id=base_id)
+            s, ids = topk(res["device_scores"].view(NQ, POOL), TOPK, base_id=base_id)
             gather_topk(s, ids, TOPK)
     sync_all()
     e2e_s = time.perf_counter() - t0
@@ -272,8 +291,8 @@ def main():
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    h2d = host_pools[0].numel() * 4 + host_q[0].numel() * 4 + host_lens.numel() * 4
-    d2h = POOL * 4
+    h2d = host_pools[0].numel() * 4 + host_q[0].numel() * 4 + host_lens.numel() * 4 + host_qlens.numel() * 4
+    d2h = NP * 4
 
     if rank != 0:
         if world > 1:
@@ -281,42 +300,42 @@ def main():
         return
 
     peak, peak_src = peaks()
-    dom_name, dom_ms = ("pair_cost_kernel", t_cost) if t_cost >= t_sink else ("sinkhorn kernel", t_sink)
-    achieved = BYTES_PER_PAIR * POOL / (dom_ms * 1e-3) / 1e9
-    cfg = workload_config(world)
+    achieved = BYTES_PER_PAIR * NP / (t_fused * 1e-3) / 1e9
+    cfg = workload_config(world, NQ)
     cfg["n_eps"] = len(eps)
     line = {
-        "metric": METRIC, "value": POOL * world * args.steps / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+        "metric": METRIC, "value": NP * world * args.steps / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "clocks": clocks,
-        "e2e": {"value": POOL * world * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": NP * world * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "aspire_b200.similarity.score_pool_tensors (pinned host tensors in, host scores out)"},
+                "api": "aspire_b200.similarity.score_pools_host (pinned host tensors in, chunked H2D overlapped with "
+                       "scoring, host scores out)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": dom_name, "kernel_ms": dom_ms, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": BYTES_PER_PAIR * POOL,
-                     "per_kernel_ms": {"pair_cost_kernel": t_cost, "sinkhorn": t_sink},
-                     "step_hbm_frac": BYTES_PER_PAIR * POOL / (ms / args.steps * 1e-3) / 1e9 / peak},
+                     "traffic": None, "kernel": "ot_fused_kernel", "kernel_ms": t_fused, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": BYTES_PER_PAIR * NP,
+                     "step_hbm_frac": BYTES_PER_PAIR * NP / (ms / args.steps * 1e-3) / 1e9 / peak},
+        "latency_1x1k": {"pairs_per_launch": POOL, "ms_per_launch": lat_ms, "pairs_per_s": POOL / (lat_ms * 1e-3)},
     }
     if world == 1:
         from oracle import aspire_ref as ar
         threads = os.cpu_count() or 1
-        qc = queries[0].cpu()
-        pc = pools[0].cpu()
-        lq, lc = [SENTS] * POOL, [SENTS] * POOL
-        cpu_reference_step(ar, qc, pc, lq, lc, threads)
+        qc = queries[0][:CPU_QUERIES].cpu()
+        pc = pools[0][:CPU_QUERIES * POOL].cpu()
+        cpu_reference_step(ar, qc[:1], pc[:POOL], threads)
         n, tot = 0, 0.0
-        while tot < args.cpu_seconds and n < 200:
-            dt, dref = cpu_reference_step(ar, qc, pc, lq, lc, threads)
+        while tot < args.cpu_seconds and n < 50:
+            dt, dref = cpu_reference_step(ar, qc, pc, threads)
             tot += dt
             n += 1
-        got = ot_scores(queries[0], q_lens, pools[0], c_lens, eps, temp=TEMP, broadcast_query=True)["dual"].cpu()
+        got = ot_scores(queries[0], q_lens, pools[0], c_lens, eps, temp=TEMP, q_group=POOL)["dual"][:CPU_QUERIES * POOL].cpu()
         rel = ((got - dref).abs() / dref.abs().clamp(min=1)).max().item()
-        line["cpu_baseline"] = {"value": POOL * n / tot, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                "sample": f"{n} calls x {POOL} pairs ({tot:.1f} s) of oracle/aspire_ref.ot_distance "
-                                          f"(torch CPU restatement of pair_distances.py:21-92 + geomloss 0.2.4)",
+        line["cpu_baseline"] = {"value": CPU_QUERIES * POOL * n / tot, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} passes over {CPU_QUERIES} of the step's queries x {POOL} candidates "
+                                          f"({tot:.1f} s) of oracle/aspire_ref.ot_distance (torch CPU restatement of "
+                                          f"pair_distances.py:21-92 + geomloss 0.2.4)",
                                 "parity_max_rel_err_vs_gpu": rel}
     print(json.dumps(line))
     if world > 1:

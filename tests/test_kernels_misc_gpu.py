@@ -133,3 +133,24 @@ def test_ranking_parity_map():
         maps_o.append(ar.average_precision([int(rel[qi, j]) for j in order_ref]))
     assert abs(np.mean(maps_k) - np.mean(maps_o)) <= 1e-3
     assert np.mean(maps_k) > 0.5  # the synthetic relevance signal is actually recovered
+
+
+def test_score_pools_host_matches_device_path_and_oracle():
+    """Host-buffer API (chunked, overlapped H2D): same scores as the resident-tensor path; ragged last chunk."""
+    from aspire_b200 import epsilon_schedule, ot_scores
+    from aspire_b200.similarity import score_pools_host
+    g = torch.Generator().manual_seed(31)
+    NQ, G = 5, 40
+    NP = NQ * G - 7
+    q = (0.3 * torch.randn(NQ, 10, 768, generator=g)).pin_memory()
+    c = (0.3 * torch.randn(NP, 10, 768, generator=g)).pin_memory()
+    ql = torch.randint(2, 11, (NQ,), generator=g).int()
+    cl = torch.randint(1, 11, (NP,), generator=g).int()
+    res = score_pools_host(q, ql, c, cl, G, diameter=60.0, chunk_queries=2)
+    dev = ot_scores(q.cuda(), ql.cuda(), c.cuda(), cl.cuda(), epsilon_schedule(60.0, 0.05, 0.9), q_group=G)["dual"]
+    assert torch.equal(res["scores"], -dev.cpu())
+    assert res["scores"].is_pinned() and not res["scores"].is_cuda
+    ts = score_pools_host(q, ql, c, cl, G, score_aggregation='l2max', chunk_queries=2)["scores"]
+    qi = torch.arange(NP) // G
+    best, _, _ = ar.l2max(q[qi], ql[qi].tolist(), c, cl.tolist())
+    assert np.allclose(ts.numpy(), best.numpy(), rtol=1e-5, atol=2e-5)
