@@ -64,15 +64,20 @@ def lib():
     L.asp_ot_sinkhorn_from_cost.argtypes = [vp, vp, ci, vp, ci, ci, ci, c_float_p, ci, cf,
                                             ctypes.POINTER(AspOtOutputs), vp]
     L.asp_gemm_bf16_tn.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
+    L.asp_l2max_allpairs.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, vp, vp, vp, ctypes.c_size_t, vp]
+    L.asp_l2max_allpairs_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.asp_bbox_diameter.argtypes = [vp, cll, vp, cll, ci, vp, vp, vp]
     L.asp_topk.argtypes = [vp, ci, cll, ci, cll, vp, vp, vp]
     L.asp_topk_merge.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
-        if name not in ("asp_last_error", "asp_launch_count", "asp_ot_score_workspace_bytes"):
+        if name not in ("asp_last_error", "asp_launch_count", "asp_ot_score_workspace_bytes", "asp_l2max_allpairs_workspace_bytes",
+                        "asp_bert_workspace_bytes"):
             fn.restype = ci
     L.asp_launch_count.restype = cll
     L.asp_ot_score_workspace_bytes.restype = ctypes.c_size_t
+    L.asp_l2max_allpairs_workspace_bytes.restype = ctypes.c_size_t
+    L.asp_bert_workspace_bytes.restype = ctypes.c_size_t
     _lib = L
     return L
 

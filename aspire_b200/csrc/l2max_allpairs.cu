@@ -1,0 +1,242 @@
+// K2+K3 all-pairs: tsAspire scores of EVERY query document against EVERY candidate document (config 3:
+// 1k queries x 100k candidates) -- a dense [Q*S, D] x [D, C*S] contraction with a segmented max epilogue, on tcgen05.
+//
+// Replaces the numpy path of src/pre_process/pp_gen_nearest.py: `-scipy cdist(query_sents, pool_sents)` (:942; the
+// all-queries x all-corpus variant :788-795) followed by the per-candidate column-slice `np.max` (:949-961), and
+// allpair_masked_dist_l2max (pair_distances.py:138-186) applied to all Q x C pairs.
+//
+// Documents are rows-of-S sentence blocks ([N, S, D] zero padded), so a 128-row A tile holds floor(128/S) whole query
+// documents and a 160-column B tile floor(160/S) whole candidate documents (12 x 16 documents per CTA at S = 10).
+// Main loop = gemm.cu's (TMA 128B-swizzled boxes -> 4-stage mbarrier ring -> tcgen05.mma, fp32 accumulator in TMEM),
+// with fp32-equivalent bf16x3 operands: the fp32 representations are split once (split_rows_kernel) into bf16 hi / lo
+// halves + exact fp32 squared norms, and every K block accumulates hi.hi + hi.lo + lo.hi.
+// Epilogue: each thread owns one query-sentence row of the accumulator: d^2 = |q|^2 + |c|^2 - 2 q.c, running
+// (min d^2, first j) per candidate document -> shared memory -> min over the query document's rows (first i on ties,
+// i.e. the flat index i*S+j of the first maximum, pair_distances.py:176) -> score = -sqrt(max(d^2, 1e-8)).
+#include "common.cuh"
+#include "bert/tc05.cuh"
+
+namespace asp {
+
+using namespace tc;
+
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+constexpr int kApStages = 4;
+constexpr int kApBlockM = 128, kApBlockN = 160, kApBlockK = 64;
+constexpr int kApABytes = kApBlockM * kApBlockK * 2, kApBBytes = kApBlockN * kApBlockK * 2;
+constexpr int kApStage = kApABytes + kApBBytes;
+constexpr int kApMaxDocsN = 80;  // floor(160 / 2)
+constexpr int kApSmem = kApStages * kApStage + 128 + kApBlockM * 17 * 8 + 1024;
+
+struct AllPairsArgs {
+    const float* qn;        // [NQ*S] squared norms of the query sentence rows
+    const float* cn;        // [NC*S]
+    const int32_t* q_lens;  // [NQ]
+    const int32_t* c_lens;  // [NC]
+    int NQ, NC, S, D;
+    int docs_m, docs_n;     // whole documents per tile
+    float* scores;          // [NQ, NC]
+    int32_t* flat_idx;      // [NQ, NC] or NULL
+};
+
+// fp32 rows -> bf16 hi / lo halves + exact fp32 squared norm.  One warp per row; D % 4 == 0.
+__global__ void __launch_bounds__(128)
+split_rows_kernel(const float* __restrict__ x, long long rows, int D, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo, float* __restrict__ norms) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float4* src = reinterpret_cast<const float4*>(x + r * D);
+    float s = 0.f;
+    for (int k4 = lane; k4 < (D >> 2); k4 += 32) {
+        const float4 v = ldg_stream(src + k4);
+        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+        uint2 ph, pl;
+        ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+        pl.x = *reinterpret_cast<const uint32_t*>(&l0); pl.y = *reinterpret_cast<const uint32_t*>(&l1);
+        reinterpret_cast<uint2*>(hi + r * D)[k4] = ph;
+        reinterpret_cast<uint2*>(lo + r * D)[k4] = pl;
+    }
+    s = warp_sum(s);
+    if (lane == 0) norms[r] = s;
+}
+
+__global__ void __launch_bounds__(128)
+l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_constant__ CUtensorMap tq_lo,
+                      const __grid_constant__ CUtensorMap tc_hi, const __grid_constant__ CUtensorMap tc_lo,
+                      const AllPairsArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kApStages * kApStage);
+    uint64_t* empty = full + kApStages;
+    uint64_t* accum = empty + kApStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+    float* ep_d2 = reinterpret_cast<float*>(smem + kApStages * kApStage + 128);  // [128][17] min d^2 per (row, cand doc)
+    int* ep_j = reinterpret_cast<int*>(ep_d2 + kApBlockM * 17);                  // [128][17] its column within the doc
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = g.S;
+    const int qd0 = blockIdx.x * g.docs_m, cd0 = blockIdx.y * g.docs_n;  // first query / candidate document of the tile
+    const int m0 = qd0 * S, n0 = cd0 * S;
+    const int rows_m = g.docs_m * S, cols_n = g.docs_n * S;
+    const int total = (g.D / kApBlockK) * 3;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tq_hi);
+        tma_prefetch_desc(&tc_hi);
+        for (int s = 0; s < kApStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        for (int it = 0; it < total; ++it) {
+            const int s = it % kApStages, ph = (it / kApStages) & 1;
+            const int kb = it / 3, term = it - kb * 3;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], (uint32_t)(rows_m + cols_n) * (kApBlockK * 2));
+            uint8_t* sa = smem + s * kApStage;
+            tma_load_2d(sa, term == 2 ? &tq_lo : &tq_hi, &full[s], kb * kApBlockK, m0);
+            tma_load_2d(sa + kApABytes, term == 1 ? &tc_lo : &tc_hi, &full[s], kb * kApBlockK, n0);
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(kApBlockM, kApBlockN);
+        for (int it = 0; it < total; ++it) {
+            const int s = it % kApStages, ph = (it / kApStages) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after_sync();
+            const uint32_t sa = smem_u32(smem + s * kApStage);
+            const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + kApABytes);
+#pragma unroll
+            for (int k = 0; k < kApBlockK / 16; ++k)
+                umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            umma_commit(&empty[s]);
+        }
+        umma_commit(accum);
+    }
+    __syncwarp();
+
+    // ---------------- epilogue ----------------
+    mbar_wait(accum, 0);
+    tc_fence_after_sync();
+    const int r = warp * 32 + lane;  // accumulator row = query sentence row m0 + r
+    const bool row_in = r < rows_m && (m0 + r) < g.NQ * S;
+    const float qn = row_in ? __ldg(g.qn + m0 + r) : 0.f;
+    float best = INFINITY;
+    int best_j = 0, cdoc = 0, j = 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kApBlockN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+            const int col = c0 + e;
+            if (col < cols_n) {
+                const int cl = (cd0 + cdoc < g.NC) ? min(max(__ldg(g.c_lens + cd0 + cdoc), 0), S) : 0;
+                const float cnv = (n0 + col < g.NC * S) ? __ldg(g.cn + n0 + col) : 0.f;
+                const float d2 = qn + cnv - 2.f * v[e];
+                if (j < cl && d2 < best) {
+                    best = d2;
+                    best_j = j;
+                }
+                if (++j == S) {  // candidate document finished
+                    ep_d2[r * 17 + (cdoc & 15)] = best;
+                    ep_j[r * 17 + (cdoc & 15)] = best_j;
+                    // more than 16 documents per tile (S < 10) are flushed in rounds of 16 below
+                    best = INFINITY;
+                    best_j = 0;
+                    j = 0;
+                    ++cdoc;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
+    // min over the rows of each query document (first row wins ties => first flat index i*S+j)
+    for (int t = threadIdx.x; t < g.docs_m * g.docs_n; t += blockDim.x) {
+        const int qd = t / g.docs_n, cd = t - qd * g.docs_n;
+        const int gq = qd0 + qd, gc = cd0 + cd;
+        if (gq >= g.NQ || gc >= g.NC) continue;
+        const int ql = min(max(__ldg(g.q_lens + gq), 0), S), cl = min(max(__ldg(g.c_lens + gc), 0), S);
+        float bd = INFINITY;
+        int bi = 0;
+        for (int i = 0; i < ql; ++i) {
+            const float d = ep_d2[(qd * S + i) * 17 + cd];
+            if (d < bd) {
+                bd = d;
+                bi = i * S + ep_j[(qd * S + i) * 17 + cd];
+            }
+        }
+        const bool any = ql > 0 && cl > 0 && bd < INFINITY;
+        g.scores[(size_t)gq * g.NC + gc] = any ? -sqrtf(fmaxf(bd, 1e-8f)) : kPadNeg;
+        if (g.flat_idx) g.flat_idx[(size_t)gq * g.NC + gc] = any ? bi : 0;
+    }
+}
+
+}  // namespace asp
+
+extern "C" size_t asp_l2max_allpairs_workspace_bytes(int NQ, int NC, int S, int D) {
+    const size_t rows = (size_t)(NQ + NC) * S;
+    return rows * D * 2 * 2 + rows * sizeof(float) + 1024;
+}
+
+extern "C" int asp_l2max_allpairs(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens,
+                                  int NC, int S, int D, float* scores, int32_t* flat_idx, void* workspace,
+                                  size_t workspace_bytes, asp_stream_t stream_) {
+    using namespace asp;
+    ASP_REQUIRE(q && c && q_lens && c_lens && scores, "asp_l2max_allpairs: NULL pointer");
+    ASP_REQUIRE(NQ >= 0 && NC >= 0 && S >= 10 && S <= 64, "asp_l2max_allpairs: sentences per document must be in [10, 64] (got %d)", S);
+    ASP_REQUIRE(D >= 64 && (D % 64) == 0, "asp_l2max_allpairs: D must be a multiple of 64 (got %d)", D);
+    ASP_REQUIRE(aligned16(q) && aligned16(c), "asp_l2max_allpairs: q/c must be 16-byte aligned");
+    ASP_REQUIRE(workspace && workspace_bytes >= asp_l2max_allpairs_workspace_bytes(NQ, NC, S, D),
+                "asp_l2max_allpairs: workspace too small");
+    if (NQ == 0 || NC == 0) return ASP_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t qrows = (size_t)NQ * S, crows = (size_t)NC * S;
+    char* w = static_cast<char*>(workspace);
+    w += (256 - (reinterpret_cast<uintptr_t>(w) & 255)) & 255;
+    __nv_bfloat16* q_hi = reinterpret_cast<__nv_bfloat16*>(w); w += qrows * D * 2;
+    __nv_bfloat16* q_lo = reinterpret_cast<__nv_bfloat16*>(w); w += qrows * D * 2;
+    __nv_bfloat16* c_hi = reinterpret_cast<__nv_bfloat16*>(w); w += crows * D * 2;
+    __nv_bfloat16* c_lo = reinterpret_cast<__nv_bfloat16*>(w); w += crows * D * 2;
+    float* qn = reinterpret_cast<float*>(w); w += qrows * 4;
+    float* cn = reinterpret_cast<float*>(w);
+    split_rows_kernel<<<(unsigned)((qrows + 3) / 4), 128, 0, stream>>>(q, (long long)qrows, D, q_hi, q_lo, qn);
+    ASP_LAUNCH_CHECK("split_rows_kernel");
+    split_rows_kernel<<<(unsigned)((crows + 3) / 4), 128, 0, stream>>>(c, (long long)crows, D, c_hi, c_lo, cn);
+    ASP_LAUNCH_CHECK("split_rows_kernel");
+    const int docs_m = kApBlockM / S, docs_n = kApBlockN / S;
+    CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
+    int rc;
+    if ((rc = make_tmap_bf16(&tq_hi, q_hi, qrows, D, docs_m * S))) return rc;
+    if ((rc = make_tmap_bf16(&tq_lo, q_lo, qrows, D, docs_m * S))) return rc;
+    if ((rc = make_tmap_bf16(&tc_hi, c_hi, crows, D, docs_n * S))) return rc;
+    if ((rc = make_tmap_bf16(&tc_lo, c_lo, crows, D, docs_n * S))) return rc;
+    AllPairsArgs g{qn, cn, q_lens, c_lens, NQ, NC, S, D, docs_m, docs_n, scores, flat_idx};
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        ASP_CUDA(cudaFuncSetAttribute(l2max_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
+        attr_dev = dev;
+    }
+    dim3 grid((NQ + docs_m - 1) / docs_m, (NC + docs_n - 1) / docs_n);
+    l2max_allpairs_kernel<<<grid, 128, kApSmem, stream>>>(tq_hi, tq_lo, tc_hi, tc_lo, g);
+    ASP_LAUNCH_CHECK("l2max_allpairs_kernel");
+    return ASP_OK;
+}

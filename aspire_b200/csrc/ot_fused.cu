@@ -22,6 +22,7 @@
 //     and step, no shuffles, no shared memory in the loop.
 // The query rows come through L1 (30 KB per query, re-read by every pair of its pool); their squared norms are
 // computed once per (warp, query) and kept in shared memory.
+#include <algorithm>
 #include "gram.cuh"
 #include "ot_pair.cuh"
 
@@ -32,7 +33,7 @@ constexpr int kHR = kFT / 2;   // query rows per half-warp
 constexpr int kFusedWarps = 4; // warps per CTA
 constexpr int kCostLd = 101;   // floats per pair in the shared cost tile
 constexpr int kRedVals = 64;   // 50 dot products + 10 candidate norms, padded for the 16-lane transpose-reduce
-constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 16;  // cost tile + reduced values per half + query norms
+constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 32;  // cost tile + reduced values per half + 2 x query norms
 constexpr int kCounterSlots = 256;
 
 __device__ unsigned int g_tile_counter[kCounterSlots];
@@ -44,6 +45,7 @@ struct FusedArgs {
     const float* c;
     const int32_t* c_lens;
     int q_group, B, Sq, Sc, D, slot;
+    int tile_pairs;  // pairs per warp tile (32 when the batch fills the machine, fewer for small batches)
     float inv_temp;
 };
 
@@ -70,6 +72,151 @@ __device__ __forceinline__ void transpose_reduce_w(float (&v)[NV], int lane) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Squared norms of the kFT rows of query `qidx` -> qn_s[0..kFT) (each half-warp takes kHR rows).
+__device__ __forceinline__ void query_norms(const FusedArgs& a, int qidx, int nq, int D, int lane, float* qn_s) {
+    const int h = lane >> 4, l16 = lane & 15, d4 = D >> 2;
+    const float4* qb = reinterpret_cast<const float4*>(a.q + (size_t)qidx * a.Sq * D) + (size_t)(kHR * h) * d4 + l16;
+    float2 s[kHR];
+#pragma unroll
+    for (int i = 0; i < kHR; ++i) s[i] = make_float2(0.f, 0.f);
+    for (int k = 0; k < d4; k += 16) {
+#pragma unroll
+        for (int i = 0; i < kHR; ++i) {
+            if (kHR * h + i < nq) {
+                const float4 v = __ldg(qb + (size_t)i * d4 + k);
+                s[i] = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), s[i]);
+                s[i] = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), s[i]);
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kHR; ++i) {
+        float t = s[i].x + s[i].y;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (l16 == 0) qn_s[kHR * h + i] = t;
+    }
+    __syncwarp();
+}
+
+// Phase 1 of one tile: distances of `npairs` pairs -> Cs[p][kCostLd].  FULL: all documents have kFT sentences.
+// Register plan per lane: 5x10 packed accumulators (100) + 10 packed candidate norms (20) + one 10-row candidate
+// slice (40, refilled row by row right after its last use so the next slice is in flight during the multiplies)
+// + two 5-row query slices (40, double buffered: L1 hits still cost ~30 cycles).
+template <int DT, bool FULL>
+__device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs, int my_ql, int my_cl, int lane, float* Cs,
+                                       float* red, float* qn_s) {
+    const int h = lane >> 4, l16 = lane & 15;
+    const int D = DT ? DT : a.D, d4 = D >> 2;
+    const int nit = d4 >> 4;  // 64-float slices per row (16 lanes x float4)
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float2 zero2 = make_float2(0.f, 0.f);
+    const int rev4 = (int)(__brev((unsigned)l16) >> 28);
+    const size_t doc = (size_t)a.Sc * D;  // floats per candidate document
+
+    float2 acc[kHR][kFT], cn[kFT];
+    float4 cv[kFT], qa[kHR], qb4[kHR];
+    int cur_q = -1, qslot = 0;  // qn_s holds two sets of query norms: pair_setup runs one pair ahead of the epilogue
+
+    // per-pair state (uniform across the warp)
+    int nq = kFT, nc = kFT, qidx = 0;
+    const float4* cptr = nullptr;  // candidate slice of the chunk being multiplied (+ j*d4 per row)
+    const float4* qptr = nullptr;  // query slice of the chunk being multiplied (+ i*d4 per row)
+
+    auto pair_setup = [&](int p) {
+        qidx = (base + p) / a.q_group;
+        if (!FULL) {
+            nq = __shfl_sync(0xffffffffu, my_ql, p);
+            nc = __shfl_sync(0xffffffffu, my_cl, p);
+        }
+        cptr = reinterpret_cast<const float4*>(a.c + (size_t)(base + p) * doc) + l16;
+        qptr = reinterpret_cast<const float4*>(a.q + (size_t)qidx * a.Sq * D) + (size_t)(kHR * h) * d4 + l16;
+        if (qidx != cur_q) {
+            qslot ^= 1;
+            query_norms(a, qidx, FULL ? kFT : nq, D, lane, qn_s + 16 * qslot);
+            cur_q = qidx;
+        }
+    };
+    auto load_q = [&](float4 (&dst)[kHR], const float4* src) {
+#pragma unroll
+        for (int i = 0; i < kHR; ++i) dst[i] = (FULL || kHR * h + i < nq) ? __ldg(src + (size_t)i * d4) : zero4;
+    };
+    // one 64-float slice: multiply with q (the slice's query rows), prefetch the following slice's rows into cv[]
+    auto slice = [&](const float4 (&q)[kHR], const float4* c_next, int nc_next) {
+#pragma unroll
+        for (int j = 0; j < kFT; ++j) {
+            const float2 c0 = make_float2(cv[j].x, cv[j].y), c1 = make_float2(cv[j].z, cv[j].w);
+#pragma unroll
+            for (int i = 0; i < kHR; ++i) acc[i][j] = __ffma2_rn(make_float2(q[i].x, q[i].y), c0, acc[i][j]);
+            cn[j] = __ffma2_rn(c0, c0, cn[j]);
+#pragma unroll
+            for (int i = 0; i < kHR; ++i) acc[i][j] = __ffma2_rn(make_float2(q[i].z, q[i].w), c1, acc[i][j]);
+            cn[j] = __ffma2_rn(c1, c1, cn[j]);
+            // row j of this slice is dead: refill its registers with row j of the next slice
+            if (c_next != nullptr) cv[j] = (FULL || j < nc_next) ? ldg_stream(c_next + (size_t)j * d4) : zero4;
+        }
+    };
+
+    pair_setup(0);
+#pragma unroll
+    for (int j = 0; j < kFT; ++j) cv[j] = (FULL || j < nc) ? ldg_stream(cptr + (size_t)j * d4) : zero4;
+    load_q(qa, qptr);
+
+    for (int p = 0; p < npairs; ++p) {
+#pragma unroll
+        for (int i = 0; i < kHR; ++i)
+#pragma unroll
+            for (int j = 0; j < kFT; ++j) acc[i][j] = zero2;
+#pragma unroll
+        for (int j = 0; j < kFT; ++j) cn[j] = zero2;
+        if (p + 1 < npairs) {  // pull the next pair's candidate rows into L2 (128-byte lines)
+            const char* nxt = reinterpret_cast<const char*>(a.c + (size_t)(base + p + 1) * doc);
+            const int nbytes = (FULL ? kFT : __shfl_sync(0xffffffffu, my_cl, (p + 1) & 31)) * D * 4;
+            for (int o = lane * 128; o < nbytes; o += 32 * 128) prefetch_l2(nxt + o);
+        }
+        const int nq_p = nq, nc_p = nc;  // lengths / query-norm slot of the pair being accumulated
+        const float* qn_p = qn_s + 16 * qslot;  // (pair_setup below moves on to the next pair)
+        // slices 0 .. nit-1 of this pair, two per iteration (query slices ping-pong between qa and qb4)
+        for (int it = 0; it < nit; it += 2) {
+            load_q(qb4, qptr + ((it + 1) << 4));                  // it+1 < nit because nit is even
+            slice(qa, cptr + ((it + 1) << 4), nc);
+            if (it + 2 < nit) {
+                load_q(qa, qptr + ((it + 2) << 4));
+                slice(qb4, cptr + ((it + 2) << 4), nc);
+            } else if (p + 1 < npairs) {  // last slice of the pair: the stream continues with the next pair
+                pair_setup(p + 1);
+                load_q(qa, qptr);
+                slice(qb4, cptr, nc);
+            } else {
+                slice(qb4, nullptr, 0);
+            }
+        }
+        // pair finished: reduce over each half-warp, turn Gram values into distances
+        float v[kRedVals];
+#pragma unroll
+        for (int i = 0; i < kHR; ++i)
+#pragma unroll
+            for (int j = 0; j < kFT; ++j) v[i * kFT + j] = acc[i][j].x + acc[i][j].y;
+#pragma unroll
+        for (int j = 0; j < kFT; ++j) v[kHR * kFT + j] = cn[j].x + cn[j].y;
+#pragma unroll
+        for (int e = kHR * kFT + kFT; e < kRedVals; ++e) v[e] = 0.f;
+        transpose_reduce_w<kRedVals, 16>(v, lane);
+        __syncwarp();  // the previous pair's readers of red[] are done
+#pragma unroll
+        for (int m = 0; m < kRedVals / 16; ++m) red[h * kRedVals + 16 * m + rev4] = v[m];
+        __syncwarp();
+        float* row = Cs + p * kCostLd;
+        for (int e = lane; e < kFT * kFT; e += 32) {
+            const int i = e / kFT, j = e - i * kFT;
+            const int hh = i / kHR, ii = i - hh * kHR;
+            const float d2 = qn_p[i] + red[kHR * kFT + j] - 2.f * red[hh * kRedVals + ii * kFT + j];
+            row[e] = (i < nq_p && j < nc_p) ? sqrtf(fmaxf(d2, 1e-8f)) : 1.0e30f;
+        }
+    }
+}
+
 // Phase 2 lives in its own (non-inlined) function so that it gets a register allocation of its own: the solver wants
 // ~200 registers for the 10x10 tile and the potentials, and must not share them with phase 1's live state.
 __device__ __noinline__ void fused_phase2(const float* row, int ql, int cl, int b, int Sq, int Sc, const float* eps_s,
@@ -78,7 +225,7 @@ __device__ __noinline__ void fused_phase2(const float* row, int ql, int cl, int 
                                 *out);
 }
 
-template <int DT>  // embedding size known at compile time (0 = runtime a.D); D % 64 == 0
+template <int DT>  // embedding size known at compile time (0 = runtime a.D); D % 128 == 0
 __global__ void __launch_bounds__(kFusedWarps * 32, 2)
 ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     extern __shared__ float smem[];
@@ -88,130 +235,31 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     if (threadIdx.x == 0) out_s = out;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int h = lane >> 4, l16 = lane & 15;
     float* Cs = smem + (size_t)warp * kWarpSmem;  // cost tile of this warp's 32 pairs
     float* red = Cs + 32 * kCostLd;               // [2][kRedVals] reduced Gram values of the pair being finished
-    float* qn_s = red + 2 * kRedVals;             // squared norms of the current query's rows
-    const int D = DT ? DT : a.D, d4 = D >> 2;
-    const int nit = d4 >> 4;  // 64-float slices per row (16 lanes x float4)
-    const int ntiles = (a.B + 31) >> 5;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float2 zero2 = make_float2(0.f, 0.f);
-    const int rev4 = (int)(__brev((unsigned)l16) >> 28);
+    float* qn_s = red + 2 * kRedVals;             // [2][16] squared norms of the current / next query's rows
+    const int ntiles = (a.B + a.tile_pairs - 1) / a.tile_pairs;
 
     for (;;) {
         int tile = 0;
         if (lane == 0) tile = (int)atomicAdd(&g_tile_counter[a.slot], 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
-        const int base = tile << 5;
-        const int npairs = min(32, a.B - base);
+        const int base = tile * a.tile_pairs;
+        const int npairs = min(a.tile_pairs, a.B - base);
         // lane p keeps the lengths of pair base+p
         int my_ql = 0, my_cl = 0;
         if (lane < npairs) {
             my_ql = min(max(a.q_lens[(base + lane) / a.q_group], 0), a.Sq);
             my_cl = min(max(a.c_lens[base + lane], 0), a.Sc);
         }
-        int cur_q = -1;  // query whose row norms are in qn_s
-
-        // ---------------- phase 1: cost tiles of the 32 pairs ------------------------------------------------
-        float2 acc[kHR][kFT], cn[kFT], qn[kHR];
-        float4 cv[kFT];
-        const int total = npairs * nit;
-        auto chunk_ptr = [&](int n, int& nc) -> const float4* {
-            const int p = n / nit, it = n - p * nit;
-            const int cl_p = __shfl_sync(0xffffffffu, my_cl, p & 31);  // every lane takes part in the shuffle
-            nc = (n < total) ? cl_p : 0;
-            return reinterpret_cast<const float4*>(a.c + (size_t)(base + p) * a.Sc * D) + (it << 4) + l16;
-        };
-        {
-            int nc0;
-            const float4* cb0 = chunk_ptr(0, nc0);
-#pragma unroll
-            for (int j = 0; j < kFT; ++j) cv[j] = (j < nc0) ? ldg_stream(cb0 + (size_t)j * d4) : zero4;
-        }
-        bool need_qn = false;
-        for (int n = 0; n < total; ++n) {
-            const int p = n / nit, it = n - p * nit;
-            const int nq = __shfl_sync(0xffffffffu, my_ql, p), nc = __shfl_sync(0xffffffffu, my_cl, p);
-            const int qidx = (base + p) / a.q_group;
-            int nc_next;
-            const float4* cb_next = chunk_ptr(n + 1, nc_next);
-            if (it == 0) {
-#pragma unroll
-                for (int i = 0; i < kHR; ++i) {
-                    qn[i] = zero2;
-#pragma unroll
-                    for (int j = 0; j < kFT; ++j) acc[i][j] = zero2;
-                }
-#pragma unroll
-                for (int j = 0; j < kFT; ++j) cn[j] = zero2;
-                need_qn = (qidx != cur_q);
-                if (p + 1 < npairs) {  // pull the next pair's candidate rows into L2 (128-byte lines)
-                    const char* nxt = reinterpret_cast<const char*>(a.c + (size_t)(base + p + 1) * a.Sc * D);
-                    const int nbytes = __shfl_sync(0xffffffffu, my_cl, (p + 1) & 31) * D * 4;
-                    for (int o = lane * 128; o < nbytes; o += 32 * 128) prefetch_l2(nxt + o);
-                }
-            }
-            const float4* qb = reinterpret_cast<const float4*>(a.q + (size_t)qidx * a.Sq * D) + (size_t)(kHR * h) * d4 +
-                               (it << 4) + l16;
-            float4 qv[kHR];
-#pragma unroll
-            for (int i = 0; i < kHR; ++i) qv[i] = (kHR * h + i < nq) ? __ldg(qb + (size_t)i * d4) : zero4;
-#pragma unroll
-            for (int j = 0; j < kFT; ++j) {
-                const float4 cj = cv[j];
-                cv[j] = (j < nc_next) ? ldg_stream(cb_next + (size_t)j * d4) : zero4;
-                const float2 c0 = make_float2(cj.x, cj.y), c1 = make_float2(cj.z, cj.w);
-#pragma unroll
-                for (int i = 0; i < kHR; ++i) {
-                    acc[i][j] = __ffma2_rn(make_float2(qv[i].x, qv[i].y), c0, acc[i][j]);
-                    acc[i][j] = __ffma2_rn(make_float2(qv[i].z, qv[i].w), c1, acc[i][j]);
-                }
-                cn[j] = __ffma2_rn(c0, c0, cn[j]);
-                cn[j] = __ffma2_rn(c1, c1, cn[j]);
-            }
-            if (need_qn) {
-#pragma unroll
-                for (int i = 0; i < kHR; ++i) {
-                    qn[i] = __ffma2_rn(make_float2(qv[i].x, qv[i].y), make_float2(qv[i].x, qv[i].y), qn[i]);
-                    qn[i] = __ffma2_rn(make_float2(qv[i].z, qv[i].w), make_float2(qv[i].z, qv[i].w), qn[i]);
-                }
-            }
-            if (it == nit - 1) {  // pair finished: reduce over each half-warp, turn Gram values into distances
-                float v[kRedVals];
-#pragma unroll
-                for (int i = 0; i < kHR; ++i)
-#pragma unroll
-                    for (int j = 0; j < kFT; ++j) v[i * kFT + j] = acc[i][j].x + acc[i][j].y;
-#pragma unroll
-                for (int j = 0; j < kFT; ++j) v[kHR * kFT + j] = cn[j].x + cn[j].y;
-#pragma unroll
-                for (int e = kHR * kFT + kFT; e < kRedVals; ++e) v[e] = 0.f;
-                transpose_reduce_w<kRedVals, 16>(v, lane);
-                __syncwarp();  // the previous pair's readers of red[] are done
-#pragma unroll
-                for (int m = 0; m < kRedVals / 16; ++m) red[h * kRedVals + 16 * m + rev4] = v[m];
-                if (need_qn) {  // once per (tile, query): row norms of the query, reduced over the 16 lanes
-#pragma unroll
-                    for (int i = 0; i < kHR; ++i) {
-                        float s = qn[i].x + qn[i].y;
-#pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                        if (l16 == 0) qn_s[kHR * h + i] = s;
-                    }
-                    cur_q = qidx;
-                }
-                __syncwarp();
-                float* row = Cs + p * kCostLd;
-                for (int e = lane; e < kFT * kFT; e += 32) {
-                    const int i = e / kFT, j = e - i * kFT;
-                    const int hh = i / kHR, ii = i - hh * kHR;
-                    const float d2 = qn_s[i] + red[kHR * kFT + j] - 2.f * red[hh * kRedVals + ii * kFT + j];
-                    row[e] = (i < nq && j < nc) ? sqrtf(fmaxf(d2, 1e-8f)) : 1.0e30f;
-                }
-            }
-        }
+        // uniform fast path: every pair of the tile has all kFT x kFT sentences (no predicates, no zero fill)
+        const bool full_tile = __all_sync(0xffffffffu, lane >= npairs || (my_ql == kFT && my_cl == kFT)) &&
+                               a.Sq == kFT && a.Sc == kFT;
+        if (full_tile)
+            phase1<DT, true>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s);
+        else
+            phase1<DT, false>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s);
         __syncwarp();
 
         // ---------------- phase 2: one pair per thread ---------------------------------------------------------
@@ -231,7 +279,7 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     }
 }
 
-bool ot_fused_supported(int Sq, int Sc, int D) { return Sq <= kFT && Sc <= kFT && D >= 64 && (D % 64) == 0; }
+bool ot_fused_supported(int Sq, int Sc, int D) { return Sq <= kFT && Sc <= kFT && D >= 128 && (D % 128) == 0; }
 
 int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens, int B,
                     int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out, cudaStream_t stream) {
@@ -245,10 +293,14 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
         ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_dev = dev;
     }
-    FusedArgs a{q, q_lens, c, c_lens, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), 1.0f / temp};
-    const int ntiles = (B + 31) / 32;
+    // Tile size: 32 pairs per warp once the batch can feed every resident warp; smaller batches are spread over more
+    // warps (down to one pair per warp) so that a single-query call (1 x 1k candidates) still uses the whole GPU.
     const int max_ctas = 2 * sm_count();
-    const int ctas = min(max_ctas, (ntiles + kFusedWarps - 1) / kFusedWarps);
+    const int tile_pairs = std::min(32, std::max(1, (B + max_ctas * kFusedWarps - 1) / (max_ctas * kFusedWarps)));
+    FusedArgs a{q, q_lens, c, c_lens, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), tile_pairs,
+                1.0f / temp};
+    const int ntiles = (B + tile_pairs - 1) / tile_pairs;
+    const int ctas = std::min(max_ctas, (ntiles + kFusedWarps - 1) / kFusedWarps);
     if (D == 768)
         ot_fused_kernel<768><<<ctas, kFusedWarps * 32, smem, stream>>>(a, sched, out);
     else
@@ -267,6 +319,7 @@ extern "C" size_t asp_ot_score_workspace_bytes(int B, int Sq, int Sc, int D) {
 extern "C" int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
                             int B, int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp,
                             const asp_ot_outputs* out, void* workspace, size_t workspace_bytes, asp_stream_t stream) {
+    if (B == 0) return ASP_OK;
     int rc = asp::check_pair_args(q, q_lens, c, c_lens, B, Sq, Sc, D);
     if (rc) return rc;
     ASP_REQUIRE(out, "asp_ot_score: out is NULL");

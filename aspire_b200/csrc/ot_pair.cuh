@@ -41,20 +41,18 @@ __device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql, int
     const float t = kLog2e / eps;
     const float scale = weight * eps * kLn2;
     const float2 t2 = dup2(t), nt2 = dup2(-t), nscale2 = dup2(-scale);
-    float u[TQ];
     float2 v[TP], S[TP];
-#pragma unroll
-    for (int i = 0; i < TQ; ++i) u[i] = fmaf(st.f[i], t, st.la[i]);
 #pragma unroll
     for (int j = 0; j < TP; ++j) {
         v[j] = __ffma2_rn(st.g[j], t2, st.lb[j]);
         S[j] = f2(0.f, 0.f);
     }
-    bool bad = false;
+    // `chk` accumulates the log-sums of the valid rows / columns: it leaves the finite range iff one of them did
+    float chk = 0.f;
     float fnew[TQ];
 #pragma unroll
     for (int i = 0; i < TQ; ++i) {
-        const float2 uu = dup2(u[i]);
+        const float2 uu = dup2(fmaf(st.f[i], t, st.la[i]));
         float2 R = f2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < TP; ++j) {
@@ -65,20 +63,24 @@ __device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql, int
         }
         const float l = lg2(R.x + R.y);
         fnew[i] = fmaf(-scale, l - st.la[i], st.f[i]);
-        bad |= (i < ql) && !(fabsf(l) < 1e30f);
+        chk += (i < ql) ? fabsf(l) : 0.f;
     }
     float2 gnew[TP];
 #pragma unroll
     for (int j = 0; j < TP; ++j) {
         const float2 l = f2(lg2(S[j].x), lg2(S[j].y));
         gnew[j] = __ffma2_rn(nscale2, __fadd2_rn(l, f2(-st.lb[j].x, -st.lb[j].y)), st.g[j]);
-        bad |= (2 * j < cl) && !(fabsf(l.x) < 1e30f);
-        bad |= (2 * j + 1 < cl) && !(fabsf(l.y) < 1e30f);
+        chk += (2 * j < cl) ? fabsf(l.x) : 0.f;
+        chk += (2 * j + 1 < cl) ? fabsf(l.y) : 0.f;
     }
+    const bool bad = !(chk < 1e30f);
     if (__builtin_expect(bad, 0)) {
         // max-stabilised recomputation of both half-steps from the old potentials (rare).  Padded rows/columns
         // carry log-weight -1e5 and vanish from every sum, exactly as in the reference.
         const float nt = -t;
+        float u[TQ];
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) u[i] = fmaf(st.f[i], t, st.la[i]);
 #pragma unroll
         for (int i = 0; i < TQ; ++i) {
             float m = -INFINITY, s = 0.f;

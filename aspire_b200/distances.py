@@ -120,6 +120,27 @@ def l2max_scores(q, q_lens, c, c_lens, broadcast_query=False, want_pair_sims=Fal
     return best, idx, sims
 
 
+def l2max_allpairs(q, q_lens, c, c_lens, want_idx=True):
+    """tsAspire for EVERY (query, candidate) pair on the tensor cores (``asp_l2max_allpairs``).
+
+    q [NQ,S,D], c [NC,S,D] contiguous fp32 CUDA (same S, zero padded), lens int32 CUDA.
+    Returns (scores fp32 [NQ,NC] = max -dist, flat argmax int32 [NQ,NC] = i*S+j or None).
+    """
+    _abi.require_cuda(q, c, q_lens, c_lens)
+    NQ, S, D = q.shape
+    NC = c.shape[0]
+    assert c.shape[1] == S and c.shape[2] == D and q.is_contiguous() and c.is_contiguous()
+    dev = c.device
+    L = _abi.lib()
+    scores = torch.empty((NQ, NC), dtype=torch.float32, device=dev)
+    idx = torch.empty((NQ, NC), dtype=torch.int32, device=dev) if want_idx else None
+    ws = torch.empty(int(L.asp_l2max_allpairs_workspace_bytes(NQ, NC, S, D)), dtype=torch.uint8, device=dev)
+    _abi.check(L.asp_l2max_allpairs(_abi.ptr(q), _abi.ptr(q_lens), NQ, _abi.ptr(c), _abi.ptr(c_lens), NC, S, D,
+                                    _abi.ptr(scores), _abi.ptr(idx), _abi.ptr(ws), ws.numel(), _abi.stream_of(dev)),
+               "asp_l2max_allpairs")
+    return scores, idx
+
+
 class AllPairMaskedWasserstein:
     """Drop-in for pair_distances.AllPairMaskedWasserstein (same hparam keys and defaults, :15-19).
 

@@ -126,6 +126,20 @@ int asp_l2max(const float* q, const int32_t* q_lens, int q_broadcast, const floa
               int B, int Sq, int Sc, int D, float* best, int32_t* flat_idx, float* pair_sims,
               asp_stream_t stream);
 
+/* ---- K2+K3 ALL PAIRS: tsAspire scores of every query document against every candidate document -------------
+ * Replaces the numpy ranking path src/pre_process/pp_gen_nearest.py:939-961 (`-cdist(query_sents, pool_sents)`
+ * then a per-candidate column-slice np.max; all-queries x all-corpus variant :788-816) and
+ * allpair_masked_dist_l2max (pair_distances.py:138-186) applied to all NQ x NC pairs: one tcgen05 contraction
+ * [NQ*S, D] x [D, NC*S] with fp32-equivalent (bf16x3) products and a segmented max epilogue.
+ * q [NQ,S,D], c [NC,S,D] zero padded fp32, lens int32; S in [10,64], D % 64 == 0.
+ * scores [NQ,NC] = max_{i<ql,j<cl} -||q_i-c_j|| (-1e9 if a side is empty); flat_idx [NQ,NC] (optional) = i*S+j
+ * of the first maximum.  workspace: asp_l2max_allpairs_workspace_bytes() of device scratch (bf16 hi/lo copies).
+ */
+size_t asp_l2max_allpairs_workspace_bytes(int NQ, int NC, int S, int D);
+int asp_l2max_allpairs(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens, int NC,
+                       int S, int D, float* scores, int32_t* flat_idx, void* workspace, size_t workspace_bytes,
+                       asp_stream_t stream);
+
 /* ---- K2+K4: otAspire masked Sinkhorn optimal transport -----------------------------------------
  * Replaces AllPairMaskedWasserstein.compute_distance, src/learning/facetid_models/pair_distances.py:21-92
  * (release copy examples/ex_aspire_consent_multimatch.py:118-189) INCLUDING the third-party solver it

@@ -93,3 +93,39 @@ def test_large_batch_property():
         assert abs(-blk.min().item() - best[b].item()) < 2e-5
         i, j = divmod(int(idx[b]), 10)
         assert abs(blk[i, j].item() - blk.min().item()) < 1e-5
+
+
+@pytest.mark.parametrize("NQ,NC,S,D", [(30, 500, 10, 768), (13, 161, 10, 128), (5, 40, 12, 256)])
+def test_allpairs_tensor_core_path_vs_pair_kernel_and_fp64(NQ, NC, S, D):
+    """Config-3 shape (all queries x all candidates, tcgen05 bf16x3): scores within 2e-5 of the exact-fp32 pair
+    kernel and of an fp64 cdist; flat argmax identical except fp64 near-ties (< 1e-5)."""
+    from aspire_b200 import l2max_allpairs, l2max_scores
+    g = torch.Generator().manual_seed(NQ * 7 + NC)
+    q = 0.3 * torch.randn(NQ, S, D, generator=g)
+    c = 0.3 * torch.randn(NC, S, D, generator=g)
+    ql = torch.randint(1, S + 1, (NQ,), generator=g).int()
+    cl = torch.randint(0, S + 1, (NC,), generator=g).int()
+    cl[:3] = S
+    for b in range(NQ):
+        q[b, ql[b]:] = 0
+    for b in range(NC):
+        c[b, cl[b]:] = 0
+    # plant near-duplicates so some pairs have a sharp best match
+    c[5, 0] = q[2, 1] + 0.01 * torch.randn(D, generator=g)
+    scores, idx = l2max_allpairs(q.cuda(), ql.cuda(), c.cuda(), cl.cuda())
+    torch.cuda.synchronize()
+    d = torch.cdist(q.double().reshape(1, NQ * S, D), c.double().reshape(1, NC * S, D))[0].reshape(NQ, S, NC, S)
+    valid = (torch.arange(S)[None, :, None, None] < ql[:, None, None, None]) & \
+            (torch.arange(S)[None, None, None, :] < cl[None, None, :, None])
+    neg = torch.where(valid, -d, torch.full_like(d, -1e9)).permute(0, 2, 1, 3).reshape(NQ, NC, S * S)
+    ref, ref_idx = neg.max(dim=2)
+    got = scores.cpu().double()
+    assert (got - ref).abs().max().item() <= 2e-5
+    top2 = neg.topk(2, dim=2)[0]
+    clear = (top2[..., 0] - top2[..., 1]) > 1e-5
+    assert (idx.cpu().long()[clear] == ref_idx[clear]).all()
+    empty = (cl == 0)
+    assert (scores.cpu()[:, empty] == -1e9).all() and (idx.cpu()[:, empty] == 0).all()
+    # one query through the streaming pair kernel (exact fp32 FMA) agrees too
+    best, pidx, _ = l2max_scores(q[2:3].cuda(), ql[2:3].cuda(), c.cuda(), cl.cuda(), broadcast_query=True)
+    assert (best.cpu() - scores.cpu()[2]).abs().max().item() <= 2e-5

@@ -1,0 +1,47 @@
+"""Developer benchmark of the sm_100a BERT encoder (not the judged bench): docs/s and TFLOP/s per precision mode,
+next to the HF module run by PyTorch (cuBLAS / SDPA library kernels) on the same GPU."""
+import sys
+import time
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from oracle import ref_shims
+from aspire_b200.encoder import B200BertEncoder
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    quick = "--quick" in sys.argv
+    model = ref_shims.seeded_bert(seed=0, num_hidden_layers=12)
+    enc = B200BertEncoder(model)
+    hf32 = model.cuda().float()
+    for B, L in ([(32, 256)] if quick else [(8, 256), (32, 256), (32, 512), (128, 256)]):
+        ids = torch.randint(1000, 31000, (B, L)).cuda()
+        lens = torch.full((B,), L, dtype=torch.int32).cuda()
+        mask = torch.ones((B, L), dtype=torch.long).cuda()
+        flops = B * L * (2 * 85.05e6 + 12 * 4 * L * 768)
+        out = {}
+        for prec in ("bf16", "bf16x3"):
+            out[prec] = timeit(lambda: enc.forward(ids, lens, precision=prec))
+        if not quick:
+            with torch.no_grad():
+                out["hf_fp32"] = timeit(lambda: hf32(ids, attention_mask=mask).last_hidden_state, iters=3, warm=1)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    out["hf_autocast_bf16"] = timeit(lambda: hf32(ids, attention_mask=mask).last_hidden_state, iters=3, warm=1)
+        print(f"B={B} L={L} ({flops / 1e12:.2f} TFLOP): " + "  ".join(
+            f"{k} {v:.3f} ms ({B / v * 1e3:.0f} docs/s, {flops / v / 1e9:.0f} TFLOP/s)" for k, v in out.items()), flush=True)
+
+
+if __name__ == "__main__":
+    main()
