@@ -9,7 +9,8 @@
 // documents and a 160-column B tile floor(160/S) whole candidate documents (12 x 16 documents per CTA at S = 10).
 // Main loop = gemm.cu's (TMA 128B-swizzled boxes -> 4-stage mbarrier ring -> tcgen05.mma, fp32 accumulator in TMEM),
 // with fp32-equivalent bf16x3 operands: the fp32 representations are split once (split_rows_kernel) into bf16 hi / lo
-// halves + exact fp32 squared norms, and every K block accumulates hi.hi + hi.lo + lo.hi.
+// halves + exact fp32 squared norms, and every K block accumulates hi.hi + hi.lo + lo.hi + lo.lo (the last term is
+// coherent -- not noise -- when a query sentence nearly equals a candidate sentence, so it is kept here).
 // Epilogue: each thread owns one query-sentence row of the accumulator: d^2 = |q|^2 + |c|^2 - 2 q.c, running
 // (min d^2, first j) per candidate document -> shared memory -> min over the query document's rows (first i on ties,
 // i.e. the flat index i*S+j of the first maximum, pair_distances.py:176) -> score = -sqrt(max(d^2, 1e-8)).
@@ -26,7 +27,6 @@ constexpr int kApStages = 4;
 constexpr int kApBlockM = 128, kApBlockN = 160, kApBlockK = 64;
 constexpr int kApABytes = kApBlockM * kApBlockK * 2, kApBBytes = kApBlockN * kApBlockK * 2;
 constexpr int kApStage = kApABytes + kApBBytes;
-constexpr int kApMaxDocsN = 80;  // floor(160 / 2)
 constexpr int kApSmem = kApStages * kApStage + 128 + kApBlockM * 17 * 8 + 1024;
 
 struct AllPairsArgs {
@@ -36,6 +36,8 @@ struct AllPairsArgs {
     const int32_t* c_lens;  // [NC]
     int NQ, NC, S, D;
     int docs_m, docs_n;     // whole documents per tile
+    const float* q;         // original fp32 rows (exact re-evaluation of strongly cancelling minima)
+    const float* c;
     float* scores;          // [NQ, NC]
     int32_t* flat_idx;      // [NQ, NC] or NULL
 };
@@ -83,7 +85,7 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
     const int qd0 = blockIdx.x * g.docs_m, cd0 = blockIdx.y * g.docs_n;  // first query / candidate document of the tile
     const int m0 = qd0 * S, n0 = cd0 * S;
     const int rows_m = g.docs_m * S, cols_n = g.docs_n * S;
-    const int total = (g.D / kApBlockK) * 3;
+    const int total = (g.D / kApBlockK) * 4;  // hi.hi, hi.lo, lo.hi, lo.lo per K block
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tq_hi);
@@ -104,12 +106,12 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
     if (warp == 0 && lane == 0) {
         for (int it = 0; it < total; ++it) {
             const int s = it % kApStages, ph = (it / kApStages) & 1;
-            const int kb = it / 3, term = it - kb * 3;
+            const int kb = it >> 2, term = it & 3;
             mbar_wait(&empty[s], ph ^ 1);
             mbar_arrive_expect_tx(&full[s], (uint32_t)(rows_m + cols_n) * (kApBlockK * 2));
             uint8_t* sa = smem + s * kApStage;
-            tma_load_2d(sa, term == 2 ? &tq_lo : &tq_hi, &full[s], kb * kApBlockK, m0);
-            tma_load_2d(sa + kApABytes, term == 1 ? &tc_lo : &tc_hi, &full[s], kb * kApBlockK, n0);
+            tma_load_2d(sa, (term & 2) ? &tq_lo : &tq_hi, &full[s], kb * kApBlockK, m0);
+            tma_load_2d(sa + kApABytes, (term & 1) ? &tc_lo : &tc_hi, &full[s], kb * kApBlockK, n0);
         }
     } else if (warp == 1 && lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(kApBlockM, kApBlockN);
@@ -183,6 +185,22 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
             }
         }
         const bool any = ql > 0 && cl > 0 && bd < INFINITY;
+        if (any) {
+            // |q|^2 + |c|^2 - 2 q.c loses its digits when q ~ c (near-duplicate sentences): re-evaluate such a
+            // minimum as sum (q-c)^2 in fp32 from the original rows (rare; exact where the ranking is decided)
+            const size_t qrow = (size_t)gq * S + bi / S, crow = (size_t)gc * S + bi % S;
+            if (bd < 0.01f * (__ldg(g.qn + qrow) + __ldg(g.cn + crow))) {
+                const float4* qr = reinterpret_cast<const float4*>(g.q + qrow * g.D);
+                const float4* cr = reinterpret_cast<const float4*>(g.c + crow * g.D);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                for (int k4 = 0; k4 < (g.D >> 2); ++k4) {
+                    const float4 x = __ldg(qr + k4), y = __ldg(cr + k4);
+                    const float d0 = x.x - y.x, d1 = x.y - y.y, d2_ = x.z - y.z, d3 = x.w - y.w;
+                    s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2_, d2_, s2); s3 = fmaf(d3, d3, s3);
+                }
+                bd = (s0 + s1) + (s2 + s3);
+            }
+        }
         g.scores[(size_t)gq * g.NC + gc] = any ? -sqrtf(fmaxf(bd, 1e-8f)) : kPadNeg;
         if (g.flat_idx) g.flat_idx[(size_t)gq * g.NC + gc] = any ? bi : 0;
     }
@@ -227,7 +245,7 @@ extern "C" int asp_l2max_allpairs(const float* q, const int32_t* q_lens, int NQ,
     if ((rc = make_tmap_bf16(&tq_lo, q_lo, qrows, D, docs_m * S))) return rc;
     if ((rc = make_tmap_bf16(&tc_hi, c_hi, crows, D, docs_n * S))) return rc;
     if ((rc = make_tmap_bf16(&tc_lo, c_lo, crows, D, docs_n * S))) return rc;
-    AllPairsArgs g{qn, cn, q_lens, c_lens, NQ, NC, S, D, docs_m, docs_n, scores, flat_idx};
+    AllPairsArgs g{qn, cn, q_lens, c_lens, NQ, NC, S, D, docs_m, docs_n, q, c, scores, flat_idx};
     static thread_local int attr_dev = -1;
     int dev = 0;
     ASP_CUDA(cudaGetDevice(&dev));

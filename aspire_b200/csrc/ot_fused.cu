@@ -12,10 +12,9 @@
 //   * persistent grid of independent WARPS (2 CTAs x 4 warps per SM); a warp takes tiles of 32 pairs from a global
 //     atomic counter, so memory-phase warps and math-phase warps of the same SM overlap (FMA pipe vs MUFU pipe);
 //   * phase 1 (streaming): for each of its 32 pairs the two HALF-WARPS take 5 query rows each and their 16 lanes
-//     split the embedding dimension; candidate rows arrive through 128-bit non-allocating loads (both halves read the
-//     same addresses, so a row still crosses L2->SM once), the next 10-row slice is always in flight while the current
-//     one is multiplied (slot j of cv[] is refilled as soon as row j has been consumed; the stream runs across pair
-//     boundaries) and the pair after that is prefetched into L2.  The 5x10 Gram tile + squared norms accumulate in
+//     split the embedding dimension; candidate rows are staged by cp.async through a per-warp shared-memory ring
+//     (4 slices = 10 KB in flight per warp, ~80 KB per SM: enough bytes in flight for HBM latency; the stream runs
+//     across pair boundaries) and read back with one 128-bit LDS per row.  The 5x10 Gram tile + squared norms accumulate in
 //     packed fp32 (FFMA2: two k-partials per register pair), are transpose-reduced over the 16 lanes and leave
 //     sqrt(max(|q|^2+|c|^2-2q.c, 1e-8)) in a shared cost tile [32][101] (odd stride: conflict-free in phase 2);
 //   * phase 2 (math): each THREAD solves one pair entirely in registers (ot_pair.cuh): one ex2 per (i,j)
@@ -33,7 +32,10 @@ constexpr int kHR = kFT / 2;   // query rows per half-warp
 constexpr int kFusedWarps = 4; // warps per CTA
 constexpr int kCostLd = 101;   // floats per pair in the shared cost tile
 constexpr int kRedVals = 64;   // 50 dot products + 10 candidate norms, padded for the 16-lane transpose-reduce
-constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 32;  // cost tile + reduced values per half + 2 x query norms
+constexpr int kRing = 5;                   // candidate slices in the per-warp cp.async ring (kRing-1 in flight)
+constexpr int kSliceFloats = kFT * 64;     // one slice: 64 floats of each of the kFT rows
+constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 32 + kRing * kSliceFloats;  // cost tile, reduced values per
+                                                                                   // half, 2 x query norms, the ring
 constexpr int kCounterSlots = 256;
 
 __device__ unsigned int g_tile_counter[kCounterSlots];
@@ -100,13 +102,26 @@ __device__ __forceinline__ void query_norms(const FusedArgs& a, int qidx, int nq
     __syncwarp();
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Phase 1 of one tile: distances of `npairs` pairs -> Cs[p][kCostLd].  FULL: all documents have kFT sentences.
-// Register plan per lane: 5x10 packed accumulators (100) + 10 packed candidate norms (20) + one 10-row candidate
-// slice (40, refilled row by row right after its last use so the next slice is in flight during the multiplies)
-// + two 5-row query slices (40, double buffered: L1 hits still cost ~30 cycles).
+//
+// The candidate rows stream through a per-warp shared-memory ring of kRing slices (one slice = the same 64 floats of
+// all kFT rows = 2.5 KB) filled with cp.async (16 B per lane, L1 bypassed): kRing-1 slices are always in flight per
+// warp (~80 KB per SM), which is what Little's law asks for at HBM latency -- registers could only hold one slice
+// ahead.  The stream runs straight across pair boundaries of the tile.
+// Register plan per lane: 5x10 packed accumulators (100) + 10 packed candidate norms (20) + the current candidate
+// slice (40, read from the ring with one 128-bit LDS per row; lanes l and l+16 read the same address) + two 5-row
+// query slices (40, double buffered loads through L1).
 template <int DT, bool FULL>
 __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs, int my_ql, int my_cl, int lane, float* Cs,
-                                       float* red, float* qn_s) {
+                                       float* red, float* qn_s, float* ring) {
     const int h = lane >> 4, l16 = lane & 15;
     const int D = DT ? DT : a.D, d4 = D >> 2;
     const int nit = d4 >> 4;  // 64-float slices per row (16 lanes x float4)
@@ -116,13 +131,34 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
     const size_t doc = (size_t)a.Sc * D;  // floats per candidate document
 
     float2 acc[kHR][kFT], cn[kFT];
-    float4 cv[kFT], qa[kHR], qb4[kHR];
+    float4 qa[kHR], qb4[kHR];
     int cur_q = -1, qslot = 0;  // qn_s holds two sets of query norms: pair_setup runs one pair ahead of the epilogue
+
+    // ---- producer side of the ring: slices are issued in stream order (pair ip, slice iit) ----
+    int ip = 0, iit = 0, islot = 0;
+    auto issue_next = [&]() {
+        if (ip < npairs) {
+            const int ncp = FULL ? kFT : __shfl_sync(0xffffffffu, my_cl, ip);
+            const float* src = a.c + (size_t)(base + ip) * doc + (iit << 6);
+            float* dst = ring + islot * kSliceFloats;
+#pragma unroll
+            for (int m = 0; m < kFT * 16 / 32; ++m) {  // 160 16-byte pieces per slice, 5 per lane
+                const int id = lane + 32 * m, row = id >> 4, c16 = id & 15;
+                if (FULL || row < ncp) cp_async16(dst + id * 4, src + (size_t)row * D + c16 * 4);
+            }
+            if (++iit == nit) {
+                iit = 0;
+                ++ip;
+            }
+        }
+        cp_async_commit();  // always commit: the wait below counts groups
+        islot = (islot + 1 == kRing) ? 0 : islot + 1;
+    };
+    int cslot = 0;
 
     // per-pair state (uniform across the warp)
     int nq = kFT, nc = kFT, qidx = 0;
-    const float4* cptr = nullptr;  // candidate slice of the chunk being multiplied (+ j*d4 per row)
-    const float4* qptr = nullptr;  // query slice of the chunk being multiplied (+ i*d4 per row)
+    const float4* qptr = nullptr;  // query slice 0 of the pair being multiplied (+ i*d4 per row, + 16 per slice)
 
     auto pair_setup = [&](int p) {
         qidx = (base + p) / a.q_group;
@@ -130,7 +166,6 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
             nq = __shfl_sync(0xffffffffu, my_ql, p);
             nc = __shfl_sync(0xffffffffu, my_cl, p);
         }
-        cptr = reinterpret_cast<const float4*>(a.c + (size_t)(base + p) * doc) + l16;
         qptr = reinterpret_cast<const float4*>(a.q + (size_t)qidx * a.Sq * D) + (size_t)(kHR * h) * d4 + l16;
         if (qidx != cur_q) {
             qslot ^= 1;
@@ -142,8 +177,17 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 #pragma unroll
         for (int i = 0; i < kHR; ++i) dst[i] = (FULL || kHR * h + i < nq) ? __ldg(src + (size_t)i * d4) : zero4;
     };
-    // one 64-float slice: multiply with q (the slice's query rows), prefetch the following slice's rows into cv[]
-    auto slice = [&](const float4 (&q)[kHR], const float4* c_next, int nc_next) {
+    // one 64-float slice of the current pair (nc_cur rows valid): wait for it, refill the slot freed by the previous
+    // slice, pull the rows out of the ring and multiply with the query slice q
+    auto slice = [&](const float4 (&q)[kHR], int nc_cur) {
+        cp_async_wait<kRing - 2>();
+        __syncwarp();
+        issue_next();
+        const float4* sl = reinterpret_cast<const float4*>(ring + cslot * kSliceFloats) + l16;
+        cslot = (cslot + 1 == kRing) ? 0 : cslot + 1;
+        float4 cv[kFT];
+#pragma unroll
+        for (int j = 0; j < kFT; ++j) cv[j] = (FULL || j < nc_cur) ? sl[j * 16] : zero4;
 #pragma unroll
         for (int j = 0; j < kFT; ++j) {
             const float2 c0 = make_float2(cv[j].x, cv[j].y), c1 = make_float2(cv[j].z, cv[j].w);
@@ -153,14 +197,12 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 #pragma unroll
             for (int i = 0; i < kHR; ++i) acc[i][j] = __ffma2_rn(make_float2(q[i].z, q[i].w), c1, acc[i][j]);
             cn[j] = __ffma2_rn(c1, c1, cn[j]);
-            // row j of this slice is dead: refill its registers with row j of the next slice
-            if (c_next != nullptr) cv[j] = (FULL || j < nc_next) ? ldg_stream(c_next + (size_t)j * d4) : zero4;
         }
     };
 
+#pragma unroll 1
+    for (int k = 0; k < kRing - 1; ++k) issue_next();
     pair_setup(0);
-#pragma unroll
-    for (int j = 0; j < kFT; ++j) cv[j] = (FULL || j < nc) ? ldg_stream(cptr + (size_t)j * d4) : zero4;
     load_q(qa, qptr);
 
     for (int p = 0; p < npairs; ++p) {
@@ -170,27 +212,19 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
             for (int j = 0; j < kFT; ++j) acc[i][j] = zero2;
 #pragma unroll
         for (int j = 0; j < kFT; ++j) cn[j] = zero2;
-        if (p + 1 < npairs) {  // pull the next pair's candidate rows into L2 (128-byte lines)
-            const char* nxt = reinterpret_cast<const char*>(a.c + (size_t)(base + p + 1) * doc);
-            const int nbytes = (FULL ? kFT : __shfl_sync(0xffffffffu, my_cl, (p + 1) & 31)) * D * 4;
-            for (int o = lane * 128; o < nbytes; o += 32 * 128) prefetch_l2(nxt + o);
-        }
-        const int nq_p = nq, nc_p = nc;  // lengths / query-norm slot of the pair being accumulated
+        const int nq_p = nq, nc_p = nc;         // lengths / query-norm slot of the pair being accumulated
         const float* qn_p = qn_s + 16 * qslot;  // (pair_setup below moves on to the next pair)
         // slices 0 .. nit-1 of this pair, two per iteration (query slices ping-pong between qa and qb4)
         for (int it = 0; it < nit; it += 2) {
-            load_q(qb4, qptr + ((it + 1) << 4));                  // it+1 < nit because nit is even
-            slice(qa, cptr + ((it + 1) << 4), nc);
+            load_q(qb4, qptr + ((it + 1) << 4));  // it+1 < nit because nit is even
+            slice(qa, nc_p);
             if (it + 2 < nit) {
                 load_q(qa, qptr + ((it + 2) << 4));
-                slice(qb4, cptr + ((it + 2) << 4), nc);
-            } else if (p + 1 < npairs) {  // last slice of the pair: the stream continues with the next pair
+            } else if (p + 1 < npairs) {  // last slice of the pair: fetch the next pair's first query slice
                 pair_setup(p + 1);
                 load_q(qa, qptr);
-                slice(qb4, cptr, nc);
-            } else {
-                slice(qb4, nullptr, 0);
             }
+            slice(qb4, nc_p);
         }
         // pair finished: reduce over each half-warp, turn Gram values into distances
         float v[kRedVals];
@@ -215,6 +249,8 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
             row[e] = (i < nq_p && j < nc_p) ? sqrtf(fmaxf(d2, 1e-8f)) : 1.0e30f;
         }
     }
+    cp_async_wait<0>();  // only empty groups can still be pending; leave the ring quiescent for the next tile
+    __syncwarp();
 }
 
 // Phase 2 lives in its own (non-inlined) function so that it gets a register allocation of its own: the solver wants
@@ -238,6 +274,7 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     float* Cs = smem + (size_t)warp * kWarpSmem;  // cost tile of this warp's 32 pairs
     float* red = Cs + 32 * kCostLd;               // [2][kRedVals] reduced Gram values of the pair being finished
     float* qn_s = red + 2 * kRedVals;             // [2][16] squared norms of the current / next query's rows
+    float* ring = qn_s + 32;                      // [kRing][kSliceFloats] candidate slices (16-byte aligned)
     const int ntiles = (a.B + a.tile_pairs - 1) / a.tile_pairs;
 
     for (;;) {
@@ -257,9 +294,9 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
         const bool full_tile = __all_sync(0xffffffffu, lane >= npairs || (my_ql == kFT && my_cl == kFT)) &&
                                a.Sq == kFT && a.Sc == kFT;
         if (full_tile)
-            phase1<DT, true>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s);
+            phase1<DT, true>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring);
         else
-            phase1<DT, false>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s);
+            phase1<DT, false>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring);
         __syncwarp();
 
         // ---------------- phase 2: one pair per thread ---------------------------------------------------------

@@ -1,0 +1,169 @@
+"""Callers of the scoring kernels, rewritten batch-first ("next" row 1 of SURVEY 8f): the ranking loops of
+
+  * src/evaluation/evaluate.py:35-82   ``score(model, dataset, facet, scores_filename)``
+  * src/pre_process/pp_gen_nearest.py:131-204  ``CachingTrainedScoringModel.predict``
+  * src/learning/facetid_models/disent_models.py:344-371  ``caching_encode``
+
+and the file formats on either side of them: ``abstracts-{ds}.jsonl``,
+``test-pid2anns-{ds}[-{facet}].json`` in, ``scores[-facet].json`` / ``{qpid: [[cpid, score], ...]}`` out -- so the
+reference's ``evaluate()`` / ``ranking_eval.py`` consume the results unchanged.
+
+The reference scores one pair per Python call (evaluate.py:72-74) or 64 candidates per call (pp_gen_nearest.py:182);
+here one query's whole pool is ONE kernel launch.  geomloss derives its epsilon schedule from the bounding box of the
+points of a call, so the batching decides the schedule: ``mode='reference'`` reproduces the reference's calls exactly
+(one get_similarity / one 64-candidate caching_score per call), ``mode='batched'`` (default) uses one schedule per
+pool -- scores move by <= 3e-5 relative, rankings agree (tests/test_evaluation_gpu.py).
+"""
+import codecs
+import collections
+import json
+import logging
+import os
+
+import numpy as np
+import torch
+
+from .consent import prepare_abstracts
+from .similarity import SimilarityModel, caching_score
+
+
+class EvalDataset:
+    """Reader of the reference's evaluation files (src/evaluation/utils/datasets.py:7-128)."""
+
+    def __init__(self, name, root_path):
+        self.name = name
+        self.root_path = root_path
+        self.dataset = {}
+        with codecs.open(os.path.join(root_path, f'abstracts-{name}.jsonl'), 'r', 'utf-8') as fh:
+            for line in fh:
+                if not line.strip():
+                    continue
+                rec = json.loads(line)
+                paper = {'TITLE': rec['title'], 'ABSTRACT': rec['abstract']}
+                if 'pred_labels' in rec:
+                    paper['FACETS'] = rec['pred_labels']
+                self.dataset[rec['paper_id']] = paper
+        ner_file = os.path.join(root_path, f'{name}-ner.jsonl')
+        self.ner_data = None
+        if os.path.exists(ner_file):
+            with codecs.open(ner_file, 'r', 'utf-8') as fh:
+                self.ner_data = json.load(fh)
+
+    def get(self, pid):
+        paper = self.dataset[pid]
+        return paper if self.ner_data is None else {**paper, 'ENTITIES': self.ner_data[pid]}
+
+    def _pool_file(self, facet):
+        suffix = f'-{facet}' if facet is not None else ''
+        return os.path.join(self.root_path, f'test-pid2anns-{self.name}{suffix}.json')
+
+    def get_test_pool(self, facet=None):
+        with codecs.open(self._pool_file(facet), 'r', 'utf-8') as fh:
+            return json.load(fh)
+
+    def get_gold_test_data(self, facet=None):
+        return {q: dict(zip(v['cands'], v['relevance_adju'])) for q, v in self.get_test_pool(facet).items()}
+
+    def get_threshold_grade(self):
+        return 1 if self.name in {'treccovid', 'scidcite', 'scidcocite', 'scidcoread', 'scidcoview'} else 2
+
+    def __iter__(self):
+        return iter(self.dataset.items())
+
+
+def rank_candidates(candidate_pids, similarities):
+    """Stable descending sort (evaluate.py:76): ties keep the pool order.  Returns [(cpid, similarity), ...]."""
+    sims = np.asarray(similarities, dtype=np.float64)
+    order = np.argsort(-sims, kind='stable')
+    return [(candidate_pids[i], float(sims[i])) for i in order]
+
+
+def score(model: SimilarityModel, dataset, facet, scores_filename, mode='batched'):
+    """evaluate.py:35-82 with one launch per query pool.  Writes ``{qpid: [[cpid, -similarity], ...]}`` best first."""
+    assert mode in ('batched', 'reference')
+    test_pool = dataset.get_test_pool(facet=facet)
+    logging.info(f"Scoring {len(test_pool)} queries in {dataset.name}" + (f', facet: {facet}' if facet is not None else ''))
+    results = collections.OrderedDict()
+    for query_pid, query_pool in test_pool.items():
+        query_encoding = model.get_encoding(pids=[query_pid], dataset=dataset)[query_pid]
+        if facet is not None:
+            query_encoding = model.get_faceted_encoding(query_encoding, facet, dataset.get(query_pid))
+        candidate_pids = query_pool['cands']
+        candidate_encodings = model.get_encoding(pids=candidate_pids, dataset=dataset)
+        if mode == 'batched' and hasattr(model, 'score_pool'):
+            sims = model.score_pool(query_encoding, [candidate_encodings[c] for c in candidate_pids]).tolist()
+        else:
+            sims = [model.get_similarity(query_encoding, candidate_encodings[c]) for c in candidate_pids]
+        results[query_pid] = [(cpid, -1 * sim) for cpid, sim in rank_candidates(candidate_pids, sims)]
+    if scores_filename:
+        with codecs.open(scores_filename, 'w', 'utf-8') as fh:
+            json.dump(results, fh)
+        logging.info(f'Wrote: {scores_filename}')
+    return results
+
+
+def caching_encode(model, batch_dict):
+    """disent_models.py:344-371 -- encode a prepared batch and un-pad it into per-document numpy dicts.
+
+    ``model``: an AspireConSent; ``batch_dict``: {'bert_batch', 'abs_lens', 'senttok_idxs'}.
+    Returns [{'doc_cls_reps': np [D], 'sent_reps': np [num_sents, D]}, ...].
+    """
+    with torch.no_grad():
+        cls, reps = model.forward(bert_batch=batch_dict['bert_batch'], abs_lens=batch_dict['abs_lens'],
+                                  sent_tok_idxs=batch_dict['senttok_idxs'])
+    cls, reps = cls.cpu().numpy(), reps.cpu().numpy()
+    return [{'doc_cls_reps': cls[i], 'sent_reps': reps[i, :n]} for i, n in enumerate(batch_dict['abs_lens'])]
+
+
+class CachingScoringModel:
+    """pp_gen_nearest.py:90-204 ``CachingTrainedScoringModel`` on the B200 kernels.
+
+    ``predict(query_pid, cand_pids, pid2abstract, facet)`` encodes whatever is not cached yet (batches of 32, :141)
+    and scores the pool.  ``score_batch_size=64`` reproduces the reference's 64-candidate calls (and with them its
+    per-call epsilon schedules, :182-202); ``None`` scores the whole pool in one launch.
+    """
+
+    def __init__(self, model, tokenizer, score_agg_type='l2wasserstein', model_hparams=None, encode_batch_size=32,
+                 score_batch_size=64):
+        self.model, self.tokenizer = model, tokenizer
+        self.score_agg_type = score_agg_type
+        self.model_hparams = dict(model_hparams or {})
+        self.encode_batch_size, self.score_batch_size = encode_batch_size, score_batch_size
+        self.pid2model_reps = {}
+
+    def save_cache(self, out_fname):
+        np.savez(out_fname, **{f"{p}::{k}": v for p, d in self.pid2model_reps.items() for k, v in d.items()})
+
+    def _encode_missing(self, pids, pid2abstract):
+        missing = [p for p in pids if p not in self.pid2model_reps]
+        for s in range(0, len(missing), self.encode_batch_size):
+            chunk = missing[s:s + self.encode_batch_size]
+            docs = [{'TITLE': pid2abstract[p]['title'], 'ABSTRACT': pid2abstract[p]['abstract']} for p in chunk]
+            bert_batch, abs_lens, senttok = prepare_abstracts(batch_abs=docs, pt_lm_tokenizer=self.tokenizer)
+            reps = caching_encode(self.model, {'bert_batch': bert_batch, 'abs_lens': abs_lens, 'senttok_idxs': senttok})
+            assert len(reps) == len(chunk)
+            self.pid2model_reps.update(zip(chunk, reps))
+
+    def predict(self, query_pid, cand_pids, pid2abstract, facet='all'):
+        self._encode_missing(list(cand_pids) + [query_pid], pid2abstract)
+        query_rep = self.pid2model_reps[query_pid]
+        if facet != 'all':
+            labs = ['background_label' if lab == 'objective_label' else lab for lab in pid2abstract[query_pid]['pred_labels']]
+            keep = [i for i, lab in enumerate(labs) if lab == f'{facet}_label']
+            query_rep = dict(query_rep, sent_reps=query_rep['sent_reps'][keep, :])
+        cands = [self.pid2model_reps[c] for c in cand_pids]
+        step = self.score_batch_size or max(len(cands), 1)
+        cand_scores, pair_sm = [], []
+        for s in range(0, len(cands), step):
+            out = caching_score(query_rep, cands[s:s + step], score_agg_type=self.score_agg_type,
+                                model_hparams=self.model_hparams)
+            cand_scores.extend(out['batch_scores'].tolist())
+            pair_sm.extend(out['pair_scores'])
+        return {'cand_scores': cand_scores, 'pair_scores': pair_sm}
+
+    def rank_pool(self, query_pid, cand_pids, pid2abstract, facet='all'):
+        """[[cpid, score], ...] sorted by score descending, stable -- the ``test-pid2pool-*-ranked.json`` entry
+        (pp_gen_nearest.py:339,360-362)."""
+        scores = self.predict(query_pid, cand_pids, pid2abstract, facet)['cand_scores']
+        assert len(scores) == len(cand_pids)
+        return [[c, s] for c, s in rank_candidates(list(cand_pids), scores)]

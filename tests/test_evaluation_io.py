@@ -1,0 +1,64 @@
+"""CPU: file formats and ranking order of the batched evaluation callers (aspire_b200/evaluation.py) against the
+formats the reference reads/writes (src/evaluation/utils/datasets.py:24-94, evaluate.py:76-82)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from aspire_b200.evaluation import EvalDataset, rank_candidates, score
+from aspire_b200.similarity import SimilarityModel
+
+
+def _write_dataset(root, name="toyds", n=12):
+    rng = np.random.RandomState(0)
+    with open(os.path.join(root, f"abstracts-{name}.jsonl"), "w") as fh:
+        for i in range(n):
+            rec = {"paper_id": str(1000 + i), "title": f"title {i}", "abstract": [f"sent {i} {j}" for j in range(1 + i % 4)]}
+            if i % 2 == 0:
+                rec["pred_labels"] = ["background_label"] * (1 + i % 4)
+            fh.write(json.dumps(rec) + "\n")
+    pool = {"1000": {"cands": [str(1000 + i) for i in range(1, n)], "relevance_adju": rng.randint(0, 4, n - 1).tolist()},
+            "1001": {"cands": [str(1000 + i) for i in range(2, n)], "relevance_adju": rng.randint(0, 4, n - 2).tolist()}}
+    with open(os.path.join(root, f"test-pid2anns-{name}.json"), "w") as fh:
+        json.dump(pool, fh)
+    return name, pool
+
+
+class _LenModel(SimilarityModel):
+    """similarity = -|#sentences difference| -> many exact ties, which must keep pool order (stable sort)."""
+
+    def encode(self, batch_papers):
+        return [np.full((len(p["ABSTRACT"]), 4), float(len(p["ABSTRACT"])), dtype=np.float32) for p in batch_papers]
+
+    def get_similarity(self, x, y):
+        return -abs(float(len(x)) - float(len(y)))
+
+
+def test_dataset_reader_and_scores_file(tmp_path):
+    name, pool = _write_dataset(str(tmp_path))
+    ds = EvalDataset(name, str(tmp_path))
+    assert ds.get("1000") == {"TITLE": "title 0", "ABSTRACT": ["sent 0 0"], "FACETS": ["background_label"]}
+    assert "FACETS" not in ds.get("1001")
+    assert ds.get_test_pool() == pool
+    assert ds.get_gold_test_data()["1000"]["1001"] == pool["1000"]["relevance_adju"][0]
+    assert ds.get_threshold_grade() == 2 and EvalDataset.__new__(EvalDataset).__class__ is EvalDataset
+    model = _LenModel(name="len", encoding_type="sentence")
+    out = str(tmp_path / "scores.json")
+    res = score(model, ds, None, out)
+    with open(out) as fh:
+        on_disk = json.load(fh)
+    assert list(on_disk) == ["1000", "1001"]
+    for q, ranked in on_disk.items():
+        assert [c for c, _ in ranked] == [c for c, _ in res[q]]
+        vals = [v for _, v in ranked]
+        assert vals == sorted(vals)  # stored value = -similarity, best (smallest) first (evaluate.py:77)
+        # exact ties keep the candidate-pool order
+        for (c1, v1), (c2, v2) in zip(ranked, ranked[1:]):
+            if v1 == v2:
+                assert pool[q]["cands"].index(c1) < pool[q]["cands"].index(c2)
+
+
+def test_rank_candidates_is_stable_descending():
+    r = rank_candidates(["a", "b", "c", "d"], [1.0, 3.0, 1.0, 3.0])
+    assert r == [("b", 3.0), ("d", 3.0), ("a", 1.0), ("c", 1.0)]
