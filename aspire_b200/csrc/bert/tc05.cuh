@@ -128,5 +128,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// ---- TMEM as per-thread scratch (32x32b shape: thread t of warp w <-> TMEM lane 32*(w%4)+t, consecutive columns) ------
+// Registers -> TMEM, 4 consecutive columns of this thread's lane.  Complete (for this thread) after tmem_wait_st().
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float4& v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TMEM -> registers, 20 consecutive columns (x16 + x4), WITHOUT waiting: the destination registers are undefined until
+// tmem_ld20_wait() on the same array, which is what lets a load run under the previous slice's arithmetic.
+__device__ __forceinline__ void tmem_ld20_issue(uint32_t taddr, float4 (&d)[5]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(d[0].x), "=f"(d[0].y), "=f"(d[0].z), "=f"(d[0].w), "=f"(d[1].x), "=f"(d[1].y), "=f"(d[1].z), "=f"(d[1].w),
+          "=f"(d[2].x), "=f"(d[2].y), "=f"(d[2].z), "=f"(d[2].w), "=f"(d[3].x), "=f"(d[3].y), "=f"(d[3].z), "=f"(d[3].w)
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(d[4].x), "=f"(d[4].y), "=f"(d[4].z), "=f"(d[4].w)
+                 : "r"(taddr + 16u)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld20_wait(float4 (&d)[5]) {
+    // every destination register is an in/out operand of the wait, so no use of d[] can be scheduled above it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(d[0].x), "+f"(d[0].y), "+f"(d[0].z), "+f"(d[0].w), "+f"(d[1].x), "+f"(d[1].y), "+f"(d[1].z),
+                   "+f"(d[1].w), "+f"(d[2].x), "+f"(d[2].y), "+f"(d[2].z), "+f"(d[2].w), "+f"(d[3].x), "+f"(d[3].y),
+                   "+f"(d[3].z), "+f"(d[3].w), "+f"(d[4].x), "+f"(d[4].y), "+f"(d[4].z), "+f"(d[4].w)
+                 :
+                 : "memory");
+}
+
 }  // namespace tc
 }  // namespace asp

@@ -22,6 +22,7 @@
 // The query rows come through L1 (30 KB per query, re-read by every pair of its pool); their squared norms are
 // computed once per (warp, query) and kept in shared memory.
 #include <algorithm>
+#include "bert/tc05.cuh"
 #include "gram.cuh"
 #include "ot_pair.cuh"
 
@@ -34,9 +35,13 @@ constexpr int kCostLd = 101;   // floats per pair in the shared cost tile
 constexpr int kRedVals = 64;   // 50 dot products + 10 candidate norms, padded for the 16-lane transpose-reduce
 constexpr int kRing = 5;                   // candidate slices in the per-warp cp.async ring (kRing-1 in flight)
 constexpr int kSliceFloats = kFT * 64;     // one slice: 64 floats of each of the kFT rows
-constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 32 + kRing * kSliceFloats;  // cost tile, reduced values per
-                                                                                   // half, 2 x query norms, the ring
+constexpr int kSliceBytes = kSliceFloats * 4;
+constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 16 + kRing * kSliceFloats;  // cost tile, reduced values per
+                                                                                   // half, query norms, the ring
 constexpr int kCounterSlots = 256;
+constexpr int kQCols = 20;        // TMEM columns per query slice and lane: kHR rows x 4 floats
+constexpr int kTmemCols = 256;    // per CTA (two CTAs per SM share the 512 columns); D/64 * kQCols <= 256  =>  D <= 768
+constexpr int kMaxFusedD = 768;
 
 __device__ unsigned int g_tile_counter[kCounterSlots];
 __device__ unsigned int g_done_counter[kCounterSlots];
@@ -47,7 +52,7 @@ struct FusedArgs {
     const float* c;
     const int32_t* c_lens;
     int q_group, B, Sq, Sc, D, slot;
-    int tile_pairs;  // pairs per warp tile (32 when the batch fills the machine, fewer for small batches)
+    int tile_pairs;  // pairs per warp tile (<= 32; chosen by the launcher so that the tiles fill whole waves of warps)
     float inv_temp;
 };
 
@@ -72,26 +77,52 @@ __device__ __forceinline__ void transpose_reduce_w(float (&v)[NV], int lane) {
     }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 16-byte cp.async (L1 bypass) with compile-time byte offsets on both sides: one LDGSTS, no address arithmetic.
+template <int SOFF, int GOFF>
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(smem_dst), "l"(gmem_src), "n"(SOFF), "n"(GOFF)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const float* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Squared norms of the kFT rows of query `qidx` -> qn_s[0..kFT) (each half-warp takes kHR rows).
-__device__ __forceinline__ void query_norms(const FusedArgs& a, int qidx, int nq, int D, int lane, float* qn_s) {
-    const int h = lane >> 4, l16 = lane & 15, d4 = D >> 2;
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// The kHR rows of query `qidx` that this half-warp multiplies go into the lane's private TMEM columns: slice s
+// (floats [64s, 64s+64) of every row; the lane owns 4 of them per row) occupies columns [20s, 20s+20) in row-major
+// (row, component) order, so one x16 + one x4 tcgen05.ld brings a whole slice back.  Rows >= nq are stored as zeros.
+// Squared row norms are accumulated on the way and left in qn_s[0..kFT).  Nothing else of the query is ever re-read:
+// per (warp, query) the 30 KB come from L2 once instead of once per pair.
+template <int DT, bool FULL>
+__device__ __forceinline__ void query_to_tmem(const FusedArgs& a, int qidx, int nq, int lane, uint32_t tq, float* qn_s) {
+    const int h = lane >> 4, l16 = lane & 15;
+    const int D = DT ? DT : a.D, d4 = D >> 2, nit = d4 >> 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* qb = reinterpret_cast<const float4*>(a.q + (size_t)qidx * a.Sq * D) + (size_t)(kHR * h) * d4 + l16;
     float2 s[kHR];
 #pragma unroll
     for (int i = 0; i < kHR; ++i) s[i] = make_float2(0.f, 0.f);
-    for (int k = 0; k < d4; k += 16) {
+#pragma unroll 3
+    for (int it = 0; it < nit; ++it) {
+        float4 v[kHR];
+#pragma unroll
+        for (int i = 0; i < kHR; ++i) v[i] = (FULL || kHR * h + i < nq) ? __ldg(qb + (size_t)i * d4 + (it << 4)) : zero4;
 #pragma unroll
         for (int i = 0; i < kHR; ++i) {
-            if (kHR * h + i < nq) {
-                const float4 v = __ldg(qb + (size_t)i * d4 + k);
-                s[i] = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), s[i]);
-                s[i] = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), s[i]);
-            }
+            s[i] = __ffma2_rn(make_float2(v[i].x, v[i].y), make_float2(v[i].x, v[i].y), s[i]);
+            s[i] = __ffma2_rn(make_float2(v[i].z, v[i].w), make_float2(v[i].z, v[i].w), s[i]);
+            tc::tmem_st4(tq + it * kQCols + i * 4, v[i]);
         }
     }
-    __syncwarp();
+    tc::tmem_wait_st();
 #pragma unroll
     for (int i = 0; i < kHR; ++i) {
         float t = s[i].x + s[i].y;
@@ -102,26 +133,20 @@ __device__ __forceinline__ void query_norms(const FusedArgs& a, int qidx, int nq
     __syncwarp();
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // Phase 1 of one tile: distances of `npairs` pairs -> Cs[p][kCostLd].  FULL: all documents have kFT sentences.
 //
-// The candidate rows stream through a per-warp shared-memory ring of kRing slices (one slice = the same 64 floats of
+// Candidate rows stream through a per-warp shared-memory ring of kRing slices (one slice = the same 64 floats of
 // all kFT rows = 2.5 KB) filled with cp.async (16 B per lane, L1 bypassed): kRing-1 slices are always in flight per
-// warp (~80 KB per SM), which is what Little's law asks for at HBM latency -- registers could only hold one slice
-// ahead.  The stream runs straight across pair boundaries of the tile.
+// warp (~80 KB per SM), which is what Little's law asks for at HBM latency.  The stream runs straight across pair
+// boundaries of the tile; producer and consumer positions are plain running pointers (the five copies of a slice
+// differ by compile-time offsets).
+// The query comes from tensor memory (query_to_tmem): its slices are tcgen05.ld'ed one slice ahead into a pair of
+// register buffers, so the inner loop issues no global or shared load for the query at all.
 // Register plan per lane: 5x10 packed accumulators (100) + 10 packed candidate norms (20) + the current candidate
-// slice (40, read from the ring with one 128-bit LDS per row; lanes l and l+16 read the same address) + two 5-row
-// query slices (40, double buffered loads through L1).
+// slice (40, one 128-bit LDS per row; lanes l and l+16 read the same address) + two 5-row query slices (40).
 template <int DT, bool FULL>
 __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs, int my_ql, int my_cl, int lane, float* Cs,
-                                       float* red, float* qn_s, float* ring) {
+                                       float* red, float* qn_s, float* ring, uint32_t tq, const int* lut_s) {
     const int h = lane >> 4, l16 = lane & 15;
     const int D = DT ? DT : a.D, d4 = D >> 2;
     const int nit = d4 >> 4;  // 64-float slices per row (16 lanes x float4)
@@ -132,62 +157,65 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 
     float2 acc[kHR][kFT], cn[kFT];
     float4 qa[kHR], qb4[kHR];
-    int cur_q = -1, qslot = 0;  // qn_s holds two sets of query norms: pair_setup runs one pair ahead of the epilogue
 
     // ---- producer side of the ring: slices are issued in stream order (pair ip, slice iit) ----
+    // lane l copies the 16-byte piece (row (l>>4) + 2m, float4 column l&15) for m = 0..4
     int ip = 0, iit = 0, islot = 0;
+    const float* gsrc = a.c + (size_t)base * doc + (size_t)h * D + l16 * 4;
+    const uint32_t sring = tc::smem_u32(ring) + (uint32_t)lane * 16u;
+    uint32_t sdst = sring;
     auto issue_next = [&]() {
         if (ip < npairs) {
-            const int ncp = FULL ? kFT : __shfl_sync(0xffffffffu, my_cl, ip);
-            const float* src = a.c + (size_t)(base + ip) * doc + (iit << 6);
-            float* dst = ring + islot * kSliceFloats;
+            if (FULL) {
+                if (DT) {
+                    cp_async16<0 * 512, 0 * 8 * DT>(sdst, gsrc);
+                    cp_async16<1 * 512, 1 * 8 * DT>(sdst, gsrc);
+                    cp_async16<2 * 512, 2 * 8 * DT>(sdst, gsrc);
+                    cp_async16<3 * 512, 3 * 8 * DT>(sdst, gsrc);
+                    cp_async16<4 * 512, 4 * 8 * DT>(sdst, gsrc);
+                } else {
 #pragma unroll
-            for (int m = 0; m < kFT * 16 / 32; ++m) {  // 160 16-byte pieces per slice, 5 per lane
-                const int id = lane + 32 * m, row = id >> 4, c16 = id & 15;
-                if (FULL || row < ncp) cp_async16(dst + id * 4, src + (size_t)row * D + c16 * 4);
+                    for (int m = 0; m < kHR; ++m) cp_async16(sdst + m * 512, gsrc + (size_t)(2 * m) * D);
+                }
+            } else {
+                const int ncp = __shfl_sync(0xffffffffu, my_cl, ip);
+#pragma unroll
+                for (int m = 0; m < kHR; ++m)
+                    if (h + 2 * m < ncp) cp_async16(sdst + m * 512, gsrc + (size_t)(2 * m) * D);
             }
+            gsrc += 64;
             if (++iit == nit) {
                 iit = 0;
                 ++ip;
+                gsrc += doc - D;
             }
         }
         cp_async_commit();  // always commit: the wait below counts groups
-        islot = (islot + 1 == kRing) ? 0 : islot + 1;
+        sdst += kSliceBytes;
+        if (++islot == kRing) {
+            islot = 0;
+            sdst = sring;
+        }
     };
+    // consumer side
     int cslot = 0;
+    const float4* const cring = reinterpret_cast<const float4*>(ring) + l16;
+    const float4* cptr = cring;
 
-    // per-pair state (uniform across the warp)
-    int nq = kFT, nc = kFT, qidx = 0;
-    const float4* qptr = nullptr;  // query slice 0 of the pair being multiplied (+ i*d4 per row, + 16 per slice)
-
-    auto pair_setup = [&](int p) {
-        qidx = (base + p) / a.q_group;
-        if (!FULL) {
-            nq = __shfl_sync(0xffffffffu, my_ql, p);
-            nc = __shfl_sync(0xffffffffu, my_cl, p);
-        }
-        qptr = reinterpret_cast<const float4*>(a.q + (size_t)qidx * a.Sq * D) + (size_t)(kHR * h) * d4 + l16;
-        if (qidx != cur_q) {
-            qslot ^= 1;
-            query_norms(a, qidx, FULL ? kFT : nq, D, lane, qn_s + 16 * qslot);
-            cur_q = qidx;
-        }
-    };
-    auto load_q = [&](float4 (&dst)[kHR], const float4* src) {
-#pragma unroll
-        for (int i = 0; i < kHR; ++i) dst[i] = (FULL || kHR * h + i < nq) ? __ldg(src + (size_t)i * d4) : zero4;
-    };
     // one 64-float slice of the current pair (nc_cur rows valid): wait for it, refill the slot freed by the previous
     // slice, pull the rows out of the ring and multiply with the query slice q
     auto slice = [&](const float4 (&q)[kHR], int nc_cur) {
         cp_async_wait<kRing - 2>();
         __syncwarp();
         issue_next();
-        const float4* sl = reinterpret_cast<const float4*>(ring + cslot * kSliceFloats) + l16;
-        cslot = (cslot + 1 == kRing) ? 0 : cslot + 1;
         float4 cv[kFT];
 #pragma unroll
-        for (int j = 0; j < kFT; ++j) cv[j] = (FULL || j < nc_cur) ? sl[j * 16] : zero4;
+        for (int j = 0; j < kFT; ++j) cv[j] = (FULL || j < nc_cur) ? cptr[j * 16] : zero4;
+        cptr += kSliceFloats / 4;
+        if (++cslot == kRing) {
+            cslot = 0;
+            cptr = cring;
+        }
 #pragma unroll
         for (int j = 0; j < kFT; ++j) {
             const float2 c0 = make_float2(cv[j].x, cv[j].y), c1 = make_float2(cv[j].z, cv[j].w);
@@ -202,8 +230,16 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 
 #pragma unroll 1
     for (int k = 0; k < kRing - 1; ++k) issue_next();
-    pair_setup(0);
-    load_q(qa, qptr);
+
+    // per-pair state (uniform across the warp): current pair / next pair
+    int cur_q = base / a.q_group;
+    int nq_p = kFT, nc_p = kFT;
+    if (!FULL) {
+        nq_p = __shfl_sync(0xffffffffu, my_ql, 0);
+        nc_p = __shfl_sync(0xffffffffu, my_cl, 0);
+    }
+    query_to_tmem<DT, FULL>(a, cur_q, nq_p, lane, tq, qn_s);
+    tc::tmem_ld20_issue(tq, qa);
 
     for (int p = 0; p < npairs; ++p) {
 #pragma unroll
@@ -212,18 +248,20 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
             for (int j = 0; j < kFT; ++j) acc[i][j] = zero2;
 #pragma unroll
         for (int j = 0; j < kFT; ++j) cn[j] = zero2;
-        const int nq_p = nq, nc_p = nc;         // lengths / query-norm slot of the pair being accumulated
-        const float* qn_p = qn_s + 16 * qslot;  // (pair_setup below moves on to the next pair)
-        // slices 0 .. nit-1 of this pair, two per iteration (query slices ping-pong between qa and qb4)
+        const bool more = p + 1 < npairs;
+        const int next_q = more ? (base + p + 1) / a.q_group : cur_q;
+        const bool same_q = more && next_q == cur_q;
+        // slices 0 .. nit-1 of this pair, two per iteration (query slices ping-pong between qa and qb4; each is
+        // requested from TMEM one slice ahead, right after the wait for the one about to be used)
         for (int it = 0; it < nit; it += 2) {
-            load_q(qb4, qptr + ((it + 1) << 4));  // it+1 < nit because nit is even
+            tc::tmem_ld20_wait(qa);
+            tc::tmem_ld20_issue(tq + (it + 1) * kQCols, qb4);  // it+1 < nit because nit is even
             slice(qa, nc_p);
-            if (it + 2 < nit) {
-                load_q(qa, qptr + ((it + 2) << 4));
-            } else if (p + 1 < npairs) {  // last slice of the pair: fetch the next pair's first query slice
-                pair_setup(p + 1);
-                load_q(qa, qptr);
-            }
+            tc::tmem_ld20_wait(qb4);
+            if (it + 2 < nit)
+                tc::tmem_ld20_issue(tq + (it + 2) * kQCols, qa);
+            else if (same_q)
+                tc::tmem_ld20_issue(tq, qa);  // last slice of the pair: the next pair's first query slice
             slice(qb4, nc_p);
         }
         // pair finished: reduce over each half-warp, turn Gram values into distances
@@ -241,40 +279,78 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 #pragma unroll
         for (int m = 0; m < kRedVals / 16; ++m) red[h * kRedVals + 16 * m + rev4] = v[m];
         __syncwarp();
-        float* row = Cs + p * kCostLd;
-        for (int e = lane; e < kFT * kFT; e += 32) {
-            const int i = e / kFT, j = e - i * kFT;
-            const int hh = i / kHR, ii = i - hh * kHR;
-            const float d2 = qn_p[i] + red[kHR * kFT + j] - 2.f * red[hh * kRedVals + ii * kFT + j];
-            row[e] = (i < nq_p && j < nc_p) ? sqrtf(fmaxf(d2, 1e-8f)) : 1.0e30f;
+        // entry e = lane + 32k of the 10x10 tile; lut_s packs (index of its dot product in red[], j, i)
+        float* row = Cs + p * kCostLd + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int pk = lut_s[k * 32 + lane];
+            if (pk >= 0) {
+                const int i = pk >> 16, j = (pk >> 8) & 0xff;
+                const float d2 = qn_s[i] + red[kHR * kFT + j] - 2.f * red[pk & 0xff];
+                const float d = sqrt_approx(fmaxf(d2, 1e-8f));
+                row[32 * k] = (FULL || (i < nq_p && j < nc_p)) ? d : 1.0e30f;
+            }
+        }
+        if (more) {
+            if (!FULL) {
+                nq_p = __shfl_sync(0xffffffffu, my_ql, p + 1);
+                nc_p = __shfl_sync(0xffffffffu, my_cl, p + 1);
+            }
+            if (!same_q) {  // the tile crosses into the next query's pool: swap the query held in TMEM
+                __syncwarp();  // every lane has read qn_s for the finished pair
+                cur_q = next_q;
+                query_to_tmem<DT, FULL>(a, cur_q, nq_p, lane, tq, qn_s);
+                tc::tmem_ld20_issue(tq, qa);
+            }
         }
     }
     cp_async_wait<0>();  // only empty groups can still be pending; leave the ring quiescent for the next tile
     __syncwarp();
 }
 
-// Phase 2 lives in its own (non-inlined) function so that it gets a register allocation of its own: the solver wants
+// Phase 2 lives in its own (non-inlined) functions so that it gets a register allocation of its own: the solver wants
 // ~200 registers for the 10x10 tile and the potentials, and must not share them with phase 1's live state.
 __device__ __noinline__ void fused_phase2(const float* row, int ql, int cl, int b, int Sq, int Sc, const float* eps_s,
                                           int n_eps, float inv_temp, const OtOut* out) {
-    solve_pair_thread<kFT, kFT>([&](int i, int j) { return row[i * kFT + j]; }, ql, cl, b, Sq, Sc, eps_s, n_eps, inv_temp,
-                                *out);
+    solve_pair_thread<kFT, kFT, false>([&](int i, int j) { return row[i * kFT + j]; }, ql, cl, b, Sq, Sc, eps_s, n_eps,
+                                       inv_temp, *out);
+}
+// every pair of the tile is a full kFT x kFT problem: no length masks anywhere in the step
+__device__ __noinline__ void fused_phase2_full(const float* row, int b, const float* eps_s, int n_eps, float inv_temp,
+                                               const OtOut* out) {
+    solve_pair_thread<kFT, kFT, true>([&](int i, int j) { return row[i * kFT + j]; }, kFT, kFT, b, kFT, kFT, eps_s, n_eps,
+                                      inv_temp, *out);
 }
 
-template <int DT>  // embedding size known at compile time (0 = runtime a.D); D % 128 == 0
+template <int DT>  // embedding size known at compile time (0 = runtime a.D); D % 128 == 0, D <= kMaxFusedD
 __global__ void __launch_bounds__(kFusedWarps * 32, 2)
 ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     extern __shared__ float smem[];
     __shared__ float eps_s[ASP_MAX_EPS];
     __shared__ OtOut out_s;
+    __shared__ int lut_s[128];
+    __shared__ uint32_t tmem_slot;
     for (int k = threadIdx.x; k < sched.n; k += blockDim.x) eps_s[k] = sched.eps[k];
     if (threadIdx.x == 0) out_s = out;
-    __syncthreads();
+    {
+        const int e = threadIdx.x;  // blockDim.x == 128: entry e of the 10x10 tile (row-major)
+        int pk = -1;
+        if (e < kFT * kFT) {
+            const int i = e / kFT, j = e - i * kFT, hh = i / kHR, ii = i - hh * kHR;
+            pk = (hh * kRedVals + ii * kFT + j) | (j << 8) | (i << 16);
+        }
+        lut_s[e] = pk;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, kTmemCols);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tq = tmem_slot + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
     float* Cs = smem + (size_t)warp * kWarpSmem;  // cost tile of this warp's 32 pairs
     float* red = Cs + 32 * kCostLd;               // [2][kRedVals] reduced Gram values of the pair being finished
-    float* qn_s = red + 2 * kRedVals;             // [2][16] squared norms of the current / next query's rows
-    float* ring = qn_s + 32;                      // [kRing][kSliceFloats] candidate slices (16-byte aligned)
+    float* qn_s = red + 2 * kRedVals;             // [16] squared norms of the current query's rows
+    float* ring = qn_s + 16;                      // [kRing][kSliceFloats] candidate slices (16-byte aligned)
     const int ntiles = (a.B + a.tile_pairs - 1) / a.tile_pairs;
 
     for (;;) {
@@ -294,14 +370,18 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
         const bool full_tile = __all_sync(0xffffffffu, lane >= npairs || (my_ql == kFT && my_cl == kFT)) &&
                                a.Sq == kFT && a.Sc == kFT;
         if (full_tile)
-            phase1<DT, true>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring);
+            phase1<DT, true>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
         else
-            phase1<DT, false>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring);
+            phase1<DT, false>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
         __syncwarp();
 
         // ---------------- phase 2: one pair per thread ---------------------------------------------------------
         if (lane < npairs) {
-            fused_phase2(Cs + lane * kCostLd, my_ql, my_cl, base + lane, a.Sq, a.Sc, eps_s, sched.n, a.inv_temp, &out_s);
+            if (full_tile)
+                fused_phase2_full(Cs + lane * kCostLd, base + lane, eps_s, sched.n, a.inv_temp, &out_s);
+            else
+                fused_phase2(Cs + lane * kCostLd, my_ql, my_cl, base + lane, a.Sq, a.Sc, eps_s, sched.n, a.inv_temp,
+                             &out_s);
         }
         __syncwarp();
     }
@@ -314,9 +394,14 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
             __threadfence();
         }
     }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_slot, kTmemCols);
 }
 
-bool ot_fused_supported(int Sq, int Sc, int D) { return Sq <= kFT && Sc <= kFT && D >= 128 && (D % 128) == 0; }
+bool ot_fused_supported(int Sq, int Sc, int D) {
+    return Sq <= kFT && Sc <= kFT && D >= 128 && (D % 128) == 0 && D <= kMaxFusedD;
+}
 
 int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens, int B,
                     int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out, cudaStream_t stream) {
@@ -332,8 +417,13 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
     }
     // Tile size: 32 pairs per warp once the batch can feed every resident warp; smaller batches are spread over more
     // warps (down to one pair per warp) so that a single-query call (1 x 1k candidates) still uses the whole GPU.
+    // Tile size: the batch is cut into the smallest number of whole waves of resident warps (waves = ceil(B / (32 *
+    // warps))) and every tile gets ceil(B / (waves * warps)) <= 32 pairs, so no warp runs one tile more than the
+    // others; small batches spread down to one pair per warp so that a single 1 x 1k call still uses the whole GPU.
     const int max_ctas = 2 * sm_count();
-    const int tile_pairs = std::min(32, std::max(1, (B + max_ctas * kFusedWarps - 1) / (max_ctas * kFusedWarps)));
+    const int nwarps = max_ctas * kFusedWarps;
+    const int waves = (B + 32 * nwarps - 1) / (32 * nwarps);
+    const int tile_pairs = std::min(32, std::max(1, (B + waves * nwarps - 1) / (waves * nwarps)));
     FusedArgs a{q, q_lens, c, c_lens, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), tile_pairs,
                 1.0f / temp};
     const int ntiles = (B + tile_pairs - 1) / tile_pairs;

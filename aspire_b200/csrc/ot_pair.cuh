@@ -34,10 +34,12 @@ struct PairState {
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 
-template <int TQ, int TC>
-__device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql, int cl, float eps, float weight) {
+template <int TQ, int TC, bool FULL = false>
+__device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql_in, int cl_in, float eps, float weight) {
     // weight = 1 (un-averaged) or 0.5 (averaged): new = old - weight * eps ln2 (log2 sum - logw)
+    // FULL: the pair is known to have TQ x TC valid sentences, so every length mask folds away at compile time.
     constexpr int TP = TC / 2;
+    const int ql = FULL ? TQ : ql_in, cl = FULL ? TC : cl_in;
     const float t = kLog2e / eps;
     const float scale = weight * eps * kLn2;
     const float2 t2 = dup2(t), nt2 = dup2(-t), nscale2 = dup2(-scale);
@@ -119,10 +121,11 @@ __device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql, int
 // Solve one pair in the calling thread.  load_cost(i, j) returns C_ij for i < ql, j < cl (never called outside).
 // eps_sched[0..n_eps): the epsilon schedule (kernel-parameter / constant-bank or shared memory).
 // Writes every requested output of pair b.
-template <int TQ, int TC, typename LoadCost>
-__device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql, int cl, int b, int Sq, int Sc,
+template <int TQ, int TC, bool FULL = false, typename LoadCost>
+__device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql_in, int cl_in, int b, int Sq_in, int Sc_in,
                                                   const float* eps_sched, int n_eps, float inv_temp, const OtOut& out) {
     constexpr int TP = TC / 2;
+    const int ql = FULL ? TQ : ql_in, cl = FULL ? TC : cl_in, Sq = FULL ? TQ : Sq_in, Sc = FULL ? TC : Sc_in;
     PairState<TQ, TC> st;
     const float kBig = 1.0e30f;
 #pragma unroll
@@ -198,7 +201,7 @@ __device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql, in
 #pragma unroll 1
         for (int k = -1; k <= n_eps; ++k) {
             const bool plain = (k < 0) | (k == n_eps);
-            sinkhorn_step<TQ, TC>(st, ql, cl, eps_sched[min(max(k, 0), n_eps - 1)], plain ? 1.0f : 0.5f);
+            sinkhorn_step<TQ, TC, FULL>(st, ql, cl, eps_sched[min(max(k, 0), n_eps - 1)], plain ? 1.0f : 0.5f);
         }
     }
 
