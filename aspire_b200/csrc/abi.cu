@@ -58,6 +58,10 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_ot_kernel = value;
         return ASP_OK;
     }
+    if (strcmp(key, "ot_stagger") == 0) {  // developer switch: phase stagger of the fused kernel on (1) / off (0)
+        asp::g_ot_stagger = value != 0;
+        return ASP_OK;
+    }
     asp::set_error("asp_set_option: unknown key '%s'", key);
     return ASP_ERR_INVALID;
 }

@@ -37,6 +37,7 @@ void count_launch();  // every kernel launch of this library is counted (asp_lau
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int sm_count();
 extern int g_ot_kernel;  // asp_set_option("ot_kernel")
+extern int g_ot_stagger; // asp_set_option("ot_stagger")
 
 // Epsilon schedule passed by value in kernel parameter space (uniform, read through the constant bank).
 struct EpsSched {

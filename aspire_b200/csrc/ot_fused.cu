@@ -30,9 +30,9 @@ namespace asp {
 
 constexpr int kFT = 10;        // max sentences per document on the fused path
 constexpr int kHR = kFT / 2;   // query rows per half-warp
-constexpr int kFusedWarps = 4; // warps per CTA
+constexpr int kFusedWarps = 8; // warps per CTA; ONE CTA per SM, so warps w and w+4 share a scheduler (SM sub-partition)
 constexpr int kCostLd = 101;   // floats per pair in the shared cost tile
-constexpr int kRedVals = 64;   // 50 dot products + 10 candidate norms, padded for the 16-lane transpose-reduce
+constexpr int kRedVals = 64;   // 50 dot products + 5 candidate norms, padded for the 16-lane transpose-reduce
 constexpr int kRing = 5;                   // candidate slices in the per-warp cp.async ring (kRing-1 in flight)
 constexpr int kSliceFloats = kFT * 64;     // one slice: 64 floats of each of the kFT rows
 constexpr int kSliceBytes = kSliceFloats * 4;
@@ -40,7 +40,8 @@ constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 16 + kRing * kSliceFloat
                                                                                    // half, query norms, the ring
 constexpr int kCounterSlots = 256;
 constexpr int kQCols = 20;        // TMEM columns per query slice and lane: kHR rows x 4 floats
-constexpr int kTmemCols = 256;    // per CTA (two CTAs per SM share the 512 columns); D/64 * kQCols <= 256  =>  D <= 768
+constexpr int kTmemCols = 512;    // the whole tensor memory of the SM: 256 columns per warp of a lane quadrant;
+                                  // D/64 * kQCols <= 256  =>  D <= 768
 constexpr int kMaxFusedD = 768;
 
 __device__ unsigned int g_tile_counter[kCounterSlots];
@@ -52,6 +53,7 @@ struct FusedArgs {
     const float* c;
     const int32_t* c_lens;
     int q_group, B, Sq, Sc, D, slot;
+    int stagger;     // 1: warp w+4 starts after warp w's first phase 1 (asp_set_option "ot_stagger")
     int tile_pairs;  // pairs per warp tile (<= 32; chosen by the launcher so that the tiles fill whole waves of warps)
     float inv_temp;
 };
@@ -155,7 +157,10 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
     const int rev4 = (int)(__brev((unsigned)l16) >> 28);
     const size_t doc = (size_t)a.Sc * D;  // floats per candidate document
 
-    float2 acc[kHR][kFT], cn[kFT];
+    // Half-warp h keeps candidate row (j + kHR*h) % kFT in position j: the labels of its accumulators rotate (the
+    // epilogue's table undoes that), and each half squares only its positions 0..4, i.e. rows kHR*h .. kHR*h+4 -- every
+    // candidate norm is accumulated exactly once per warp instead of once per half.
+    float2 acc[kHR][kFT], cn[kHR];
     float4 qa[kHR], qb4[kHR];
 
     // ---- producer side of the ring: slices are issued in stream order (pair ip, slice iit) ----
@@ -201,6 +206,7 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
     int cslot = 0;
     const float4* const cring = reinterpret_cast<const float4*>(ring) + l16;
     const float4* cptr = cring;
+    const int rotA = kHR * h * 16, rotB = kHR * (1 - h) * 16;  // float4 offsets of rows kHR*h.. and of the other five
 
     // one 64-float slice of the current pair (nc_cur rows valid): wait for it, refill the slot freed by the previous
     // slice, pull the rows out of the ring and multiply with the query slice q
@@ -210,7 +216,10 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
         issue_next();
         float4 cv[kFT];
 #pragma unroll
-        for (int j = 0; j < kFT; ++j) cv[j] = (FULL || j < nc_cur) ? cptr[j * 16] : zero4;
+        for (int j = 0; j < kHR; ++j) {
+            cv[j] = (FULL || kHR * h + j < nc_cur) ? cptr[rotA + j * 16] : zero4;
+            cv[kHR + j] = (FULL || kHR * (1 - h) + j < nc_cur) ? cptr[rotB + j * 16] : zero4;
+        }
         cptr += kSliceFloats / 4;
         if (++cslot == kRing) {
             cslot = 0;
@@ -221,10 +230,10 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
             const float2 c0 = make_float2(cv[j].x, cv[j].y), c1 = make_float2(cv[j].z, cv[j].w);
 #pragma unroll
             for (int i = 0; i < kHR; ++i) acc[i][j] = __ffma2_rn(make_float2(q[i].x, q[i].y), c0, acc[i][j]);
-            cn[j] = __ffma2_rn(c0, c0, cn[j]);
+            if (j < kHR) cn[j] = __ffma2_rn(c0, c0, cn[j]);
 #pragma unroll
             for (int i = 0; i < kHR; ++i) acc[i][j] = __ffma2_rn(make_float2(q[i].z, q[i].w), c1, acc[i][j]);
-            cn[j] = __ffma2_rn(c1, c1, cn[j]);
+            if (j < kHR) cn[j] = __ffma2_rn(c1, c1, cn[j]);
         }
     };
 
@@ -247,7 +256,7 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 #pragma unroll
             for (int j = 0; j < kFT; ++j) acc[i][j] = zero2;
 #pragma unroll
-        for (int j = 0; j < kFT; ++j) cn[j] = zero2;
+        for (int j = 0; j < kHR; ++j) cn[j] = zero2;
         const bool more = p + 1 < npairs;
         const int next_q = more ? (base + p + 1) / a.q_group : cur_q;
         const bool same_q = more && next_q == cur_q;
@@ -271,22 +280,23 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 #pragma unroll
             for (int j = 0; j < kFT; ++j) v[i * kFT + j] = acc[i][j].x + acc[i][j].y;
 #pragma unroll
-        for (int j = 0; j < kFT; ++j) v[kHR * kFT + j] = cn[j].x + cn[j].y;
+        for (int j = 0; j < kHR; ++j) v[kHR * kFT + j] = cn[j].x + cn[j].y;
 #pragma unroll
-        for (int e = kHR * kFT + kFT; e < kRedVals; ++e) v[e] = 0.f;
+        for (int e = kHR * kFT + kHR; e < kRedVals; ++e) v[e] = 0.f;
         transpose_reduce_w<kRedVals, 16>(v, lane);
         __syncwarp();  // the previous pair's readers of red[] are done
 #pragma unroll
         for (int m = 0; m < kRedVals / 16; ++m) red[h * kRedVals + 16 * m + rev4] = v[m];
         __syncwarp();
-        // entry e = lane + 32k of the 10x10 tile; lut_s packs (index of its dot product in red[], j, i)
+        // entry e = lane + 32k of the 10x10 tile; lut_s packs (index of its dot product in red[], index of |c_j|^2 in
+        // red[], j, i)
         float* row = Cs + p * kCostLd + lane;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int pk = lut_s[k * 32 + lane];
             if (pk >= 0) {
-                const int i = pk >> 16, j = (pk >> 8) & 0xff;
-                const float d2 = qn_s[i] + red[kHR * kFT + j] - 2.f * red[pk & 0xff];
+                const int i = pk >> 24, j = (pk >> 16) & 0xff;
+                const float d2 = qn_s[i] + red[(pk >> 8) & 0xff] - 2.f * red[pk & 0xff];
                 const float d = sqrt_approx(fmaxf(d2, 1e-8f));
                 row[32 * k] = (FULL || (i < nq_p && j < nc_p)) ? d : 1.0e30f;
             }
@@ -323,35 +333,52 @@ __device__ __noinline__ void fused_phase2_full(const float* row, int b, const fl
 }
 
 template <int DT>  // embedding size known at compile time (0 = runtime a.D); D % 128 == 0, D <= kMaxFusedD
-__global__ void __launch_bounds__(kFusedWarps * 32, 2)
+__global__ void __launch_bounds__(kFusedWarps * 32, 1)
 ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     extern __shared__ float smem[];
     __shared__ float eps_s[ASP_MAX_EPS];
     __shared__ OtOut out_s;
     __shared__ int lut_s[128];
     __shared__ uint32_t tmem_slot;
+    __shared__ volatile int stagger_s[4];  // set by warp w (< 4) when its first phase 1 is over (or it has no work)
+    if (threadIdx.x < 4) stagger_s[threadIdx.x] = 0;
     for (int k = threadIdx.x; k < sched.n; k += blockDim.x) eps_s[k] = sched.eps[k];
     if (threadIdx.x == 0) out_s = out;
     {
-        const int e = threadIdx.x;  // blockDim.x == 128: entry e of the 10x10 tile (row-major)
+        const int e = threadIdx.x;  // entry e of the 10x10 tile (row-major); 128 table slots
         int pk = -1;
         if (e < kFT * kFT) {
+            // query row i lives in half hh = i / kHR; that half holds candidate row j at position (j - kHR*hh) mod kFT,
+            // and |c_j|^2 was accumulated by half j / kHR at position j % kHR
             const int i = e / kFT, j = e - i * kFT, hh = i / kHR, ii = i - hh * kHR;
-            pk = (hh * kRedVals + ii * kFT + j) | (j << 8) | (i << 16);
+            const int jpos = (j + kFT - kHR * hh) % kFT;
+            const int dot = hh * kRedVals + ii * kFT + jpos, nrm = (j / kHR) * kRedVals + kHR * kFT + (j % kHR);
+            pk = dot | (nrm << 8) | (j << 16) | (i << 24);
         }
-        lut_s[e] = pk;
+        if (e < 128) lut_s[e] = pk;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp == 0) tc::tmem_alloc(&tmem_slot, kTmemCols);
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
-    const uint32_t tq = tmem_slot + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
+    // this warp's private tensor memory: the 32 lanes of quadrant warp % 4 (the only ones it can address), columns
+    // [256 * (warp / 4), +256)
+    const uint32_t tq = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
     float* Cs = smem + (size_t)warp * kWarpSmem;  // cost tile of this warp's 32 pairs
     float* red = Cs + 32 * kCostLd;               // [2][kRedVals] reduced Gram values of the pair being finished
     float* qn_s = red + 2 * kRedVals;             // [16] squared norms of the current query's rows
     float* ring = qn_s + 16;                      // [kRing][kSliceFloats] candidate slices (16-byte aligned)
     const int ntiles = (a.B + a.tile_pairs - 1) / a.tile_pairs;
+
+    // Phase stagger.  Phase 1 saturates the FMA pipe and phase 2 the MUFU pipe, but two warps of one scheduler that
+    // start together stay in lockstep (equal tiles), queue for the same pipe and leave the other idle.  So warp w+4
+    // starts only when warp w has finished its first phase 1: from then on one of them streams/multiplies while the
+    // other iterates, and both pipes stay busy.
+    bool first = true;
+    if (a.stagger && warp >= 4) {
+        while (stagger_s[warp - 4] == 0) __nanosleep(2000);
+    }
 
     for (;;) {
         int tile = 0;
@@ -374,6 +401,10 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
         else
             phase1<DT, false>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
         __syncwarp();
+        if (first && warp < 4) {
+            if (lane == 0) stagger_s[warp] = 1;
+            first = false;
+        }
 
         // ---------------- phase 2: one pair per thread ---------------------------------------------------------
         if (lane < npairs) {
@@ -385,6 +416,7 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
         }
         __syncwarp();
     }
+    if (first && warp < 4 && lane == 0) stagger_s[warp] = 1;  // no tile at all: release the partner
     // the last warp to leave re-arms the counters for the next launch that uses this slot
     if (lane == 0) {
         const unsigned int total_warps = gridDim.x * kFusedWarps;
@@ -398,6 +430,8 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_slot, kTmemCols);
 }
+
+int g_ot_stagger = 1;
 
 bool ot_fused_supported(int Sq, int Sc, int D) {
     return Sq <= kFT && Sc <= kFT && D >= 128 && (D % 128) == 0 && D <= kMaxFusedD;
@@ -420,11 +454,12 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
     // Tile size: the batch is cut into the smallest number of whole waves of resident warps (waves = ceil(B / (32 *
     // warps))) and every tile gets ceil(B / (waves * warps)) <= 32 pairs, so no warp runs one tile more than the
     // others; small batches spread down to one pair per warp so that a single 1 x 1k call still uses the whole GPU.
-    const int max_ctas = 2 * sm_count();
+    const int max_ctas = sm_count();
     const int nwarps = max_ctas * kFusedWarps;
     const int waves = (B + 32 * nwarps - 1) / (32 * nwarps);
     const int tile_pairs = std::min(32, std::max(1, (B + waves * nwarps - 1) / (waves * nwarps)));
-    FusedArgs a{q, q_lens, c, c_lens, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), tile_pairs,
+    FusedArgs a{q, q_lens, c, c_lens, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), g_ot_stagger,
+                tile_pairs,
                 1.0f / temp};
     const int ntiles = (B + tile_pairs - 1) / tile_pairs;
     const int ctas = std::min(max_ctas, (ntiles + kFusedWarps - 1) / kFusedWarps);

@@ -49,7 +49,9 @@ __device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql_in, 
         v[j] = __ffma2_rn(st.g[j], t2, st.lb[j]);
         S[j] = f2(0.f, 0.f);
     }
-    // `chk` accumulates the log-sums of the valid rows / columns: it leaves the finite range iff one of them did
+    // `chk` = largest |log-sum| over the valid rows / columns: it leaves the finite range iff a sum over- or
+    // underflowed (the sums are of non-negative terms, so +-inf is the only way out; max runs on the ALU pipe, the
+    // FMA pipe being the busy one here)
     float chk = 0.f;
     float fnew[TQ];
 #pragma unroll
@@ -65,15 +67,14 @@ __device__ __forceinline__ void sinkhorn_step(PairState<TQ, TC>& st, int ql_in, 
         }
         const float l = lg2(R.x + R.y);
         fnew[i] = fmaf(-scale, l - st.la[i], st.f[i]);
-        chk += (i < ql) ? fabsf(l) : 0.f;
+        chk = fmaxf(chk, (i < ql) ? fabsf(l) : 0.f);
     }
     float2 gnew[TP];
 #pragma unroll
     for (int j = 0; j < TP; ++j) {
         const float2 l = f2(lg2(S[j].x), lg2(S[j].y));
         gnew[j] = __ffma2_rn(nscale2, __fadd2_rn(l, f2(-st.lb[j].x, -st.lb[j].y)), st.g[j]);
-        chk += (2 * j < cl) ? fabsf(l.x) : 0.f;
-        chk += (2 * j + 1 < cl) ? fabsf(l.y) : 0.f;
+        chk = fmaxf(chk, fmaxf((2 * j < cl) ? fabsf(l.x) : 0.f, (2 * j + 1 < cl) ? fabsf(l.y) : 0.f));
     }
     const bool bad = !(chk < 1e30f);
     if (__builtin_expect(bad, 0)) {

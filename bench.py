@@ -51,9 +51,25 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(pairs_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one ot_fused_kernel launch of this size, in GB, from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json); None when no capture of that launch shape exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            t = json.load(fh)
+        e = t["ot_fused_kernel"].get(str(pairs_per_launch))
+        if e:
+            return e["dram_gb"], e["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 class ClockSampler:
-    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampler (B200_PROFILING.md clocks line).  It is started BEFORE the warm-up (the process needs a few
+    hundred ms to come up) and samples every 20 ms with a timestamp; stop(t0, t1) keeps the samples that fall inside
+    the measured window [t0, t1] (host wall-clock, the window is bracketed by synchronisations)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -61,13 +77,18 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(ts):
+        import datetime
+        return datetime.datetime.strptime(ts.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+
+    def stop(self, t0, t1):
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -75,24 +96,29 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().strip().splitlines():
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                rows.append((self._epoch(parts[0]), float(parts[1]), float(parts[2]), float(parts[3]),
+                             [n for n, v in zip(names, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        busy = [s for s in sm if s > 0.5 * max(mx + [1.0])] or sm
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        window = "measured window"
+        if len(inside) < 3:  # very short run: fall back to every sample taken under load (warm-up runs the same steps)
+            mx = max([r[2] for r in rows] + [1.0])
+            inside = [r for r in rows if r[1] > 0.5 * mx] or rows
+            window = "whole run (measured window shorter than 3 samples)"
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": max(r[2] for r in inside) if inside else None,
+                "power_w": float(np.median([r[3] for r in inside])) if inside else None,
+                "reasons": reasons, "samples": len(inside), "window": window}
 
 
 def make_corpus(n_batches, nq, device, seed):
@@ -165,8 +191,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--queries", type=int, default=64, help="queries (x 1k candidates each) per step")
-    ap.add_argument("--pools", type=int, default=4, help="resident corpus batches the steps rotate over")
+    ap.add_argument("--queries", type=int, default=256, help="queries (x 1k candidates each) per step")
+    ap.add_argument("--pools", type=int, default=3, help="resident corpus batches the steps rotate over")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -186,6 +212,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _abi.lib()  # fail loudly if the CUDA library is missing
+    sampler = ClockSampler(local_rank) if rank == 0 else None
 
     NQ = args.queries
     NP = NQ * POOL  # pairs per step per GPU
@@ -224,7 +251,7 @@ def main():
         step(i)
     sync_all()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.time()
     launches0 = _abi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -248,7 +275,7 @@ def main():
         ev[i][1].record()
     torch.cuda.synchronize()
     t_fused = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_wall0, time.time()) if sampler else None
 
     # ---- latency of the un-batched shape: ONE query x 1k candidates per launch ----
     lat_out = {"dual": torch.empty(POOL, dtype=torch.float32, device=dev)}
@@ -270,7 +297,7 @@ def main():
 
     # ---- e2e: host buffers in, host scores out, through the public API ------------------------------
     from aspire_b200.similarity import score_pools_host
-    n_host = 2
+    n_host = 1 if NP * BYTES_PER_PAIR > 4e9 else 2
     host_pools = [pools[k].cpu().pin_memory() for k in range(n_host)]
     host_q = [queries[k].cpu().pin_memory() for k in range(n_host)]
     host_lens = torch.full((NP,), SENTS, dtype=torch.int32).pin_memory()
@@ -278,7 +305,7 @@ def main():
     for i in range(2):
         score_pools_host(host_q[i % n_host], host_qlens, host_pools[i % n_host], host_lens, POOL, diameter=DIAMETER)
     sync_all()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         res = score_pools_host(host_q[i % n_host], host_qlens, host_pools[i % n_host], host_lens, POOL, diameter=DIAMETER)
@@ -300,6 +327,7 @@ def main():
         return
 
     peak, peak_src = peaks()
+    traffic_gb, traffic_src = ncu_traffic(NP)
     achieved = BYTES_PER_PAIR * NP / (t_fused * 1e-3) / 1e9
     cfg = workload_config(world, NQ)
     cfg["n_eps"] = len(eps)
@@ -314,7 +342,7 @@ def main():
                        "scoring, host scores out)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "ot_fused_kernel", "kernel_ms": t_fused, "peak_source": peak_src,
+                     "traffic": traffic_gb, "traffic_source": traffic_src, "kernel": "ot_fused_kernel", "kernel_ms": t_fused, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": BYTES_PER_PAIR * NP,
                      "step_hbm_frac": BYTES_PER_PAIR * NP / (ms / args.steps * 1e-3) / 1e9 / peak},
         "latency_1x1k": {"pairs_per_launch": POOL, "ms_per_launch": lat_ms, "pairs_per_s": POOL / (lat_ms * 1e-3)},

@@ -1,0 +1,119 @@
+// Developer micro-benchmark (not product code): do the FMA pipe (FFMA2 / FFMA) and the MUFU pipe (ex2) overlap when
+// DIFFERENT warps of one scheduler use them (the fused OT kernel's phase 1 / phase 2 situation), and does FFMA2 hold
+// the issue port for its second cycle?
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench2 tools/ubench2.cu && tools/ubench2
+#include <cstdio>
+#include <cuda_runtime.h>
+#define ILP 8
+
+__device__ __forceinline__ float ffma2_chain(int iters, float a, float b, int seed) {
+    float2 x[ILP];
+    const float2 a2 = make_float2(a, a * 1.0001f), b2 = make_float2(b, b * 0.999f);
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x[i] = make_float2(seed + i, seed - i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) x[i] = __ffma2_rn(x[i], a2, b2);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i].x + x[i].y;
+    return s;
+}
+__device__ __forceinline__ float ffma_chain(int iters, float a, float b, int seed) {
+    float x[2 * ILP];
+#pragma unroll
+    for (int i = 0; i < 2 * ILP; ++i) x[i] = seed + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 2 * ILP; ++i) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * ILP; ++i) s += x[i];
+    return s;
+}
+__device__ __forceinline__ float ex2_chain(int iters, float a, int seed) {
+    float x[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) x[i] = -1.0f - 0.01f * (seed + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            float y;
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x[i]));
+            x[i] = y;
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i];
+    return s;
+}
+// FFMA2 with an independent integer (ALU pipe) instruction after each one
+__device__ __forceinline__ float ffma2_alu_chain(int iters, float a, float b, int seed) {
+    float2 x[ILP];
+    unsigned u[ILP];
+    const float2 a2 = make_float2(a, a * 1.0001f), b2 = make_float2(b, b * 0.999f);
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) { x[i] = make_float2(seed + i, seed - i); u[i] = seed * 7 + i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            x[i] = __ffma2_rn(x[i], a2, b2);
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[i]) : "r"(u[(i + 1) % ILP]), "r"(seed));
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += x[i].x + x[i].y + (float)u[i];
+    return s;
+}
+
+// mode bits: 1 = warps 0-3 run the FMA chain, 2 = warps 4-7 run the ex2 chain; kind 0 = FFMA2, 1 = FFMA, 2 = FFMA2+LOP3
+__global__ void __launch_bounds__(256, 1) k_spec(float* out, int mode, int kind, int it_fma, int it_ex2, float a, float b) {
+    const int warp = threadIdx.x >> 5;
+    float s = 0.f;
+    if (warp < 4) {
+        if (mode & 1) {
+            if (kind == 0) s = ffma2_chain(it_fma, a, b, threadIdx.x);
+            else if (kind == 1) s = ffma_chain(it_fma, a, b, threadIdx.x);
+            else s = ffma2_alu_chain(it_fma, a, b, threadIdx.x);
+        }
+    } else if (mode & 2) {
+        s = ex2_chain(it_ex2, a, threadIdx.x);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+float timeit(int sms, float* out, int mode, int kind, int it_fma, int it_ex2) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_spec<<<sms, 256>>>(out, mode, kind, it_fma, it_ex2, 1.0001f, 0.5f);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    k_spec<<<sms, 256>>>(out, mode, kind, it_fma, it_ex2, 1.0001f, 0.5f);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    return ms;
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int sms = p.multiProcessorCount;
+    float* out; cudaMalloc(&out, sizeof(float) * sms * 256);
+    const int it_fma = 1 << 16, it_ex2 = 1 << 14;  // 8 FFMA2 (2 clk each) vs 8 ex2 (8 clk each) per iteration: equal pipe time
+    const char* names[3] = {"FFMA2", "FFMA x2", "FFMA2+LOP3"};
+    for (int kind = 0; kind < 3; ++kind) {
+        float tf = timeit(sms, out, 1, kind, it_fma, it_ex2);
+        float te = timeit(sms, out, 2, kind, it_fma, it_ex2);
+        float tb = timeit(sms, out, 3, kind, it_fma, it_ex2);
+        printf("%-11s warps 0-3 alone %.3f ms | ex2 warps 4-7 alone %.3f ms | both %.3f ms  (perfect overlap %.3f, serial %.3f)\n",
+               names[kind], tf, te, tb, tf > te ? tf : te, tf + te);
+    }
+    // clocks per instruction for the single-warp-per-scheduler chains
+    int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    printf("(clock attr %d kHz: FFMA2 chain = %d instr per warp)\n", khz, it_fma * ILP);
+    return 0;
+}
