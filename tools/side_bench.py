@@ -1,0 +1,90 @@
+"""Developer benchmark of the kernels beside the headline one (not the judged bench): all-pairs tsAspire on tcgen05
+(BASELINE config 3 shape), variable-length otAspire up to 30 sentences (config 5), span mean-pool, top-k.
+Prints one line per kernel with its roofline fraction (MEASURED_PEAKS.json)."""
+import json
+import os
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from aspire_b200 import _abi, ot_scores, epsilon_schedule
+from aspire_b200.distances import l2max_allpairs, l2max_scores
+from aspire_b200.ranking import topk
+from aspire_b200.consent import span_mean_pool
+
+PEAKS = json.load(open("MEASURED_PEAKS.json")) if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    only = set(sys.argv[1:])
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(2345)
+    if not only or "allpairs" in only:
+        # config 3: 1k queries x 100k candidates, 10 sentences, 768-d (1e8 document pairs), in candidate chunks
+        NQ, NC, S, D = 1000, 100000, 10, 768
+        q = 0.3 * torch.randn(NQ, S, D, device=dev, generator=g)
+        c = 0.3 * torch.randn(NC, S, D, device=dev, generator=g)
+        ql = torch.full((NQ,), S, dtype=torch.int32, device=dev)
+        cl = torch.full((NC,), S, dtype=torch.int32, device=dev)
+        chunk = 20000
+        def run():
+            for s in range(0, NC, chunk):
+                sc, _ = l2max_allpairs(q, ql, c[s:s + chunk], cl[s:s + chunk], want_idx=True)
+                topk(sc, 100, base_id=s)
+        t = timeit(run, iters=3, warm=1)
+        flops = 2.0 * NQ * S * NC * S * D
+        print(f"allpairs tsAspire {NQ}x{NC}: {t:.1f} ms  {NQ * NC / t * 1e3:.3e} pairs/s  "
+              f"{flops / t / 1e9:.0f} TFLOP/s algorithmic ({flops / t / 1e9 / PEAKS['bf16_tflops']:.3f} of measured bf16 peak; "
+              f"the kernel issues 4 bf16 MMAs per product: {4 * flops / t / 1e9:.0f} TFLOP/s on the pipe)", flush=True)
+        del q, c
+    if not only or "varlen" in only:
+        # config 5: paired documents with 2..30 sentences, 50-step schedule
+        B, S, D = 20000, 30, 768
+        q = 0.3 * torch.randn(B, S, D, device=dev, generator=g)
+        c = 0.3 * torch.randn(B, S, D, device=dev, generator=g)
+        ql = torch.randint(2, 31, (B,), device=dev, generator=g).int()
+        cl = torch.randint(2, 31, (B,), device=dev, generator=g).int()
+        for eps_final in (0.01, 0.1, 1.0):
+            diam = 60.0
+            eps = [diam] + list(np.geomspace(diam, eps_final, 48, endpoint=False)) + [eps_final]
+            t = timeit(lambda: ot_scores(q, ql, c, cl, eps, want=("dual",)), iters=3, warm=1)
+            by = float((ql.sum() + cl.sum()).item()) * D * 4 + 12 * B
+            print(f"varlen otAspire B={B} S<=30 eps={eps_final}: {t:.2f} ms  {B / t * 1e3:.3e} pairs/s  "
+                  f"{by / t / 1e6:.0f} GB/s algorithmic ({by / t / 1e6 / PEAKS['hbm_gbs']:.3f} of measured HBM peak)", flush=True)
+        t = timeit(lambda: l2max_scores(q, ql, c, cl), iters=3, warm=1)
+        print(f"varlen tsAspire (paired) B={B} S<=30: {t:.2f} ms  {B / t * 1e3:.3e} pairs/s  {by / t / 1e6:.0f} GB/s "
+              f"({by / t / 1e6 / PEAKS['hbm_gbs']:.3f} of measured HBM peak)", flush=True)
+        del q, c
+    if not only or "pool" in only:
+        B, L, D, S = 256, 502, 768, 20
+        h = torch.randn(B, L, D, device=dev, generator=g)
+        spans = torch.zeros(B, S, 2, dtype=torch.int32, device=dev)
+        starts = torch.arange(S, device=dev) * 24 + 10
+        spans[:, :, 0] = starts
+        spans[:, :, 1] = starts + 24
+        t = timeit(lambda: span_mean_pool(h, spans))
+        by = B * S * 24 * D * 4 + B * S * D * 4 + B * D * 4
+        print(f"span mean-pool B={B} L={L} S={S}: {t * 1e3:.1f} us  {by / t / 1e6:.0f} GB/s algorithmic "
+              f"({by / t / 1e6 / PEAKS['hbm_gbs']:.3f} of measured HBM peak)", flush=True)
+    if not only or "topk" in only:
+        Q, N = 1000, 125000
+        s = torch.randn(Q, N, device=dev, generator=g)
+        t = timeit(lambda: topk(s, 100))
+        print(f"top-100 of {Q}x{N}: {t * 1e3:.1f} us  {Q * N * 4 / t / 1e6:.0f} GB/s "
+              f"({Q * N * 4 / t / 1e6 / PEAKS['hbm_gbs']:.3f} of measured HBM peak)", flush=True)
+
+
+if __name__ == "__main__":
+    main()
