@@ -7,20 +7,23 @@
 //   plan + primal value          pair_distances.py:76-85
 // for documents of at most kFT sentences (the reference's abstracts: 10-sentence synthetic config, CSFCube ~7).
 //
-// Work decomposition (HBM-bound design: every candidate row is read exactly once, 30 KB per pair, and only
-// 4-8 bytes per pair are written):
-//   * persistent grid of independent WARPS (2 CTAs x 4 warps per SM); a warp takes tiles of 32 pairs from a global
-//     atomic counter, so memory-phase warps and math-phase warps of the same SM overlap (FMA pipe vs MUFU pipe);
-//   * phase 1 (streaming): for each of its 32 pairs the two HALF-WARPS take 5 query rows each and their 16 lanes
-//     split the embedding dimension; candidate rows are staged by cp.async through a per-warp shared-memory ring
-//     (4 slices = 10 KB in flight per warp, ~80 KB per SM: enough bytes in flight for HBM latency; the stream runs
-//     across pair boundaries) and read back with one 128-bit LDS per row.  The 5x10 Gram tile + squared norms accumulate in
-//     packed fp32 (FFMA2: two k-partials per register pair), are transpose-reduced over the 16 lanes and leave
+// Work decomposition (every candidate row is read from HBM exactly once, 30 KB per pair, and only 4-8 bytes per pair
+// are written; the query never comes from memory in the inner loop at all):
+//   * ONE persistent CTA of 8 independent warps per SM; a warp takes tiles of <= 32 pairs from a global atomic
+//     counter (tile size chosen by the launcher so that the batch fills whole waves of warps);
+//   * phase 1 (streaming, FMA pipe): for each pair of its tile the two HALF-WARPS take 5 query rows each and their 16
+//     lanes split the embedding dimension.  Candidate rows are staged by cp.async through a per-warp shared-memory
+//     ring (4 slices = 10 KB in flight per warp, 80 KB per SM; the stream runs across pair boundaries) and read back
+//     with one 128-bit LDS per row.  The QUERY rows live in TENSOR MEMORY: each lane parks its 240 floats of the
+//     current query in its own TMEM lane once per (warp, query) with tcgen05.st and pulls one 20-float slice per step
+//     back with tcgen05.ld, one slice ahead -- no L1/L2 traffic and no LSU instruction for the query (the first
+//     version re-read it through L1 at a 5 % hit rate; that single stall was 22 % of the kernel).  The 5x10 Gram tile
+//     + squared norms accumulate in packed fp32 (FFMA2), are transpose-reduced over the 16 lanes and leave
 //     sqrt(max(|q|^2+|c|^2-2q.c, 1e-8)) in a shared cost tile [32][101] (odd stride: conflict-free in phase 2);
-//   * phase 2 (math): each THREAD solves one pair entirely in registers (ot_pair.cuh): one ex2 per (i,j)
-//     and step, no shuffles, no shared memory in the loop.
-// The query rows come through L1 (30 KB per query, re-read by every pair of its pool); their squared norms are
-// computed once per (warp, query) and kept in shared memory.
+//   * phase 2 (math, MUFU pipe): each THREAD solves one pair entirely in registers (ot_pair.cuh): one ex2 per (i,j)
+//     and step, no shuffles, no shared memory in the loop; full 10x10 tiles run a mask-free specialisation;
+//   * phase stagger: warps w and w+4 share a scheduler; w+4 starts after w's first phase 1, so that one of them is on
+//     the FMA pipe while the other is on the MUFU pipe instead of both queueing for the same one.
 #include <algorithm>
 #include "bert/tc05.cuh"
 #include "gram.cuh"
