@@ -38,6 +38,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int sm_count();
 extern int g_ot_kernel;  // asp_set_option("ot_kernel")
 extern int g_ot_stagger; // asp_set_option("ot_stagger")
+extern int g_ot_fused_mode;  // asp_set_option("ot_fused_mode")
 
 // Epsilon schedule passed by value in kernel parameter space (uniform, read through the constant bank).
 struct EpsSched {

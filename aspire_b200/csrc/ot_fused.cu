@@ -149,7 +149,7 @@ __device__ __forceinline__ void query_to_tmem(const FusedArgs& a, int qidx, int 
 // register buffers, so the inner loop issues no global or shared load for the query at all.
 // Register plan per lane: 5x10 packed accumulators (100) + 10 packed candidate norms (20) + the current candidate
 // slice (40, one 128-bit LDS per row; lanes l and l+16 read the same address) + two 5-row query slices (40).
-template <int DT, bool FULL>
+template <int DT, bool FULL, int LD = kCostLd>
 __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs, int my_ql, int my_cl, int lane, float* Cs,
                                        float* red, float* qn_s, float* ring, uint32_t tq, const int* lut_s) {
     const int h = lane >> 4, l16 = lane & 15;
@@ -293,7 +293,7 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
         __syncwarp();
         // entry e = lane + 32k of the 10x10 tile; lut_s packs (index of its dot product in red[], index of |c_j|^2 in
         // red[], j, i)
-        float* row = Cs + p * kCostLd + lane;
+        float* row = Cs + p * LD + lane;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int pk = lut_s[k * 32 + lane];
@@ -434,7 +434,181 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     if (warp == 0) tc::tmem_dealloc(tmem_slot, kTmemCols);
 }
 
+// ---- v7: Gram warps + Sinkhorn warps ---------------------------------------------------------------------------------------
+// 12 warps per SM, all within 168 registers.  Warps 0-7 ("Gram" warps, two per scheduler) run phase 1 back to back on
+// half-tiles of 16 pairs and between them keep the scheduler's FMA pipe busy (one warp alone cannot: it issues at
+// most one FFMA2 per ~2.8 clk).  Warps 8-11 ("Sinkhorn" warps, one per scheduler) run phase 2 on the MUFU pipe, one
+// pair per thread, with the cost tile STREAMED from shared memory in every step (solve_pair_thread_stream: ~100
+// registers instead of ~200 -- that is what makes three warps per scheduler fit).  The hand-over is a ring of four
+// 16-pair half-tiles per scheduler: Gram warps claim ring slots with a ticket, the Sinkhorn warp consumes tickets in
+// order, two at a time (lanes 0-15 / 16-31); full/empty mbarriers per slot.
+constexpr int kV7Gram = 8, kV7Warps = 12;
+constexpr int kV7Half = 16;                 // pairs per Gram tile
+constexpr int kV7Ld = kFT * kFT;            // cost floats per pair (16-byte aligned rows; LDS.128 conflict-free)
+constexpr int kV7Slots = 4;                 // half-tiles per scheduler
+constexpr int kV7SlotFloats = kV7Half * kV7Ld;
+// dynamic shared memory, floats: [4 schedulers][kV7Slots] half-tiles | per Gram warp: reduced values, query norms, ring
+constexpr int kV7GramSmem = 2 * kRedVals + 16 + kRing * kSliceFloats;
+constexpr int kV7Smem = 4 * kV7Slots * kV7SlotFloats + kV7Gram * kV7GramSmem;
+static_assert((4 * kV7Slots * kV7SlotFloats) % 4 == 0 && (2 * kRedVals + 16) % 4 == 0 && kV7GramSmem % 4 == 0, "16-byte alignment");
+
+constexpr int kV7GramRegs = 200, kV7SinkRegs = 104;  // 8 x 200 + 4 x 104 = 2016 <= 2048 registers per lane slot
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// (inlined into the Sinkhorn branch: ptxas must see them under that branch's setmaxnreg budget)
+__device__ __forceinline__ void v7_phase2(float* Cs, int ql, int cl, int b, int Sq, int Sc, const float* eps_s, int n_eps,
+                                       float inv_temp, const OtOut* out) {
+    solve_pair_thread_stream<kFT, kFT, false>(Cs, ql, cl, b, Sq, Sc, eps_s, n_eps, inv_temp, *out);
+}
+__device__ __forceinline__ void v7_phase2_full(float* Cs, int b, const float* eps_s, int n_eps, float inv_temp,
+                                            const OtOut* out) {
+    solve_pair_thread_stream<kFT, kFT, true>(Cs, kFT, kFT, b, kFT, kFT, eps_s, n_eps, inv_temp, *out);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kV7Warps * 32, 1)
+ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
+    extern __shared__ float smem[];
+    __shared__ float eps_s[ASP_MAX_EPS];
+    __shared__ OtOut out_s;
+    __shared__ int lut_s[128];
+    __shared__ uint32_t tmem_slot;
+    __shared__ uint64_t full_bar[4][kV7Slots], empty_bar[4][kV7Slots];
+    __shared__ int meta_s[4][kV7Slots][4];   // base, npairs (0 = end of a Gram warp's stream), full_tile
+    __shared__ unsigned int ticket_s[4];
+    for (int k = threadIdx.x; k < sched.n; k += blockDim.x) eps_s[k] = sched.eps[k];
+    if (threadIdx.x == 0) out_s = out;
+    if (threadIdx.x < 4) ticket_s[threadIdx.x] = 0u;
+    {
+        const int e = threadIdx.x;
+        int pk = -1;
+        if (e < kFT * kFT) {
+            const int i = e / kFT, j = e - i * kFT, hh = i / kHR, ii = i - hh * kHR;
+            const int jpos = (j + kFT - kHR * hh) % kFT;
+            const int dot = hh * kRedVals + ii * kFT + jpos, nrm = (j / kHR) * kRedVals + kHR * kFT + (j % kHR);
+            pk = dot | (nrm << 8) | (j << 16) | (i << 24);
+        }
+        if (e < 128) lut_s[e] = pk;
+    }
+    if (threadIdx.x < 4 * kV7Slots) {
+        tc::mbar_init(&full_bar[0][0] + threadIdx.x, 1);
+        tc::mbar_init(&empty_bar[0][0] + threadIdx.x, 1);
+        tc::fence_barrier_init();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, kTmemCols);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const int w = warp & 3;  // scheduler (SM sub-partition) of this warp
+    float* slots = smem + (size_t)w * kV7Slots * kV7SlotFloats;
+    const int ntiles = (a.B + a.tile_pairs - 1) / a.tile_pairs;
+
+    if (warp < kV7Gram) {
+        // ------------------------------ Gram warp --------------------------------------------------------------------
+        setmaxnreg_inc<kV7GramRegs>();
+        float* red = smem + 4 * kV7Slots * kV7SlotFloats + (size_t)warp * kV7GramSmem;
+        float* qn_s = red + 2 * kRedVals;
+        float* ring = qn_s + 16;
+        const uint32_t tq = tmem_slot + ((uint32_t)(w * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+        for (;;) {
+            int tile = 0;
+            unsigned int ticket = 0;
+            if (lane == 0) {
+                tile = (int)atomicAdd(&g_tile_counter[a.slot], 1u);
+                ticket = atomicAdd(&ticket_s[w], 1u);
+            }
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            const int sl = ticket % kV7Slots;
+            tc::mbar_wait(&empty_bar[w][sl], ((ticket / kV7Slots) & 1u) ^ 1u);  // the Sinkhorn warp is done with the slot
+            if (tile >= ntiles) {
+                if (lane == 0) {
+                    meta_s[w][sl][1] = 0;
+                    tc::mbar_arrive(&full_bar[w][sl]);
+                }
+                break;
+            }
+            const int base = tile * a.tile_pairs;
+            const int npairs = min(a.tile_pairs, a.B - base);
+            int my_ql = 0, my_cl = 0;
+            if (lane < npairs) {
+                my_ql = min(max(a.q_lens[(base + lane) / a.q_group], 0), a.Sq);
+                my_cl = min(max(a.c_lens[base + lane], 0), a.Sc);
+            }
+            const bool full_tile = __all_sync(0xffffffffu, lane >= npairs || (my_ql == kFT && my_cl == kFT)) &&
+                                   a.Sq == kFT && a.Sc == kFT;
+            float* Cs = slots + sl * kV7SlotFloats;
+            if (full_tile)
+                phase1<DT, true, kV7Ld>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
+            else
+                phase1<DT, false, kV7Ld>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
+            __syncwarp();
+            if (lane == 0) {
+                meta_s[w][sl][0] = base;
+                meta_s[w][sl][1] = npairs;
+                meta_s[w][sl][2] = full_tile ? 1 : 0;
+                tc::mbar_arrive(&full_bar[w][sl]);  // release: tile + descriptor visible to the waiter
+            }
+        }
+        if (lane == 0) {  // the last Gram warp to leave re-arms the counters for the next launch using this slot
+            const unsigned int total = gridDim.x * kV7Gram;
+            if (atomicAdd(&g_done_counter[a.slot], 1u) == total - 1) {
+                g_tile_counter[a.slot] = 0u;
+                g_done_counter[a.slot] = 0u;
+                __threadfence();
+            }
+        }
+    } else {
+        // ------------------------------ Sinkhorn warp: tickets in order, two half-tiles per pass ---------------------
+        setmaxnreg_dec<kV7SinkRegs>();
+        int ended = 0;  // Gram warps of this scheduler that have posted their end marker
+        const int hsel = lane >> 4, l16 = lane & 15;
+        for (unsigned int t0 = 0; ended < 2; t0 += 2) {
+            int base[2] = {0, 0}, np[2] = {0, 0}, ft[2] = {1, 1};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (ended >= 2) break;
+                const unsigned int t = t0 + k;
+                const int sl = t % kV7Slots;
+                while (!tc::mbar_try_wait(&full_bar[w][sl], (t / kV7Slots) & 1u)) __nanosleep(3000);
+                base[k] = meta_s[w][sl][0];
+                np[k] = meta_s[w][sl][1];
+                ft[k] = meta_s[w][sl][2];
+                if (np[k] == 0) ++ended;
+            }
+            const int my_np = hsel ? np[1] : np[0], my_base = hsel ? base[1] : base[0];
+            const int sl_mine = (t0 + hsel) % kV7Slots;
+            if (l16 < my_np) {
+                float* Cs = slots + sl_mine * kV7SlotFloats + l16 * kV7Ld;
+                const int b = my_base + l16;
+                // warp-uniform choice keeps the two specialisations from serialising inside a warp
+                if ((np[0] == 0 || ft[0]) && (np[1] == 0 || ft[1])) {
+                    v7_phase2_full(Cs, b, eps_s, sched.n, a.inv_temp, &out_s);
+                } else {
+                    const int ql = min(max(a.q_lens[b / a.q_group], 0), a.Sq);
+                    const int cl = min(max(a.c_lens[b], 0), a.Sc);
+                    v7_phase2(Cs, ql, cl, b, a.Sq, a.Sc, eps_s, sched.n, a.inv_temp, &out_s);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (np[k] > 0) tc::mbar_arrive(&empty_bar[w][(t0 + k) % kV7Slots]);
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_slot, kTmemCols);
+}
+
 int g_ot_stagger = 1;
+int g_ot_fused_mode = 1;  // 1: Gram/Sinkhorn warp kernel (v7), 0: every warp runs both phases (asp_set_option "ot_fused_mode")
 
 bool ot_fused_supported(int Sq, int Sc, int D) {
     return Sq <= kFT && Sc <= kFT && D >= 128 && (D % 128) == 0 && D <= kMaxFusedD;
@@ -443,13 +617,17 @@ bool ot_fused_supported(int Sq, int Sc, int D) {
 int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens, int B,
                     int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out, cudaStream_t stream) {
     static std::atomic<unsigned int> next_slot{0};
-    const int smem = kFusedWarps * kWarpSmem * (int)sizeof(float);
+    const bool v7 = g_ot_fused_mode == 1;
+    const int smem_v6 = kFusedWarps * kWarpSmem * (int)sizeof(float), smem_v7 = kV7Smem * (int)sizeof(float);
+    const int smem = v7 ? smem_v7 : smem_v6;
     static thread_local int attr_dev = -1;
     int dev = 0;
     ASP_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v6));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v6));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
         attr_dev = dev;
     }
     // Tile size: 32 pairs per warp once the batch can feed every resident warp; smaller batches are spread over more
@@ -458,18 +636,26 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
     // warps))) and every tile gets ceil(B / (waves * warps)) <= 32 pairs, so no warp runs one tile more than the
     // others; small batches spread down to one pair per warp so that a single 1 x 1k call still uses the whole GPU.
     const int max_ctas = sm_count();
-    const int nwarps = max_ctas * kFusedWarps;
-    const int waves = (B + 32 * nwarps - 1) / (32 * nwarps);
-    const int tile_pairs = std::min(32, std::max(1, (B + waves * nwarps - 1) / (waves * nwarps)));
+    const int per_cta = v7 ? kV7Gram : kFusedWarps;  // warps per CTA that take tiles
+    const int max_tile = v7 ? kV7Half : 32;
+    const int nwarps = max_ctas * per_cta;
+    const int waves = (B + max_tile * nwarps - 1) / (max_tile * nwarps);
+    const int tile_pairs = std::min(max_tile, std::max(1, (B + waves * nwarps - 1) / (waves * nwarps)));
     FusedArgs a{q, q_lens, c, c_lens, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), g_ot_stagger,
                 tile_pairs,
                 1.0f / temp};
     const int ntiles = (B + tile_pairs - 1) / tile_pairs;
-    const int ctas = std::min(max_ctas, (ntiles + kFusedWarps - 1) / kFusedWarps);
-    if (D == 768)
+    const int ctas = std::min(max_ctas, (ntiles + per_cta - 1) / per_cta);
+    if (v7) {
+        if (D == 768)
+            ot_fused_v7_kernel<768><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+        else
+            ot_fused_v7_kernel<0><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+    } else if (D == 768) {
         ot_fused_kernel<768><<<ctas, kFusedWarps * 32, smem, stream>>>(a, sched, out);
-    else
+    } else {
         ot_fused_kernel<0><<<ctas, kFusedWarps * 32, smem, stream>>>(a, sched, out);
+    }
     ASP_LAUNCH_CHECK("ot_fused_kernel");
     return ASP_OK;
 }

@@ -265,3 +265,250 @@ __device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql_in,
 }
 
 }  // namespace asp
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Register-light variant of the per-thread solver: the TQ x TC cost tile of the pair stays in SHARED memory
+// (Cs[i * TC + j], 16-byte aligned, TC even) and is streamed through registers four entries at a time in every step,
+// so the thread keeps only the potentials, the log-weights and the column sums (~100 registers instead of ~200).
+// Same arithmetic, same order of operations per entry as sinkhorn_step / solve_pair_thread above.
+namespace asp {
+
+template <int TQ, int TC>
+struct PairStateS {
+    float la[TQ], f[TQ];
+    float2 lb[TC / 2], g[TC / 2];
+};
+
+// Max-stabilised Sinkhorn half-steps on memory operands (the rare path of sinkhorn_step_stream when a plain sum left the
+// fp32 range).  buf = la[TQ], f[TQ], fnew[TQ] | lb[TC], g[TC], gnew[TC]; rolled loops, a handful of registers.
+static __device__ __noinline__ void stabilised_step_mem(const float* Cs, int TQ, int TC, float* buf, float eps, float weight) {
+    const float t = kLog2e / eps, nt = -t;
+    const float *la = buf, *f = buf + TQ, *lb = buf + 3 * TQ, *g = buf + 3 * TQ + TC;
+    float *fnew = buf + 2 * TQ, *gnew = buf + 3 * TQ + 2 * TC;
+#pragma unroll 1
+    for (int i = 0; i < TQ; ++i) {
+        float m = -INFINITY, s = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < TC; ++j) m = fmaxf(m, fmaf(Cs[i * TC + j], nt, fmaf(g[j], t, lb[j])));
+#pragma unroll 1
+        for (int j = 0; j < TC; ++j) s += ex2(fmaf(Cs[i * TC + j], nt, fmaf(g[j], t, lb[j])) - m);
+        const float ft = -eps * kLn2 * (m + lg2(s));
+        fnew[i] = f[i] + weight * (ft - f[i]);
+    }
+#pragma unroll 1
+    for (int j = 0; j < TC; ++j) {
+        float m = -INFINITY, s = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < TQ; ++i) m = fmaxf(m, fmaf(Cs[i * TC + j], nt, fmaf(f[i], t, la[i])));
+#pragma unroll 1
+        for (int i = 0; i < TQ; ++i) s += ex2(fmaf(Cs[i * TC + j], nt, fmaf(f[i], t, la[i])) - m);
+        const float gt = -eps * kLn2 * (m + lg2(s));
+        gnew[j] = g[j] + weight * (gt - g[j]);
+    }
+}
+
+template <int TQ, int TC, bool FULL>
+__device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, const float* Cs, int ql_in, int cl_in, float eps,
+                                                     float weight) {
+    static_assert((TQ * TC) % 4 == 0 && TC % 2 == 0, "tile is read as float4 chunks holding whole column pairs");
+    constexpr int TP = TC / 2;
+    const int ql = FULL ? TQ : ql_in, cl = FULL ? TC : cl_in;
+    const float t = kLog2e / eps;
+    const float scale = weight * eps * kLn2;
+    const float2 t2 = dup2(t), nt2 = dup2(-t), nscale2 = dup2(-scale);
+    float2 v[TP], S[TP];
+#pragma unroll
+    for (int j = 0; j < TP; ++j) {
+        v[j] = __ffma2_rn(st.g[j], t2, st.lb[j]);
+        S[j] = f2(0.f, 0.f);
+    }
+    float chk = 0.f;
+    float fnew[TQ];
+    float2 R = f2(0.f, 0.f);
+    const float4* C4 = reinterpret_cast<const float4*>(Cs);
+    constexpr int kGroup = (TC % 2 == 0 && (2 * TC) % 4 == 0) ? (2 * TC) / 4 : 1;  // float4 chunks per two rows
+#pragma unroll
+    for (int c = 0; c < TQ * TC / 4; ++c) {
+        // keep the compiler from hoisting the whole tile into registers (that is what this variant exists to avoid):
+        // loads may not move above the end of the previous two-row group
+        if (c % kGroup == 0) asm volatile("" ::: "memory");
+        const float4 cv = C4[c];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            const int e = 4 * c + 2 * hlf, i = e / TC, j = (e % TC) / 2;  // compile-time after unrolling
+            const float2 cc = hlf ? f2(cv.z, cv.w) : f2(cv.x, cv.y);
+            const float2 uu = dup2(fmaf(st.f[i], t, st.la[i]));
+            const float2 x = __ffma2_rn(cc, nt2, __fadd2_rn(uu, v[j]));
+            const float2 ex = f2(ex2(x.x), ex2(x.y));
+            R = __fadd2_rn(R, ex);
+            S[j] = __fadd2_rn(S[j], ex);
+            if (j == TP - 1) {  // row i complete
+                const float l = lg2(R.x + R.y);
+                fnew[i] = fmaf(-scale, l - st.la[i], st.f[i]);
+                chk = fmaxf(chk, (i < ql) ? fabsf(l) : 0.f);
+                R = f2(0.f, 0.f);
+            }
+        }
+    }
+    float2 gnew[TP];
+#pragma unroll
+    for (int j = 0; j < TP; ++j) {
+        const float2 l = f2(lg2(S[j].x), lg2(S[j].y));
+        gnew[j] = __ffma2_rn(nscale2, __fadd2_rn(l, f2(-st.lb[j].x, -st.lb[j].y)), st.g[j]);
+        chk = fmaxf(chk, fmaxf((2 * j < cl) ? fabsf(l.x) : 0.f, (2 * j + 1 < cl) ? fabsf(l.y) : 0.f));
+    }
+    const bool bad = !(chk < 1e30f);
+    if (__builtin_expect(bad, 0)) {
+        // max-stabilised recomputation of both half-steps from the old potentials (rare): out of line, rolled loops
+        float buf[4 * TQ + 4 * TC];  // la, f, fnew | lb, g, gnew  (the helper works on memory)
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            buf[i] = st.la[i];
+            buf[TQ + i] = st.f[i];
+        }
+#pragma unroll
+        for (int j = 0; j < TP; ++j) {
+            buf[3 * TQ + 2 * j] = st.lb[j].x;
+            buf[3 * TQ + 2 * j + 1] = st.lb[j].y;
+            buf[3 * TQ + TC + 2 * j] = st.g[j].x;
+            buf[3 * TQ + TC + 2 * j + 1] = st.g[j].y;
+        }
+        stabilised_step_mem(Cs, TQ, TC, buf, eps, weight);
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) fnew[i] = buf[2 * TQ + i];
+#pragma unroll
+        for (int j = 0; j < TP; ++j) gnew[j] = f2(buf[3 * TQ + 2 * TC + 2 * j], buf[3 * TQ + 2 * TC + 2 * j + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < TQ; ++i) st.f[i] = (i < ql) ? fnew[i] : 0.f;
+#pragma unroll
+    for (int j = 0; j < TP; ++j) st.g[j] = f2((2 * j < cl) ? gnew[j].x : 0.f, (2 * j + 1 < cl) ? gnew[j].y : 0.f);
+}
+
+// Solve one pair in the calling thread with the cost tile in shared memory.  On entry Cs[i*TC+j] holds the distance for
+// i < ql, j < cl and anything >= 1e30 elsewhere (what phase 1 of the fused kernel writes); padded entries are
+// overwritten with 0 (any finite value works: their weight is exactly 0).
+template <int TQ, int TC, bool FULL>
+__device__ __forceinline__ void solve_pair_thread_stream(float* Cs, int ql_in, int cl_in, int b, int Sq_in, int Sc_in,
+                                                         const float* eps_sched, int n_eps, float inv_temp,
+                                                         const OtOut& out) {
+    constexpr int TP = TC / 2;
+    const int ql = FULL ? TQ : ql_in, cl = FULL ? TC : cl_in, Sq = FULL ? TQ : Sq_in, Sc = FULL ? TC : Sc_in;
+    PairStateS<TQ, TC> st;
+    const float kBig = 1.0e30f;
+    // marginals (pair_distances.py:57-60): row / column minima of the valid block, two small softmaxes
+    {
+        float x[TQ], mx = -INFINITY, s = 0.f;
+        float cb[TC];
+#pragma unroll
+        for (int j = 0; j < TC; ++j) cb[j] = kBig;
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            float best = kBig;
+#pragma unroll
+            for (int j = 0; j < TC; ++j) {
+                const float cij = (FULL || (i < ql && j < cl)) ? Cs[i * TC + j] : kBig;
+                best = fminf(best, cij);
+                cb[j] = fminf(cb[j], cij);
+            }
+            x[i] = -best * inv_temp;
+            if (i < ql) mx = fmaxf(mx, x[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) s += (i < ql) ? expf(x[i] - mx) : 0.f;
+        const float lse = mx + logf(s);
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            const float a = (i < ql) ? expf(x[i] - lse) : 0.f;
+            st.la[i] = (a > 0.f) ? log2f(a) : kLogZeroWeight * kLog2e;
+        }
+        float y[TC], my = -INFINITY, sy = 0.f;
+#pragma unroll
+        for (int j = 0; j < TC; ++j) {
+            y[j] = -cb[j] * inv_temp;
+            if (j < cl) my = fmaxf(my, y[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < TC; ++j) sy += (j < cl) ? expf(y[j] - my) : 0.f;
+        const float lsey = my + logf(sy);
+#pragma unroll
+        for (int j = 0; j < TP; ++j) {
+            const float b0 = (2 * j < cl) ? expf(y[2 * j] - lsey) : 0.f;
+            const float b1 = (2 * j + 1 < cl) ? expf(y[2 * j + 1] - lsey) : 0.f;
+            st.lb[j] = f2((b0 > 0.f) ? log2f(b0) : kLogZeroWeight * kLog2e, (b1 > 0.f) ? log2f(b1) : kLogZeroWeight * kLog2e);
+        }
+    }
+    if (!FULL) {
+#pragma unroll
+        for (int i = 0; i < TQ; ++i)
+#pragma unroll
+            for (int j = 0; j < TC; ++j)
+                if (!(i < ql && j < cl)) Cs[i * TC + j] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < TQ; ++i) st.f[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TP; ++j) st.g[j] = f2(0.f, 0.f);
+
+    if (ql > 0 && cl > 0) {
+#pragma unroll 1
+        for (int k = -1; k <= n_eps; ++k) {
+            const bool plain = (k < 0) | (k == n_eps);
+            sinkhorn_step_stream<TQ, TC, FULL>(st, Cs, ql, cl, eps_sched[min(max(k, 0), n_eps - 1)], plain ? 1.0f : 0.5f);
+        }
+    }
+
+    float dual = 0.f;
+#pragma unroll
+    for (int i = 0; i < TQ; ++i) dual = fmaf((i < ql) ? exp2f(st.la[i]) : 0.f, st.f[i], dual);
+#pragma unroll
+    for (int j = 0; j < TP; ++j) {
+        const float b0 = (2 * j < cl) ? exp2f(st.lb[j].x) : 0.f, b1 = (2 * j + 1 < cl) ? exp2f(st.lb[j].y) : 0.f;
+        dual = fmaf(b1, st.g[j].y, fmaf(b0, st.g[j].x, dual));
+    }
+    if (out.dual) out.dual[b] = dual;
+    if (out.f || out.alpha) {
+#pragma unroll
+        for (int i = 0; i < TQ; ++i)
+            if (i < Sq) {
+                if (out.f) out.f[(size_t)b * Sq + i] = st.f[i];
+                if (out.alpha) out.alpha[(size_t)b * Sq + i] = (i < ql) ? exp2f(st.la[i]) : 0.f;
+            }
+    }
+    if (out.g || out.beta) {
+#pragma unroll
+        for (int j = 0; j < TC; ++j)
+            if (j < Sc) {
+                if (out.g) out.g[(size_t)b * Sc + j] = (j & 1) ? st.g[j / 2].y : st.g[j / 2].x;
+                if (out.beta) out.beta[(size_t)b * Sc + j] = (j < cl) ? exp2f((j & 1) ? st.lb[j / 2].y : st.lb[j / 2].x) : 0.f;
+            }
+    }
+    if (out.primal || out.plan || out.weighted || out.neg_cost) {
+        const float tf = kLog2e / eps_sched[n_eps - 1];
+        float primal = 0.f;
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+            const float ai = (i < ql) ? exp2f(st.la[i]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < TC; ++j) {
+                if (i < Sq && j < Sc) {
+                    const bool valid = (i < ql && j < cl);
+                    const float cij = Cs[i * TC + j];
+                    const float gj = (j & 1) ? st.g[j / 2].y : st.g[j / 2].x;
+                    const float bj = (j < cl) ? exp2f((j & 1) ? st.lb[j / 2].y : st.lb[j / 2].x) : 0.f;
+                    const float p = valid ? ex2((st.f[i] + gj - cij) * tf) * (ai * bj) : 0.f;
+                    const float negc = valid ? -cij : 0.f;
+                    const float w = p * negc;
+                    primal += w;
+                    const size_t o = (size_t)b * Sq * Sc + i * Sc + j;
+                    if (out.neg_cost) out.neg_cost[o] = negc;
+                    if (out.plan) out.plan[o] = p;
+                    if (out.weighted) out.weighted[o] = w;
+                }
+            }
+        }
+        if (out.primal) out.primal[b] = primal;
+    }
+}
+
+}  // namespace asp
