@@ -524,7 +524,7 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
             tile = __shfl_sync(0xffffffffu, tile, 0);
             ticket = __shfl_sync(0xffffffffu, ticket, 0);
             const int sl = ticket % kV7Slots;
-            tc::mbar_wait(&empty_bar[w][sl], ((ticket / kV7Slots) & 1u) ^ 1u);  // the Sinkhorn warp is done with the slot
+            tc::mbar_wait_parked(&empty_bar[w][sl], ((ticket / kV7Slots) & 1u) ^ 1u);  // Sinkhorn warp done with the slot
             if (tile >= ntiles) {
                 if (lane == 0) {
                     meta_s[w][sl][1] = 0;
@@ -574,7 +574,7 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
                 if (ended >= 2) break;
                 const unsigned int t = t0 + k;
                 const int sl = t % kV7Slots;
-                while (!tc::mbar_try_wait(&full_bar[w][sl], (t / kV7Slots) & 1u)) __nanosleep(3000);
+                tc::mbar_wait_parked(&full_bar[w][sl], (t / kV7Slots) & 1u);
                 base[k] = meta_s[w][sl][0];
                 np[k] = meta_s[w][sl][1];
                 ft[k] = meta_s[w][sl][2];

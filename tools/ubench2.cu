@@ -70,6 +70,32 @@ __device__ __forceinline__ float ffma2_alu_chain(int iters, float a, float b, in
     return s;
 }
 
+// FFMA2 with THREE register-pair operands and 40 independent accumulators (the Gram tile's shape: acc[i][j] += q[i]*c[j])
+__global__ void __launch_bounds__(256, 1) k_ffma2_3reg(float* out, const float2* in, int iters, int warps_active) {
+    if ((int)(threadIdx.x >> 5) >= warps_active) return;
+    float2 a[5], b[8], acc[5][8];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) a[i] = in[threadIdx.x + 32 * i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = in[threadIdx.x + 32 * (5 + j)];
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int i = 0; i < 5; ++i) acc[i][j] = __ffma2_rn(a[i], b[j], acc[i][j]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j].x + acc[i][j].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // mode bits: 1 = warps 0-3 run the FMA chain, 2 = warps 4-7 run the ex2 chain; kind 0 = FFMA2, 1 = FFMA, 2 = FFMA2+LOP3
 __global__ void __launch_bounds__(256, 1) k_spec(float* out, int mode, int kind, int it_fma, int it_ex2, float a, float b) {
     const int warp = threadIdx.x >> 5;
@@ -111,6 +137,20 @@ int main() {
         float tb = timeit(sms, out, 3, kind, it_fma, it_ex2);
         printf("%-11s warps 0-3 alone %.3f ms | ex2 warps 4-7 alone %.3f ms | both %.3f ms  (perfect overlap %.3f, serial %.3f)\n",
                names[kind], tf, te, tb, tf > te ? tf : te, tf + te);
+    }
+    {
+        float2* in; cudaMalloc(&in, sizeof(float2) * 32 * 13 * 8); cudaMemset(in, 0, sizeof(float2) * 32 * 13 * 8);
+        int khz2 = 0; cudaDeviceGetAttribute(&khz2, cudaDevAttrClockRate, 0);
+        const int iters = 1 << 14;
+        for (int wa : {4, 8}) {
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_ffma2_3reg<<<sms, 256>>>(out, in, iters, wa); cudaDeviceSynchronize();
+            cudaEventRecord(e0); k_ffma2_3reg<<<sms, 256>>>(out, in, iters, wa); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double instr_per_smsp = (double)iters * 40 * (wa / 4);
+            printf("FFMA2 3-register-operand form, %d warp(s) per scheduler: %.3f ms -> %.2f clk per FFMA2 per scheduler at %d kHz\n",
+                   wa / 4, ms, ms * 1e-3 * khz2 * 1e3 / instr_per_smsp, khz2);
+        }
     }
     // clocks per instruction for the single-warp-per-scheduler chains
     int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
