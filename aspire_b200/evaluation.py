@@ -167,3 +167,46 @@ class CachingScoringModel:
         scores = self.predict(query_pid, cand_pids, pid2abstract, facet)['cand_scores']
         assert len(scores) == len(cand_pids)
         return [[c, s] for c, s in rank_candidates(list(cand_pids), scores)]
+
+
+def sorted_relevancies(results, dataset, facet=None):
+    """{qpid: [relevance of each candidate in the model's rank order]} (utils/utils.py:70-82 ``load_score_results``).
+    ``results``: what ``score`` returns / writes: {qpid: [[cpid, -similarity], ...]} best first."""
+    gold = dataset.get_gold_test_data(facet)
+    return {q: [gold[q][cand] for cand, _ in ranked] for q, ranked in results.items()}
+
+
+def evaluate(results, dataset, facet=None, results_dir=None, pr_atks=(5, 10, 20), split_of=None):
+    """Per-query and aggregated ranking metrics of a scored test pool (evaluate.py:85-157).
+
+    Returns (per_query: list of dicts, aggregated: list of dicts, one per (facet, split)).  When ``results_dir`` is
+    given, writes ``query-evaluations[-facet].csv`` and ``aggregated-evaluations[-facet].csv`` there with the
+    reference's columns (utils/utils.py:62-65); aggregated values are rounded to 4 places as in the reference.
+    ``split_of``: optional {qpid: 'dev'|'test'} (``{ds}-evaluation_splits.json`` in evaluate.py's reading); default 'test'.
+    """
+    from . import metrics as M
+    facet_key = 'unfaceted' if facet is None else facet
+    thr = dataset.get_threshold_grade()
+    per_query = []
+    for qpid, rels in sorted_relevancies(results, dataset, facet).items():
+        m = M.compute_metrics(rels, pr_atks=list(pr_atks), threshold_grade=thr)
+        m['facet'] = facet_key
+        m['split'] = 'test' if split_of is None else split_of[qpid]
+        m['paper_id'] = qpid
+        m['title'] = dataset.get(qpid)['TITLE']
+        per_query.append(m)
+    metric_cols = [k for k in per_query[0] if k not in ('facet', 'split', 'paper_id', 'title')] if per_query else []
+    aggregated = []
+    for split in sorted({m['split'] for m in per_query}):
+        rows = [m for m in per_query if m['split'] == split]
+        agg = {k: round(float(np.mean([r[k] for r in rows])), 4) for k in metric_cols}
+        agg['facet'] = facet_key
+        agg['split'] = split
+        aggregated.append(agg)
+    if results_dir is not None:
+        import pandas as pd
+        os.makedirs(results_dir, exist_ok=True)
+        suffix = '' if facet is None else f'-{facet}'
+        pd.DataFrame(per_query).to_csv(os.path.join(results_dir, f'query-evaluations{suffix}.csv'), index=False)
+        pd.DataFrame(aggregated).to_csv(os.path.join(results_dir, f'aggregated-evaluations{suffix}.csv'), index=False)
+    return per_query, aggregated

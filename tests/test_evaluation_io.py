@@ -62,3 +62,30 @@ def test_dataset_reader_and_scores_file(tmp_path):
 def test_rank_candidates_is_stable_descending():
     r = rank_candidates(["a", "b", "c", "d"], [1.0, 3.0, 1.0, 3.0])
     assert r == [("b", 3.0), ("d", 3.0), ("a", 1.0), ("c", 1.0)]
+
+
+def test_evaluate_writes_reference_csvs(tmp_path):
+    """score -> evaluate: per-query metrics equal compute_metrics on the gold relevances in rank order, the aggregate
+    is the rounded mean, and the two CSV files carry the reference's names and columns (evaluate.py:118-157)."""
+    import pandas as pd
+    from aspire_b200.evaluation import evaluate, sorted_relevancies
+    from aspire_b200 import metrics as M
+    name, pool = _write_dataset(str(tmp_path), n=30)
+    ds = EvalDataset(name, str(tmp_path))
+    res = score(_LenModel(name="len", encoding_type="sentence"), ds, None, None)
+    rels = sorted_relevancies(res, ds)
+    gold = ds.get_gold_test_data()
+    assert rels["1000"] == [gold["1000"][c] for c, _ in res["1000"]]
+    out_dir = str(tmp_path / "results")
+    per_query, agg = evaluate(res, ds, None, results_dir=out_dir)
+    assert [m["paper_id"] for m in per_query] == ["1000", "1001"]
+    want = M.compute_metrics(rels["1001"], [5, 10, 20], ds.get_threshold_grade())
+    for k, v in want.items():
+        assert per_query[1][k] == v
+    assert per_query[0]["title"] == "title 0" and per_query[0]["facet"] == "unfaceted" and per_query[0]["split"] == "test"
+    assert len(agg) == 1 and agg[0]["split"] == "test"
+    assert agg[0]["av_precision"] == round((per_query[0]["av_precision"] + per_query[1]["av_precision"]) / 2, 4)
+    q = pd.read_csv(os.path.join(out_dir, "query-evaluations.csv"))
+    a = pd.read_csv(os.path.join(out_dir, "aggregated-evaluations.csv"))
+    assert {"av_precision", "ndcg%20", "precision@5", "recall@20", "r_precision", "facet", "split", "paper_id", "title"} <= set(q.columns)
+    assert len(q) == 2 and len(a) == 1 and abs(a["ndcg%20"][0] - agg[0]["ndcg%20"]) < 1e-12
