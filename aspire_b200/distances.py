@@ -208,6 +208,88 @@ def allpair_masked_dist_l2max(query, cand, return_pair_sims=False):
     return (-1 * best).to(out_dev)
 
 
+def pair_heads(q, q_lens, c, c_lens, temp=1.0, want=("top2",), raw_pads=False):
+    """l2top2 / attention heads on contiguous fp32 CUDA tensors (paired): one ``asp_pair_cost`` + one ``asp_pair_heads``.
+
+    Returns a dict with any of ``top2`` [B], ``att`` [B], ``att_probs`` [B,Sq,Sc], plus ``dist`` [B,Sq,Sc] (distances;
+    0 on padding, or the raw distances to the zero pad rows with ``raw_pads`` -- what the attention head's
+    ``pair_sims`` holds in the reference, pair_distances.py:121-127).
+    """
+    _abi.require_cuda(q, c, q_lens, c_lens)
+    B, Sc, D = c.shape
+    Sq = q.shape[1]
+    dev = c.device
+    L = _abi.lib()
+    dist = torch.empty((B, Sq, Sc), dtype=torch.float32, device=dev)
+    if raw_pads:
+        fq = torch.full_like(q_lens, Sq)
+        fc = torch.full_like(c_lens, Sc)
+        _abi.check(L.asp_pair_cost(_abi.ptr(q), _abi.ptr(fq), 0, _abi.ptr(c), _abi.ptr(fc), B, Sq, Sc, D, _abi.ptr(dist),
+                                   _abi.stream_of(dev)), "asp_pair_cost")
+    else:
+        _abi.check(L.asp_pair_cost(_abi.ptr(q), _abi.ptr(q_lens), 0, _abi.ptr(c), _abi.ptr(c_lens), B, Sq, Sc, D,
+                                   _abi.ptr(dist), _abi.stream_of(dev)), "asp_pair_cost")
+    res = {"dist": dist}
+    shapes = {"top2": (B,), "att": (B,), "att_probs": (B, Sq, Sc)}
+    for k in want:
+        res[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
+    _abi.check(L.asp_pair_heads(_abi.ptr(dist), _abi.ptr(q_lens), 1, _abi.ptr(c_lens), B, Sq, Sc, float(temp),
+                                _abi.ptr(res.get("top2")), _abi.ptr(res.get("att")), _abi.ptr(res.get("att_probs")),
+                                _abi.stream_of(dev)), "asp_pair_heads")
+    return res
+
+
+def _pair_inputs(query, cand):
+    out_dev = query.embed.device
+    dev = query.embed.device if query.embed.is_cuda else _device()
+    qef_batch_size, _, qmax_sents = query.embed.size()
+    cef_batch_size, encoding_dim, cmax_sents = cand.embed.size()
+    assert (qef_batch_size == cef_batch_size)
+    return (_as_bsd(query.embed, dev), _lens_tensor(query.abs_lens, dev), _as_bsd(cand.embed, dev),
+            _lens_tensor(cand.abs_lens, dev), out_dev)
+
+
+def allpair_masked_dist_l2topk(query, cand, return_pair_sims=False):
+    """Drop-in for pair_distances.allpair_masked_dist_l2topk (:295-345): the two best sentence matches.
+
+    return_pair_sims=True -> (batch_sims [B] = sum of the two largest -dist, pair_sims [B,Sq,Sc] with -1e9 on padding);
+    False -> the positive distance -sum.  Fewer than two valid sentence pairs: the runner-up is a masked entry (-1e9),
+    as in the reference; a 1x1 padded shape raises like ``torch.topk(k=2)`` does there.
+    """
+    q, ql, c, cl, out_dev = _pair_inputs(query, cand)
+    if q.shape[1] * c.shape[1] < 2:
+        raise RuntimeError("selected index k out of range")  # torch.topk(k=2) over a single entry (:336)
+    res = pair_heads(q, ql, c, cl, want=("top2",))
+    if return_pair_sims:
+        B, Sq, Sc = res["dist"].shape
+        valid = (torch.arange(Sq, device=q.device)[None, :, None] < ql[:, None, None]) & \
+                (torch.arange(Sc, device=q.device)[None, None, :] < cl[:, None, None])
+        pair_sims = torch.where(valid, -res["dist"], torch.full_like(res["dist"], -10e8))
+        return res["top2"].to(out_dev), pair_sims.to(out_dev)
+    return (-1 * res["top2"]).to(out_dev)
+
+
+class AllPairMaskedAttention:
+    """Drop-in for pair_distances.AllPairMaskedAttention (:95-135): cross-document attention over sentence pairs."""
+
+    def __init__(self, model_hparams):
+        self.cdatt_sm_temp = model_hparams.get('cdatt_sm_temp', 1.0)
+
+    def compute_distance(self, query, cand, return_pair_sims=False):
+        """
+        :param query / cand: namedtuple(embed: batch_size x encoding_dim x max_sents; abs_lens: list(int))
+        :return: return_pair_sims=True -> (doc_sims [B], [pair_sims, pair_softmax, masked_sims]);
+                 False -> doc_dists [B] = sum softmax * dist (the training loss' distance).
+        """
+        q, ql, c, cl, out_dev = _pair_inputs(query, cand)
+        res = pair_heads(q, ql, c, cl, temp=self.cdatt_sm_temp, want=("att", "att_probs"), raw_pads=True)
+        if return_pair_sims:
+            pair_sims = -res["dist"]
+            masked_sims = res["att_probs"] * pair_sims
+            return res["att"].to(out_dev), [pair_sims.to(out_dev), res["att_probs"].to(out_dev), masked_sims.to(out_dev)]
+        return (-1 * res["att"]).to(out_dev)
+
+
 def allpair_masked_argmax_l2max(query, cand):
     """The flat argmax ``i*cmax_sents + j`` the reference computes at pair_distances.py:176 and drops."""
     dev = query.embed.device if query.embed.is_cuda else _device()

@@ -188,6 +188,19 @@ int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, const float
                  int B, int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp,
                  const asp_ot_outputs* out, void* workspace, size_t workspace_bytes, asp_stream_t stream);
 
+/*
+ * Other aggregation heads on a distance tensor [B,Sq,Sc] written by asp_pair_cost (valid block only is read):
+ *   top2      [B]        sum of the two largest (-dist) -- allpair_masked_dist_l2topk,
+ *                        src/learning/facetid_models/pair_distances.py:295-345 (a missing runner-up is the reference's
+ *                        mask constant -1e9);
+ *   att       [B]        sum softmax(-dist/temp) * (-dist) over the valid block -- AllPairMaskedAttention,
+ *                        pair_distances.py:95-135 + models_common/activations.py:35-61;
+ *   att_probs [B,Sq,Sc]  that softmax (0 on padding).
+ * Any of the three outputs may be NULL.  q_group = consecutive candidates sharing one entry of q_lens (1 = paired).
+ */
+int asp_pair_heads(const float* cost, const int32_t* q_lens, int q_group, const int32_t* c_lens, int B, int Sq, int Sc,
+                   float temp, float* top2, float* att, float* att_probs, asp_stream_t stream);
+
 /* Same solver on a precomputed cost tensor [B,Sq,Sc] (as written by asp_pair_cost). */
 int asp_ot_sinkhorn_from_cost(const float* cost, const int32_t* q_lens, int q_broadcast, const int32_t* c_lens,
                               int B, int Sq, int Sc, const float* eps_host, int n_eps, float temp,

@@ -148,3 +148,24 @@ def average_precision(ranked_rel):
 def mean_average_precision(ranked_rels):
     """src/evaluation/utils/metrics.py:124-143."""
     return float(np.mean([average_precision(r) for r in ranked_rels]))
+
+
+def l2top2(q, q_lens, c, c_lens):
+    """allpair_masked_dist_l2topk (pair_distances.py:295-345), return_pair_sims=True branch: (sum of the two largest
+    entries of -cdist + pad mask [B], the masked similarities [B,Sq,Sc]).  q [B,Sq,D], c [B,Sc,D]."""
+    sims = neg_pair_dists(q, c) + _pad_mask(q_lens, c_lens, q.shape[1], c.shape[1])
+    top = torch.topk(sims.reshape(sims.shape[0], -1), k=2, dim=1)[0]
+    return top.sum(dim=1), sims
+
+
+def attention_sim(q, q_lens, c, c_lens, temp=1.0):
+    """AllPairMaskedAttention.compute_distance (pair_distances.py:95-135), return_pair_sims=True branch, with
+    masked_2d_softmax (models_common/activations.py:35-61): (doc_sims [B], softmax [B,Sq,Sc])."""
+    sims = neg_pair_dists(q, c)
+    B, Sq, Sc = sims.shape
+    mask = torch.zeros_like(sims)
+    for b, (a, d) in enumerate(zip(q_lens, c_lens)):
+        mask[b, a:, :] = -1e32
+        mask[b, :, d:] = -1e32
+    probs = torch.log_softmax((sims / temp + mask).reshape(B, -1), dim=1).reshape(B, Sq, Sc).exp()
+    return (probs * sims).sum(dim=(1, 2)), probs

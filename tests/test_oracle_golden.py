@@ -109,3 +109,18 @@ def test_metrics_known_answers():
     assert abs(ar.average_precision(m["average_precision"]["r"]) - m["average_precision"]["value"]) < 1e-12
     assert abs(ar.mean_average_precision(m["mean_average_precision"]["rs"]) -
                m["mean_average_precision"]["value"]) < 1e-12
+
+
+def test_heads_oracle_vs_reference_golden():
+    """l2top2 / attention restatements (oracle/aspire_ref.py) against the unmodified reference's outputs."""
+    z = np.load(os.path.join(GOLDEN, "heads.npz"))
+    q, c = torch.from_numpy(z["q"]), torch.from_numpy(z["c"])
+    ql, cl = z["q_lens"].tolist(), z["c_lens"].tolist()
+    top2, sims = ar.l2top2(q, ql, c, cl)
+    np.testing.assert_allclose(top2.numpy(), z["top2_sims"], rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(sims.numpy(), z["top2_pair"], rtol=1e-6, atol=1e-5)
+    assert z["top2_sims"][0] <= -9e8  # single valid pair: the runner-up is the mask constant
+    for temp in (1.0, 0.25):
+        doc, probs = ar.attention_sim(q, ql, c, cl, temp)
+        np.testing.assert_allclose(doc.numpy(), z[f"att_sims_t{temp}"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(probs.numpy(), z[f"att_softmax_t{temp}"], rtol=1e-5, atol=1e-7)

@@ -129,3 +129,33 @@ def test_allpairs_tensor_core_path_vs_pair_kernel_and_fp64(NQ, NC, S, D):
     # one query through the streaming pair kernel (exact fp32 FMA) agrees too
     best, pidx, _ = l2max_scores(q[2:3].cuda(), ql[2:3].cuda(), c.cuda(), cl.cuda(), broadcast_query=True)
     assert (best.cpu() - scores.cpu()[2]).abs().max().item() <= 2e-5
+
+
+def test_l2top2_and_attention_heads_vs_reference_golden():
+    """allpair_masked_dist_l2topk and AllPairMaskedAttention (pair_distances.py:95-135,295-345) through
+    asp_pair_cost + asp_pair_heads, against vectors produced by the unmodified reference (oracle/make_golden_heads.py)."""
+    from aspire_b200 import AllPairMaskedAttention, allpair_masked_dist_l2topk, rep_len_tup
+    z = np.load(os.path.join(GOLDEN, "heads.npz"))
+    q, c = torch.from_numpy(z["q"]).cuda(), torch.from_numpy(z["c"]).cuda()
+    ql, cl = z["q_lens"].tolist(), z["c_lens"].tolist()
+    qt = rep_len_tup(embed=q.permute(0, 2, 1), abs_lens=ql)
+    ct = rep_len_tup(embed=c.permute(0, 2, 1), abs_lens=cl)
+    sims, pair = allpair_masked_dist_l2topk(query=qt, cand=ct, return_pair_sims=True)
+    np.testing.assert_allclose(sims.cpu().numpy(), z["top2_sims"], rtol=2e-6, atol=3e-5)
+    np.testing.assert_allclose(pair.cpu().numpy(), z["top2_pair"], rtol=2e-6, atol=3e-5)
+    dist = allpair_masked_dist_l2topk(query=qt, cand=ct, return_pair_sims=False)
+    np.testing.assert_allclose(dist.cpu().numpy(), z["top2_dist"], rtol=2e-6, atol=3e-5)
+    assert sims[0].item() <= -9e8  # one valid sentence pair: runner-up = mask constant, as in the reference
+    for temp in (1.0, 0.25):
+        att = AllPairMaskedAttention({"cdatt_sm_temp": temp})
+        doc, (pair_sims, softmax, masked) = att.compute_distance(query=qt, cand=ct, return_pair_sims=True)
+        np.testing.assert_allclose(doc.cpu().numpy(), z[f"att_sims_t{temp}"], rtol=2e-5, atol=3e-5)
+        np.testing.assert_allclose(softmax.cpu().numpy(), z[f"att_softmax_t{temp}"], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(pair_sims.cpu().numpy(), z[f"att_pair_t{temp}"], rtol=2e-6, atol=3e-5)
+        np.testing.assert_allclose(masked.cpu().numpy(), z[f"att_masked_t{temp}"], rtol=2e-4, atol=3e-6)
+        dd = att.compute_distance(query=qt, cand=ct, return_pair_sims=False)
+        np.testing.assert_allclose(dd.cpu().numpy(), z[f"att_dists_t{temp}"], rtol=2e-5, atol=3e-5)
+        # padding of the softmax is exactly zero
+        sm = softmax.cpu().numpy()
+        for b, (a_, b_) in enumerate(zip(ql, cl)):
+            assert np.all(sm[b, a_:] == 0) and np.all(sm[b, :, b_:] == 0)
