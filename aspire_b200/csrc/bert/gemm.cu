@@ -207,6 +207,28 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols
     return ASP_OK;
 }
 
+// Same matrix, [box_rows x 32] box (64-byte rows) with the 64B swizzle -- the all-pairs kernel's K block.
+int make_tmap_bf16_k32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return ASP_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {32u, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (k32) failed with code %d (ptr %p rows %llu cols %llu)", (int)r, ptr,
+                  (unsigned long long)rows, (unsigned long long)cols);
+        return ASP_ERR_CUDA;
+    }
+    return ASP_OK;
+}
+
 template <int BLOCK_N, int EPI>
 static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
                        const GemmArgs& g, cudaStream_t stream) {

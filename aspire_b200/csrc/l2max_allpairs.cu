@@ -21,13 +21,29 @@ namespace asp {
 
 using namespace tc;
 
-int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+int make_tmap_bf16_k32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
-constexpr int kApStages = 4;
-constexpr int kApBlockM = 128, kApBlockN = 160, kApBlockK = 64;
-constexpr int kApABytes = kApBlockM * kApBlockK * 2, kApBBytes = kApBlockN * kApBlockK * 2;
-constexpr int kApStage = kApABytes + kApBBytes;
-constexpr int kApSmem = kApStages * kApStage + 128 + kApBlockM * 17 * 8 + 1024;
+// One pipeline stage = one 32-wide K block of ALL FOUR operand tiles (A_hi, A_lo, B_hi, B_lo), each loaded exactly once
+// and used by the four split-precision MMAs of that block (an earlier version reloaded A and B for every term: twice
+// the L2 -> shared-memory traffic, which is what bounded it).  64-byte rows, 64B swizzle.
+constexpr int kApStages = 2;  // 94 KB per CTA: TWO CTAs per SM, so one tile's epilogue runs under the other's main loop
+constexpr int kApBlockM = 128, kApBlockN = 160, kApBlockK = 32;
+constexpr int kApABytes = kApBlockM * kApBlockK * 2, kApBBytes = kApBlockN * kApBlockK * 2;  // 8 KB, 10 KB
+constexpr int kApStage = 2 * kApABytes + 2 * kApBBytes;                                     // 36 KB
+constexpr int kApEpi = 128 + kApBlockM * 17 * 8 + kApBlockN * 4 + 64;  // barriers, per-row minima, |c|^2 of the tile, lens
+constexpr int kApSmem = kApStages * kApStage + kApEpi + 1024;
+
+// Shared-memory matrix descriptor of a K-major tile stored as 64-byte rows with the 64B swizzle (what TMA writes with
+// CU_TENSOR_MAP_SWIZZLE_64B and a 64-byte inner box): 8-row groups are 512 B apart, layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
 
 struct AllPairsArgs {
     const float* qn;        // [NQ*S] squared norms of the query sentence rows
@@ -79,13 +95,15 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
     float* ep_d2 = reinterpret_cast<float*>(smem + kApStages * kApStage + 128);  // [128][17] min d^2 per (row, cand doc)
     int* ep_j = reinterpret_cast<int*>(ep_d2 + kApBlockM * 17);                  // [128][17] its column within the doc
+    float* cn_s = reinterpret_cast<float*>(ep_j + kApBlockM * 17);               // [160] |c|^2 of the tile's columns
+    int* cl_s = reinterpret_cast<int*>(cn_s + kApBlockN);                        // [16] lengths of the tile's cand docs
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = g.S;
     const int qd0 = blockIdx.x * g.docs_m, cd0 = blockIdx.y * g.docs_n;  // first query / candidate document of the tile
     const int m0 = qd0 * S, n0 = cd0 * S;
     const int rows_m = g.docs_m * S, cols_n = g.docs_n * S;
-    const int total = (g.D / kApBlockK) * 4;  // hi.hi, hi.lo, lo.hi, lo.lo per K block
+    const int total = g.D / kApBlockK;  // K blocks; each carries hi.hi, hi.lo, lo.hi, lo.lo
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tq_hi);
@@ -106,12 +124,13 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
     if (warp == 0 && lane == 0) {
         for (int it = 0; it < total; ++it) {
             const int s = it % kApStages, ph = (it / kApStages) & 1;
-            const int kb = it >> 2, term = it & 3;
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full[s], (uint32_t)(rows_m + cols_n) * (kApBlockK * 2));
+            mbar_arrive_expect_tx(&full[s], (uint32_t)(rows_m + cols_n) * (kApBlockK * 2) * 2);
             uint8_t* sa = smem + s * kApStage;
-            tma_load_2d(sa, (term & 2) ? &tq_lo : &tq_hi, &full[s], kb * kApBlockK, m0);
-            tma_load_2d(sa + kApABytes, (term & 1) ? &tc_lo : &tc_hi, &full[s], kb * kApBlockK, n0);
+            tma_load_2d(sa, &tq_hi, &full[s], it * kApBlockK, m0);
+            tma_load_2d(sa + kApABytes, &tq_lo, &full[s], it * kApBlockK, m0);
+            tma_load_2d(sa + 2 * kApABytes, &tc_hi, &full[s], it * kApBlockK, n0);
+            tma_load_2d(sa + 2 * kApABytes + kApBBytes, &tc_lo, &full[s], it * kApBlockK, n0);
         }
     } else if (warp == 1 && lane == 0) {
         constexpr uint32_t idesc = umma_idesc_bf16(kApBlockM, kApBlockN);
@@ -120,10 +139,15 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
             mbar_wait(&full[s], ph);
             tc_fence_after_sync();
             const uint32_t sa = smem_u32(smem + s * kApStage);
-            const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + kApABytes);
+            const uint64_t a_hi = umma_desc_sw64(sa), a_lo = umma_desc_sw64(sa + kApABytes);
+            const uint64_t b_hi = umma_desc_sw64(sa + 2 * kApABytes), b_lo = umma_desc_sw64(sa + 2 * kApABytes + kApBBytes);
 #pragma unroll
-            for (int k = 0; k < kApBlockK / 16; ++k)
-                umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            for (int k = 0; k < kApBlockK / 16; ++k) {  // 16 bf16 = 32 bytes along K inside the swizzle atom
+                umma_bf16(tmem_base, a_lo + 2 * k, b_lo + 2 * k, idesc, (it | k) != 0);  // small terms first
+                umma_bf16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, true);
+                umma_bf16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, true);
+                umma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, true);
+            }
             umma_commit(&empty[s]);
         }
         umma_commit(accum);
@@ -131,6 +155,14 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
     __syncwarp();
 
     // ---------------- epilogue ----------------
+    // (warps 2 and 3, idle during the main loop, stage the tile's |c|^2 and candidate lengths in shared memory)
+    if (warp >= 2) {
+        for (int t = threadIdx.x - 64; t < kApBlockN; t += 64)
+            cn_s[t] = (t < cols_n && n0 + t < g.NC * S) ? __ldg(g.cn + n0 + t) : 0.f;
+        for (int t = threadIdx.x - 64; t < 16; t += 64)
+            cl_s[t] = (t < g.docs_n && cd0 + t < g.NC) ? min(max(__ldg(g.c_lens + cd0 + t), 0), S) : 0;
+    }
+    __syncthreads();
     mbar_wait(accum, 0);
     tc_fence_after_sync();
     const int r = warp * 32 + lane;  // accumulator row = query sentence row m0 + r
@@ -146,9 +178,8 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
         for (int e = 0; e < 32; ++e) {
             const int col = c0 + e;
             if (col < cols_n) {
-                const int cl = (cd0 + cdoc < g.NC) ? min(max(__ldg(g.c_lens + cd0 + cdoc), 0), S) : 0;
-                const float cnv = (n0 + col < g.NC * S) ? __ldg(g.cn + n0 + col) : 0.f;
-                const float d2 = qn + cnv - 2.f * v[e];
+                const int cl = cl_s[cdoc & 15];
+                const float d2 = qn + cn_s[col] - 2.f * v[e];
                 if (j < cl && d2 < best) {
                     best = d2;
                     best_j = j;
@@ -241,10 +272,10 @@ extern "C" int asp_l2max_allpairs(const float* q, const int32_t* q_lens, int NQ,
     const int docs_m = kApBlockM / S, docs_n = kApBlockN / S;
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     int rc;
-    if ((rc = make_tmap_bf16(&tq_hi, q_hi, qrows, D, docs_m * S))) return rc;
-    if ((rc = make_tmap_bf16(&tq_lo, q_lo, qrows, D, docs_m * S))) return rc;
-    if ((rc = make_tmap_bf16(&tc_hi, c_hi, crows, D, docs_n * S))) return rc;
-    if ((rc = make_tmap_bf16(&tc_lo, c_lo, crows, D, docs_n * S))) return rc;
+    if ((rc = make_tmap_bf16_k32(&tq_hi, q_hi, qrows, D, docs_m * S))) return rc;
+    if ((rc = make_tmap_bf16_k32(&tq_lo, q_lo, qrows, D, docs_m * S))) return rc;
+    if ((rc = make_tmap_bf16_k32(&tc_hi, c_hi, crows, D, docs_n * S))) return rc;
+    if ((rc = make_tmap_bf16_k32(&tc_lo, c_lo, crows, D, docs_n * S))) return rc;
     AllPairsArgs g{qn, cn, q_lens, c_lens, NQ, NC, S, D, docs_m, docs_n, q, c, scores, flat_idx};
     static thread_local int attr_dev = -1;
     int dev = 0;

@@ -284,7 +284,12 @@ class AllPairMaskedAttention:
         q, ql, c, cl, out_dev = _pair_inputs(query, cand)
         res = pair_heads(q, ql, c, cl, temp=self.cdatt_sm_temp, want=("att", "att_probs"), raw_pads=True)
         if return_pair_sims:
-            pair_sims = -res["dist"]
+            # pad-vs-pad entries: both rows are zero vectors, torch.cdist gives exactly 0 there (the cost kernel's
+            # 1e-8 clamp under the square root would give 1e-4)
+            Sq, Sc = res["dist"].shape[1:]
+            both_pad = (torch.arange(Sq, device=q.device)[None, :, None] >= ql[:, None, None]) & \
+                       (torch.arange(Sc, device=q.device)[None, None, :] >= cl[:, None, None])
+            pair_sims = -torch.where(both_pad, torch.zeros_like(res["dist"]), res["dist"])
             masked_sims = res["att_probs"] * pair_sims
             return res["att"].to(out_dev), [pair_sims.to(out_dev), res["att_probs"].to(out_dev), masked_sims.to(out_dev)]
         return (-1 * res["att"]).to(out_dev)
