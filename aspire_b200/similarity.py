@@ -302,12 +302,108 @@ class AspireModel(SimilarityModel):
         return (res[want] if return_primal else -res[want]).cpu()
 
 
+class AspireNER(AspireModel):
+    """otAspire with input augmentation: the entities extracted from the abstract's sentences are appended to it as
+    extra "sentences" (utils/models.py:211-233); everything downstream is the plain AspireModel path."""
+
+    def encode(self, batch_papers: List[Dict]):
+        assert 'ENTITIES' in batch_papers[0], 'No NER data for input. Please run NER/extract_entity.py and' \
+                                             ' place result in {dataset_dir}/{dataset_name}-ner.jsonl'
+        return super(AspireNER, self).encode(self._append_entities(batch_papers))
+
+    @staticmethod
+    def _append_entities(batch_papers):
+        out = []
+        for sample in batch_papers:
+            entities = [e for sent_entities in sample['ENTITIES'] for e in sent_entities]
+            out.append({'TITLE': sample['TITLE'], 'ABSTRACT': sample['ABSTRACT'] + entities})
+        return out
+
+
+class AspireContextNER(AspireModel):
+    """otAspire where every entity is represented by the mean of the contextual token vectors of its span inside the
+    sentence it occurs in (utils/models.py:607-734 with AspireConSenContextual :413-507).  The sentence spans and the
+    entity spans go through the SAME span mean-pool kernel (K1) over one encoder forward; a paper's encoding is its
+    sentence rows followed by the rows of the entities that could be located in the tokenisation."""
+
+    def encode(self, input_data: List[Dict]):
+        from .consent import span_mean_pool, spans_from_token_idxs
+        bert_batch, abs_lens, sent_token_idxs, ner_token_idxs = self._preprocess_input(input_data)
+        # one list of spans per paper: sentences first, then the entities that were found (contiguous token ranges)
+        merged, kept = [], []
+        for sents, ners in zip(sent_token_idxs, ner_token_idxs):
+            found = [n for n in ners if len(n) > 0]
+            merged.append(list(sents) + found)
+            kept.append(len(found))
+        dev = self.model._device()
+        tokid_tt, seg_tt, attnmask_tt = (bert_batch[k].to(dev, non_blocking=True)
+                                         for k in ('tokid_tt', 'seg_tt', 'attnmask_tt'))
+        with torch.no_grad():
+            hidden = self.model.encode_hidden(tokid_tt, seg_tt, attnmask_tt, seq_lens=bert_batch.get('seq_lens'))
+            spans = spans_from_token_idxs(merged, max(len(m) for m in merged)).to(dev, non_blocking=True)
+            _, reps = span_mean_pool(hidden, spans)
+        out_dev = bert_batch['tokid_tt'].device
+        return [reps[i, :abs_lens[i] + kept[i]].to(out_dev) for i in range(len(abs_lens))]
+
+    def _preprocess_input(self, input_data):
+        bert_batch, abs_lens, sent_token_idxs = prepare_abstracts(batch_abs=input_data, pt_lm_tokenizer=self.tokenizer)
+        return bert_batch, abs_lens, sent_token_idxs, self._get_ner_token_idxs(input_data, sent_token_idxs)
+
+    def _get_ner_token_idxs(self, input_data, sent_token_idxs):
+        """Token positions of every entity: the entity's word pieces are searched in its sentence's word pieces; an
+        entity that is not found, or that falls (partly) behind the 500-piece truncation, gets [] (:661-682)."""
+        all_idxs = []
+        for sample, sample_sent_idxs in zip(input_data, sent_token_idxs):
+            sample_idxs = []
+            for ners, sentence, token_idxs in zip(sample['ENTITIES'], sample['ABSTRACT'], sample_sent_idxs):
+                tokens = self.tokenizer.tokenize(sentence)
+                for ner in ners:
+                    rng = self.find_sublist_range(tokens, self.tokenizer.tokenize(ner))
+                    if rng and rng[-1] < len(token_idxs):
+                        sample_idxs.append([token_idxs[k] for k in rng])
+                    else:
+                        sample_idxs.append([])
+            all_idxs.append(sample_idxs)
+        return all_idxs
+
+    @staticmethod
+    def find_sublist_range(suplist: List, sublist: List):
+        """Positions of the first occurrence of ``sublist`` inside ``suplist`` (None when absent; :684-698)."""
+        n, m = len(suplist), len(sublist)
+        for i in range(n):
+            if i + m <= n and suplist[i:i + m] == sublist:
+                return list(range(i, i + m))
+        return None
+
+    def get_faceted_encoding(self, unfaceted_encoding, facet: str, input_data: Dict):
+        """Entities without an encoding (see _get_ner_token_idxs) are dropped from the entity lists before the usual
+        facet filter, so row indices line up with what ``encode`` produced (:709-734)."""
+        _, _, _, ner_token_idxs = self._preprocess_input([input_data])
+        is_valid = [len(x) > 0 for x in ner_token_idxs[0]]
+        # NOTE: as in the reference (:721-729) the cursor into is_valid advances only past VALID entities, so the first
+        # entity without an encoding also removes every entity after it; kept for result parity.
+        cursor, filtered = 0, []
+        for sent_ners in input_data['ENTITIES']:
+            keep = []
+            for entity in sent_ners:
+                if is_valid[cursor]:
+                    keep.append(entity)
+                    cursor += 1
+            filtered.append(keep)
+        return super(AspireContextNER, self).get_faceted_encoding(unfaceted_encoding, facet,
+                                                                  {**input_data, 'ENTITIES': filtered})
+
+
 def get_model(model_name, trained_model_path=None) -> SimilarityModel:
     """Factory (utils/models.py:738-768) for the model names on the fine-grained scoring path."""
     if model_name in {'aspire_compsci', 'aspire_biomed'}:
         return AspireModel(name=model_name, encoding_type='sentence')
     if model_name in {'tsaspire_compsci', 'tsaspire_biomed'}:
         return AspireModel(name=model_name, encoding_type='sentence', score_aggregation='l2max')
+    if model_name in {'aspire_ner_compsci', 'aspire_ner_biomed'}:
+        return AspireNER(name=model_name, encoding_type='sentence-entity')
+    if model_name in {'aspire_context_ner_compsci', 'aspire_context_ner_biomed'}:
+        return AspireContextNER(name=model_name, encoding_type='sentence-entity')
     raise NotImplementedError(f"No Implementation for model {model_name}")
 
 

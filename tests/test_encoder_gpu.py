@@ -80,3 +80,24 @@ def test_readme_example_end_to_end_vs_reference_golden():
     ct = rep_len_tup(embed=reps[1:2].permute(0, 2, 1), abs_lens=[al[1]])
     score, _ = allpair_masked_dist_l2max(query=qt, cand=ct, return_pair_sims=True)
     assert abs(score.item() - float(z["ts_score"].reshape(-1)[0])) <= 1e-3
+
+
+def test_entity_augmented_models_encode_vs_reference_golden():
+    """AspireNER (entities appended as sentences) and AspireContextNER (entity spans pooled by the span kernel over the
+    same encoder forward) against the unmodified reference's encodings (utils/models.py:211-233, 607-734)."""
+    import json
+    from test_host_api import _ner_model
+    with open(os.path.join(GOLDEN, "ner.json")) as fh:
+        papers = json.load(fh)["papers"]
+    z = np.load(os.path.join(GOLDEN, "ner.npz"))
+    for name, key in (("aspire_context_ner_compsci", "ctx"), ("aspire_ner_compsci", "ner")):
+        m = _ner_model(name)
+        reps = m.encode(papers)
+        assert len(reps) == len(papers)
+        for i, r in enumerate(reps):
+            want = z[f"{key}_{i}"]
+            assert tuple(r.shape) == tuple(want.shape) and not r.is_cuda
+            assert np.abs(r.numpy() - want).max() <= 2e-4, (name, i)
+    # scoring an entity-augmented pair goes through the usual otAspire path
+    s = m.get_similarity(reps[0], reps[1])
+    assert np.isfinite(s) and s < 0

@@ -146,3 +146,36 @@ def test_host_merge_order():
     i = torch.tensor([[10, 7, 4, -1, 5, 6]])
     ms, mi = host_merge(s, i, 3)
     assert mi.tolist() == [[4, 7, 5]] and ms.tolist() == [[3.0, 3.0, 2.0]]
+
+
+def _ner_model(cls_name):
+    """An entity-augmented model with the offline stand-ins (seeded 2-layer BERT, ToyTokenizer)."""
+    import transformers
+    from aspire_b200 import similarity
+    om, ot = transformers.AutoModel.from_pretrained, transformers.AutoTokenizer.from_pretrained
+    transformers.AutoModel.from_pretrained = staticmethod(lambda name, *a, **k: ref_shims.seeded_bert(0, num_hidden_layers=2))
+    transformers.AutoTokenizer.from_pretrained = staticmethod(lambda name, *a, **k: ref_shims.ToyTokenizer())
+    try:
+        return similarity.get_model(cls_name)
+    finally:
+        transformers.AutoModel.from_pretrained, transformers.AutoTokenizer.from_pretrained = om, ot
+
+
+def test_ner_models_host_logic_vs_reference_golden():
+    """Entity token spans, facet filtering and entity appending vs the unmodified reference (oracle/make_golden_ner.py)."""
+    from aspire_b200.similarity import AspireContextNER, AspireNER
+    with open(os.path.join(GOLDEN, "ner.json")) as fh:
+        z = json.load(fh)
+    for sup, sub, want in z["sublist"]:
+        assert AspireContextNER.find_sublist_range(sup, sub) == want
+    assert AspireNER._append_entities(z["papers"]) == z["appended"]
+    m = _ner_model("aspire_context_ner_compsci")
+    assert type(m).__name__ == "AspireContextNER" and m.encoding_type == "sentence-entity"
+    _, abs_lens, _, ner_idxs = m._preprocess_input(z["papers"])
+    assert abs_lens == z["abs_lens"] and ner_idxs == z["ner_token_idxs"]
+    for i, paper in enumerate(z["papers"]):
+        n_rows = abs_lens[i] + sum(1 for x in ner_idxs[i] if x)
+        enc = torch.arange(n_rows, dtype=torch.float32)[:, None].repeat(1, 2)
+        for facet in ("background", "method", "result"):
+            assert m.get_faceted_encoding(enc, facet, paper)[:, 0].tolist() == z["faceted_rows"][f"{i}_{facet}"]
+    assert type(_ner_model("aspire_ner_biomed")).__name__ == "AspireNER"
