@@ -96,6 +96,31 @@ __global__ void __launch_bounds__(256, 1) k_ffma2_3reg(float* out, const float2*
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// legacy tensor path: mma.sync.m16n8k8 tf32 (register operands), 8 independent accumulator tiles per warp
+__global__ void __launch_bounds__(512, 1) k_mma_tf32(float* out, int iters, int warps_active) {
+    if ((int)(threadIdx.x >> 5) >= warps_active) return;
+    float acc[8][4];
+    unsigned a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = 0x3f800000u + threadIdx.x * 8192u * i;
+    b[0] = 0x3f000000u + threadIdx.x * 8192u; b[1] = 0x3e800000u;
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    float s = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += acc[t][0] + acc[t][1] + acc[t][2] + acc[t][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // mode bits: 1 = warps 0-3 run the FMA chain, 2 = warps 4-7 run the ex2 chain; kind 0 = FFMA2, 1 = FFMA, 2 = FFMA2+LOP3
 __global__ void __launch_bounds__(256, 1) k_spec(float* out, int mode, int kind, int it_fma, int it_ex2, float a, float b) {
     const int warp = threadIdx.x >> 5;
@@ -150,6 +175,21 @@ int main() {
             double instr_per_smsp = (double)iters * 40 * (wa / 4);
             printf("FFMA2 3-register-operand form, %d warp(s) per scheduler: %.3f ms -> %.2f clk per FFMA2 per scheduler at %d kHz\n",
                    wa / 4, ms, ms * 1e-3 * khz2 * 1e3 / instr_per_smsp, khz2);
+        }
+    }
+    {
+        int khz3 = 0; cudaDeviceGetAttribute(&khz3, cudaDevAttrClockRate, 0);
+        float* out2; cudaMalloc(&out2, sizeof(float) * sms * 512);
+        const int iters = 1 << 14;
+        for (int wa : {4, 8, 16}) {
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_mma_tf32<<<sms, 512>>>(out2, iters, wa); cudaDeviceSynchronize();
+            cudaEventRecord(e0); k_mma_tf32<<<sms, 512>>>(out2, iters, wa); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double mma_per_smsp = (double)iters * 8 * (wa / 4);
+            double clk = ms * 1e-3 * khz3 * 1e3 / mma_per_smsp;
+            printf("mma.sync m16n8k8 tf32, %d warp(s) per scheduler: %.3f ms -> %.2f clk per MMA per scheduler = %.0f FMA/clk/SM\n",
+                   wa / 4, ms, clk, 4.0 * 1024.0 / clk);
         }
     }
     // clocks per instruction for the single-warp-per-scheduler chains
