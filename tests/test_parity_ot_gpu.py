@@ -291,3 +291,38 @@ def test_fused_kernel_ragged_grouped_vs_warp_kernel_and_oracle(D, Sq, Sc, q_grou
     qsub = q[sub // q_group]
     ref = ar.ot_distance(qsub, ql[sub // q_group].tolist(), c[sub], cl[sub].tolist(), diameter=40.0)
     assert rel_err(res[2]["dual"].cpu().numpy()[sub.numpy()], ref.numpy()).max() <= 1e-4
+
+
+def test_headline_shape_full_size_properties():
+    """BASELINE configs[1] at the bench's size (256 queries x 1k candidates, 10x10 sentences, 768-d) through
+    size-independent properties: (i) a pair's score does not depend on where it sits in the batch -- permuting the
+    candidates inside their pools permutes the scores bit-exactly; (ii) the full-tile fast path and the masked path
+    agree (a pool with one short document flips its tiles to the masked path); (iii) a 1-in-128 subsample agrees with
+    the CPU oracle to 1e-4 relative; (iv) no NaN/Inf anywhere."""
+    from aspire_b200 import ot_scores, epsilon_schedule
+    g = torch.Generator(device="cuda").manual_seed(77)
+    NQ, POOL, S, D = 256, 1000, 10, 768
+    q = 0.3 * torch.randn(NQ, S, D, device="cuda", generator=g)
+    c = 0.3 * torch.randn(NQ * POOL, S, D, device="cuda", generator=g)
+    ql = torch.full((NQ,), S, dtype=torch.int32, device="cuda")
+    cl = torch.full((NQ * POOL,), S, dtype=torch.int32, device="cuda")
+    eps = epsilon_schedule(65.0, 0.05, 0.9)
+    base = ot_scores(q, ql, c, cl, eps, q_group=POOL)["dual"]
+    assert torch.isfinite(base).all() and (base > 0).all()
+    # (i) permutation inside every pool
+    perm = torch.stack([torch.randperm(POOL, device="cuda", generator=g) + i * POOL for i in range(NQ)]).view(-1)
+    permuted = ot_scores(q, ql, c[perm].contiguous(), cl, eps, q_group=POOL)["dual"]
+    assert torch.equal(permuted, base[perm])
+    # (ii) masked path: shorten ONE document per pool (zero its last rows); every other score must not move
+    c2, cl2 = c.clone(), cl.clone()
+    short = torch.arange(NQ, device="cuda") * POOL + 500
+    c2[short, 7:] = 0
+    cl2[short] = 7
+    masked = ot_scores(q, ql, c2, cl2, eps, q_group=POOL)["dual"]
+    keep = torch.ones(NQ * POOL, dtype=torch.bool, device="cuda")
+    keep[short] = False
+    assert (masked[keep] - base[keep]).abs().max().item() <= 1e-6 * base.max().item()
+    # (iii) oracle on a subsample (same explicit diameter)
+    sub = torch.arange(0, NQ * POOL, 128, device="cuda")
+    ref = ar.ot_distance(q[sub // POOL].cpu(), [S] * len(sub), c[sub].cpu(), [S] * len(sub), diameter=65.0)
+    assert rel_err(base[sub].cpu().numpy(), ref.numpy()).max() <= 1e-4
