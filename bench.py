@@ -310,8 +310,13 @@ def main():
     # ---- e2e: host buffers in, host scores out, through the public API ------------------------------
     from aspire_b200.similarity import score_pools_host
     n_host = 1 if NP * BYTES_PER_PAIR > 4e9 else 2
-    host_pools = [pools[k].cpu().pin_memory() for k in range(n_host)]
-    host_q = [queries[k].cpu().pin_memory() for k in range(n_host)]
+
+    def pinned_copy(t):  # device -> pinned host without a pageable intermediate
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+    host_pools = [pinned_copy(pools[k]) for k in range(n_host)]
+    host_q = [pinned_copy(queries[k]) for k in range(n_host)]
     host_lens = torch.full((NP,), SENTS, dtype=torch.int32).pin_memory()
     host_qlens = torch.full((NQ,), SENTS, dtype=torch.int32).pin_memory()
     for i in range(2):
