@@ -25,7 +25,12 @@ namespace asp {
 // Lane l owns rows l, l+32, ... (as i) and columns l, l+32, ... (as j).
 // All logsumexp work is done in base 2:  x2 = log2e * x.
 // ---------------------------------------------------------------------------------------------------
-template <int RPL>  // rows (and columns) per lane: S <= 32*RPL
+// FAST (S <= 32 only): a step first tries the shared-exponential form of the thread solver -- lane i computes
+// E_ij = 2^(u_i + v_j - C_ij t) once per entry, keeps the row sum, parks the row in shared memory, and lane j adds up
+// column j -- half the exponentials and about half the instructions of the two max-stabilised softmins; when a sum
+// leaves the fp32 range the step is redone with the stabilised code below, so results stay defined wherever the
+// reference's are.
+template <int RPL, bool FAST>  // rows (and columns) per lane: S <= 32*RPL
 __global__ void __launch_bounds__(128)
 sinkhorn_warp_kernel(const float* __restrict__ cost, const int32_t* __restrict__ q_lens, int q_group,
                      const int32_t* __restrict__ c_lens, int B, int Sq, int Sc, const EpsSched sched,
@@ -33,9 +38,10 @@ sinkhorn_warp_kernel(const float* __restrict__ cost, const int32_t* __restrict__
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int ldc = Sc | 1;  // odd leading dimension: conflict-free column walks
-    const int per_warp = Sq * ldc + 2 * Sq + 2 * Sc;
+    const int per_warp = (FAST ? 2 : 1) * Sq * ldc + 2 * Sq + 2 * Sc;
     float* Cs = smem + (size_t)warp * per_warp;
-    float* hf = Cs + Sq * ldc;  // log2-domain "h" built from f (indexed by i)
+    float* Es = Cs + (FAST ? Sq * ldc : 0);  // FAST: the step's exponentials E_ij (same layout as Cs)
+    float* hf = Es + Sq * ldc;  // log2-domain "h" built from f (indexed by i)
     float* hg = hf + Sq;        // ... from g (indexed by j)
     float* la = hg + Sc;        // log2(alpha_i)
     float* lb = la + Sq;        // log2(beta_j)
@@ -139,27 +145,51 @@ sinkhorn_warp_kernel(const float* __restrict__ cost, const int32_t* __restrict__
             __syncwarp();
         };
 
-        if (ql > 0 && cl > 0) {
-            float eps = sched.eps[0], t = kLog2e / eps;
-            publish(t, false);
-            softmin_cols(eps, t, gj);
-            softmin_rows(eps, t, fi);
-            for (int k = 0; k < sched.n; ++k) {
-                eps = sched.eps[k];
-                t = kLog2e / eps;
-                publish(t, true);
-                float gt[RPL], ft[RPL];
-                softmin_cols(eps, t, gt);
-                softmin_rows(eps, t, ft);
-#pragma unroll
-                for (int r = 0; r < RPL; ++r) {
-                    gj[r] = 0.5f * (gj[r] + gt[r]);
-                    fi[r] = 0.5f * (fi[r] + ft[r]);
+        // one step in the shared-exponential form (RPL == 1): new un-averaged potentials in ft/gt; false = out of range
+        auto fast_step = [&](float eps, float t, bool with_potentials, float (&ft)[RPL], float (&gt)[RPL]) -> bool {
+            publish(t, with_potentials);
+            float R = 0.f, S = 0.f;
+            if (lane < ql) {
+                const float u = hf[lane];
+                const float* row = Cs + lane * ldc;
+                float* erow = Es + lane * ldc;
+                for (int j = 0; j < cl; ++j) {
+                    const float e = ex2(fmaf(-row[j], t, u + hg[j]));
+                    R += e;
+                    erow[j] = e;
                 }
             }
-            publish(t, true);
-            softmin_cols(eps, t, gj);
-            softmin_rows(eps, t, fi);
+            __syncwarp();
+            if (lane < cl)
+                for (int i = 0; i < ql; ++i) S += Es[i * ldc + lane];
+            const float lr = lg2(R), ls = lg2(S);
+            const bool ok = (lane >= ql || fabsf(lr) < 1e30f) && (lane >= cl || fabsf(ls) < 1e30f);
+            if (!__all_sync(0xffffffffu, ok)) return false;
+            const float scale = eps * kLn2;
+            ft[0] = (lane < ql) ? (with_potentials ? fi[0] : 0.f) - scale * (lr - la[lane]) : 0.f;
+            gt[0] = (lane < cl) ? (with_potentials ? gj[0] : 0.f) - scale * (ls - lb[lane]) : 0.f;
+            return true;
+        };
+
+        if (ql > 0 && cl > 0) {
+            // k = -1: initialisation from f = g = 0 at eps[0]; k = 0..n-1: averaged steps; k = n: final un-averaged step
+            for (int k = -1; k <= sched.n; ++k) {
+                const float eps = sched.eps[min(max(k, 0), sched.n - 1)], t = kLog2e / eps;
+                float gt[RPL], ft[RPL];
+                bool done = false;
+                if (FAST && RPL == 1) done = fast_step(eps, t, k >= 0, ft, gt);
+                if (!done) {
+                    publish(t, k >= 0);
+                    softmin_cols(eps, t, gt);
+                    softmin_rows(eps, t, ft);
+                }
+                const bool plain = (k < 0) || (k == sched.n);
+#pragma unroll
+                for (int r = 0; r < RPL; ++r) {
+                    gj[r] = plain ? gt[r] : 0.5f * (gj[r] + gt[r]);
+                    fi[r] = plain ? ft[r] : 0.5f * (fi[r] + ft[r]);
+                }
+            }
         } else {
 #pragma unroll
             for (int r = 0; r < RPL; ++r) fi[r] = gj[r] = 0.f;
@@ -249,23 +279,26 @@ int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_group, const
         ASP_LAUNCH_CHECK("sinkhorn_thread_kernel");
         return ASP_OK;
     }
-    const int per_warp = (Sq * (Sc | 1) + 2 * Sq + 2 * Sc) * (int)sizeof(float);
+    // the forced warp kernel (ot_kernel = 1) stays purely max-stabilised: it is the tests' independent cross-check
+    const bool fast = (g_ot_kernel != 1) && smax <= 32;
+    const int per_warp = ((fast ? 2 : 1) * Sq * (Sc | 1) + 2 * Sq + 2 * Sc) * (int)sizeof(float);
     int warps = 4;
     while (warps > 1 && warps * per_warp > 96 * 1024) warps >>= 1;
     const int smem = warps * per_warp;
     const int blocks = (B + warps - 1) / warps;
     const float inv_temp = 1.0f / temp;
-#define ASP_LAUNCH_WARP(RPL)                                                                                     \
-    do {                                                                                                         \
-        if (smem > 48 * 1024)                                                                                    \
-            ASP_CUDA(cudaFuncSetAttribute(sinkhorn_warp_kernel<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          smem));                                                                \
-        sinkhorn_warp_kernel<RPL><<<blocks, warps * 32, smem, stream>>>(cost, q_lens, q_group, c_lens, B, Sq,   \
-                                                                        Sc, sched, inv_temp, out);               \
+#define ASP_LAUNCH_WARP(RPL, FAST)                                                                                      \
+    do {                                                                                                                \
+        if (smem > 48 * 1024)                                                                                           \
+            ASP_CUDA(cudaFuncSetAttribute(sinkhorn_warp_kernel<RPL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          smem));                                                                       \
+        sinkhorn_warp_kernel<RPL, FAST><<<blocks, warps * 32, smem, stream>>>(cost, q_lens, q_group, c_lens, B, Sq,    \
+                                                                              Sc, sched, inv_temp, out);                \
     } while (0)
-    if (smax <= 32) ASP_LAUNCH_WARP(1);
-    else if (smax <= 64) ASP_LAUNCH_WARP(2);
-    else ASP_LAUNCH_WARP(4);
+    if (fast) ASP_LAUNCH_WARP(1, true);
+    else if (smax <= 32) ASP_LAUNCH_WARP(1, false);
+    else if (smax <= 64) ASP_LAUNCH_WARP(2, false);
+    else ASP_LAUNCH_WARP(4, false);
 #undef ASP_LAUNCH_WARP
     ASP_LAUNCH_CHECK("sinkhorn_warp_kernel");
     return ASP_OK;

@@ -50,7 +50,7 @@ def fp64_reference(q, ql, c, cl, alpha, beta, eps, blur):
     return dual, primal, f, g, plans
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["warp", "thread"])
+@pytest.mark.parametrize("kernel", [1, 2, 0], ids=["warp", "thread", "auto"])
 @pytest.mark.parametrize("fn", OT_FILES, ids=[os.path.basename(f) for f in OT_FILES])
 def test_compute_distance_vs_golden(fn, kernel):
     from aspire_b200 import AllPairMaskedWasserstein, rep_len_tup, _abi
