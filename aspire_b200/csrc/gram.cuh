@@ -22,7 +22,9 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 }
 
 // Accumulate this lane's share (k = 4*lane + 128*m) of a TI x TJ tile.
-template <int TI, int TJ>
+// STREAM_C: the candidate rows are read exactly once by this kernel (single-tile pairs) -> do not allocate them in L1;
+// false when several tiles / warps re-read the same rows (long documents) and the caches should keep them.
+template <int TI, int TJ, bool STREAM_C = true>
 __device__ __forceinline__ void gram_accumulate(const float* __restrict__ q, int nq, const float* __restrict__ c,
                                                 int nc, int D, int lane, float (&v)[GramTile<TI, TJ>::NV]) {
     using T = GramTile<TI, TJ>;
@@ -32,7 +34,9 @@ __device__ __forceinline__ void gram_accumulate(const float* __restrict__ q, int
         float4 cv[TJ];
 #pragma unroll
         for (int j = 0; j < TJ; ++j)
-            cv[j] = (j < nc) ? ldg_stream(reinterpret_cast<const float4*>(c + (size_t)j * D) + k4) : zero4;
+            cv[j] = (j < nc) ? (STREAM_C ? ldg_stream(reinterpret_cast<const float4*>(c + (size_t)j * D) + k4)
+                                         : __ldg(reinterpret_cast<const float4*>(c + (size_t)j * D) + k4))
+                             : zero4;
 #pragma unroll
         for (int i = 0; i < TI; ++i) {
             const float4 qv = (i < nq) ? __ldg(reinterpret_cast<const float4*>(q + (size_t)i * D) + k4) : zero4;

@@ -14,14 +14,14 @@ namespace asp {
 enum { MODE_COST = 0, MODE_L2MAX = 1 };
 
 // red: per-warp shared scratch of NV floats.  Leaves dots / norms of the tile in red[].
-template <int TI, int TJ>
+template <int TI, int TJ, bool STREAM_C = true>
 __device__ __forceinline__ void gram_tile_to_smem(const float* q, int nq, const float* c, int nc, int D, int lane,
                                                   float* red) {
     using T = GramTile<TI, TJ>;
     float v[T::NV];
 #pragma unroll
     for (int e = 0; e < T::NV; ++e) v[e] = 0.f;
-    gram_accumulate<TI, TJ>(q, nq, c, nc, D, lane, v);
+    gram_accumulate<TI, TJ, STREAM_C>(q, nq, c, nc, D, lane, v);
     transpose_reduce<T::NV>(v, lane);
     const int rev = __brev((unsigned)lane) >> 27;
     __syncwarp();
@@ -127,7 +127,7 @@ pair_cost_cta_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_
         for (int t = warp; t < nti * ntj; t += WARPS) {
             const int ti = (t / ntj) * TI, tj = (t % ntj) * TJ;
             const int nq = min(TI, ql - ti), nc = min(TJ, cl - tj);
-            gram_tile_to_smem<TI, TJ>(qbase + (size_t)ti * D, nq, cbase + (size_t)tj * D, nc, D, lane, red);
+            gram_tile_to_smem<TI, TJ, false>(qbase + (size_t)ti * D, nq, cbase + (size_t)tj * D, nc, D, lane, red);
             for (int e = lane; e < T::kEntries; e += 32) {
                 const int i = e / TJ, j = e - i * TJ;
                 if (i < nq && j < nc) {
