@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from .consent import prepare_abstracts
-from .similarity import SimilarityModel, caching_score
+from .similarity import SimilarityModel, caching_score, pack_pool
 
 
 class EvalDataset:
@@ -210,3 +210,53 @@ def evaluate(results, dataset, facet=None, results_dir=None, pr_atks=(5, 10, 20)
         pd.DataFrame(per_query).to_csv(os.path.join(results_dir, f'query-evaluations{suffix}.csv'), index=False)
         pd.DataFrame(aggregated).to_csv(os.path.join(results_dir, f'aggregated-evaluations{suffix}.csv'), index=False)
     return per_query, aggregated
+
+
+def rank_pool_sent(root_path, reps_path, dataset, data_to_read='sent', score_type='l2max', split='', rep_type=None,
+                   write=True):
+    """tsAspire / l2top2 re-ranking of every test pool from pre-built sentence vectors on disk -- the numpy path
+    ``rank_pool_sent`` of src/pre_process/pp_gen_nearest.py:863-985, with the ``-cdist`` + per-candidate ``max`` of
+    :942-961 done by one kernel launch per query pool (``asp_l2max`` / ``asp_pair_cost`` + ``asp_pair_heads``).
+
+    Files: ``{reps_path}/pid2idx-{dataset}-sent.json`` ({'pid-i': row}), ``{reps_path}/
+    {dataset}-{data_to_read}.npy`` ([rows, D]; NaNs read as 0, :905), ``{root_path}/test-pid2anns-{dataset}{split}.json``,
+    ``{root_path}/abstracts-{dataset}.jsonl``.  Returns {qpid: [(cpid, -similarity), ...]} best first (ties keep pool
+    order, :962) and writes it to ``{reps_path}/test-pid2pool-{dataset}{split}-{rep_type}-ranked.json`` (:981-984).
+    """
+    from .distances import l2max_scores, pair_heads
+    if score_type not in {'l2max', 'l2top2'}:
+        raise ValueError(f'Unknown score type: {score_type}')  # cosine / dot variants are not on this path
+    with codecs.open(os.path.join(root_path, f'test-pid2anns-{dataset}{split}.json'), 'r', 'utf-8') as fp:
+        qpid2pool = json.load(fp)
+    with codecs.open(os.path.join(reps_path, f'pid2idx-{dataset}-sent.json'), 'r', 'utf-8') as fp:
+        docsent2idx = json.load(fp)
+    all_reps = np.nan_to_num(np.load(os.path.join(reps_path, f'{dataset}-{data_to_read}.npy')).astype(np.float32))
+    n_sents = {}
+    with codecs.open(os.path.join(root_path, f'abstracts-{dataset}.jsonl'), 'r', 'utf-8') as fh:
+        for line in fh:
+            if line.strip():
+                rec = json.loads(line)
+                n_sents[rec['paper_id']] = len(rec['abstract'])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ranked = collections.OrderedDict()
+    for qpid, pool in qpid2pool.items():
+        cand_pids = pool['cands']
+        q_rows = [docsent2idx[f'{qpid}-{i}'] for i in range(n_sents[qpid])]
+        q = torch.from_numpy(all_reps[q_rows])[None].to(dev).contiguous()
+        q_lens = torch.tensor([len(q_rows)], dtype=torch.int32, device=dev)
+        c, c_lens = pack_pool([all_reps[[docsent2idx[f'{c_}-{i}'] for i in range(n_sents[c_])]] for c_ in cand_pids], dev)
+        best, _idx, _ = l2max_scores(q, q_lens, c, c_lens, broadcast_query=True)
+        sims = best
+        if score_type == 'l2top2':
+            qrep = q.expand(c.shape[0], -1, -1).contiguous()
+            top2 = pair_heads(qrep, q_lens.expand(c.shape[0]).contiguous(), c, c_lens, want=("top2",))["top2"]
+            # a single sentence pair: the numpy path sums what there is (:955-957), i.e. the one similarity
+            sims = torch.where((q_lens[0] * c_lens) < 2, best, top2)
+        ranked[qpid] = [(cpid, -1 * s) for cpid, s in rank_candidates(cand_pids, sims.cpu().numpy())]
+    if write:
+        name = rep_type or os.path.basename(os.path.normpath(reps_path))
+        out_fname = os.path.join(reps_path, f'test-pid2pool-{dataset}{split}-{name}-ranked.json')
+        with codecs.open(out_fname, 'w', 'utf-8') as fp:
+            json.dump(ranked, fp)
+        logging.info(f'Wrote: {out_fname}')
+    return ranked

@@ -77,3 +77,57 @@ def test_caching_scoring_model_predict_and_rank(tmp_path, patched_hf):
         ranked = scorer.rank_pool("0", cands, pid2abstract)
         assert [s for _, s in ranked] == sorted(out["cand_scores"], reverse=True)
         assert q["sent_reps"].shape == (len(pid2abstract["0"]["abstract"]), 768) and q["doc_cls_reps"].shape == (768,)
+
+
+def test_rank_pool_sent_from_npy_reps_vs_float64_numpy_path(tmp_path):
+    """pp_gen_nearest.rank_pool_sent (:863-985): sentence vectors in ``{ds}-sent.npy`` + ``pid2idx-{ds}-sent.json``;
+    scores against the float64 ``-cdist`` + per-candidate max / top-2 restatement, ranking order and output file."""
+    import json
+    from aspire_b200.evaluation import rank_pool_sent
+    rng = np.random.RandomState(5)
+    ds, n_docs, D = "toyds", 40, 768
+    root, reps = str(tmp_path), str(tmp_path / "myreps")
+    os.makedirs(reps)
+    lens = rng.randint(1, 9, n_docs)
+    lens[1] = 1
+    pid2idx, rows = {}, []
+    with open(os.path.join(root, f"abstracts-{ds}.jsonl"), "w") as fh:
+        for d in range(n_docs):
+            pid = str(500 + d)
+            fh.write(json.dumps({"paper_id": pid, "title": f"t{d}", "abstract": [f"s{j}" for j in range(lens[d])]}) + "\n")
+            for j in range(lens[d]):
+                pid2idx[f"{pid}-{j}"] = len(rows)
+                rows.append(0.3 * rng.randn(D))
+    allreps = np.asarray(rows, dtype=np.float32)
+    allreps[3, 5] = np.nan  # read as 0 (pp_gen_nearest.py:905)
+    np.save(os.path.join(reps, f"{ds}-sent.npy"), allreps)
+    with open(os.path.join(reps, f"pid2idx-{ds}-sent.json"), "w") as fh:
+        json.dump(pid2idx, fh)
+    pool = {"500": {"cands": [str(500 + d) for d in range(1, n_docs)], "relevance_adju": [0] * (n_docs - 1)},
+            "501": {"cands": [str(500 + d) for d in range(2, n_docs)], "relevance_adju": [0] * (n_docs - 2)}}
+    with open(os.path.join(root, f"test-pid2anns-{ds}.json"), "w") as fh:
+        json.dump(pool, fh)
+    clean = np.nan_to_num(allreps).astype(np.float64)
+
+    def doc(pid):
+        return clean[[pid2idx[f"{pid}-{j}"] for j in range(lens[int(pid) - 500])]]
+    from scipy.spatial.distance import cdist
+    for score_type in ("l2max", "l2top2"):
+        got = rank_pool_sent(root, reps, ds, score_type=score_type)
+        with open(os.path.join(reps, f"test-pid2pool-{ds}-myreps-ranked.json")) as fh:
+            on_disk = json.load(fh)
+        for qpid, p in pool.items():
+            want = {}
+            for cpid in p["cands"]:
+                sims = -cdist(doc(qpid), doc(cpid)).flatten()
+                if score_type == "l2max":
+                    want[cpid] = sims.max()
+                else:  # np.partition(kth=2) needs three entries; fewer are summed as they are (:949-957)
+                    want[cpid] = np.sort(sims)[::-1][:2].sum() if sims.size >= 3 else sims.sum()
+            ranked = got[qpid]
+            assert [c for c, _ in ranked] == [c for c, _ in on_disk[qpid]]
+            assert sorted(c for c, _ in ranked) == sorted(p["cands"])
+            for cpid, neg_sim in ranked:
+                assert abs(-neg_sim - want[cpid]) <= 3e-5 * max(1.0, abs(want[cpid])), (score_type, qpid, cpid)
+            vals = [v for _, v in ranked]
+            assert vals == sorted(vals)
