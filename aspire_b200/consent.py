@@ -19,6 +19,15 @@ from . import _abi
 MAX_WORDPIECES = 500  # examples/ex_aspire_consent.py:120
 
 
+def _with_special_tokens(tokenizer, ids):
+    """``[CLS] ids [SEP]`` -- ``tokenizer.build_inputs_with_special_tokens(token_ids_0=ids)`` as the reference calls it
+    (:161); transformers >= 5 dropped that method from its tokenizers, so fall back to the two ids it would have used."""
+    build = getattr(tokenizer, "build_inputs_with_special_tokens", None)
+    if build is not None:
+        return build(token_ids_0=ids)
+    return [tokenizer.cls_token_id] + list(ids) + [tokenizer.sep_token_id]
+
+
 def prepare_bert_sentences(batch_doc_sents, tokenizer):
     """Tokenise documents given as lists of "sentences" (element 0 is the title + ' [SEP] ').
 
@@ -49,7 +58,7 @@ def prepare_bert_sentences(batch_doc_sents, tokenizer):
             used += take
         docs_text.append(text)
         docs_spans.append(spans[1:])  # the title is encoded but never pooled
-        docs_ids.append(tokenizer.build_inputs_with_special_tokens(token_ids_0=ids))
+        docs_ids.append(_with_special_tokens(tokenizer, ids))
     seq_lens = [len(x) for x in docs_ids]
     width = max(seq_lens) if seq_lens else 0
     pad = tokenizer.pad_token_id
@@ -77,6 +86,61 @@ def prepare_abstracts(batch_abs, pt_lm_tokenizer):
     for n in abs_lens:
         assert (n > 0)  # an abstract whose title alone fills the budget (reference :210)
     return bert_batch, abs_lens, sent_token_idxs
+
+
+def prepare_abstracts_fast(batch_abs, pt_lm_tokenizer):
+    """Batch-first variant of ``prepare_abstracts`` for the encoder kernels ("next" row 3 of SURVEY 8f).
+
+    Same sequence layout, truncation rule and outputs as ``prepare_abstracts`` (examples/ex_aspire_consent.py:107-212),
+    but (i) every sentence of the batch is word-pieced in ONE tokenizer call when the tokenizer is a fast (Rust-backed)
+    one -- the reference calls ``tokenize`` + ``convert_tokens_to_ids`` once per sentence -- and (ii) the sentence
+    spans come back as the int32 ``[B, Smax, 2]`` half-open ``(start, end)`` table that ``asp_span_mean_pool`` consumes,
+    instead of per-token index lists.  Tokenizers without batch encoding fall back to the per-sentence protocol.
+
+    :return: (bert_batch, abs_lens: list(int), spans: int32 tensor [B, max(abs_lens), 2], (-1, -1) = no sentence)
+    """
+    docs = [[ex['TITLE'] + ' [SEP] '] + list(ex['ABSTRACT']) for ex in batch_abs]
+    flat = [s for d in docs for s in d]
+    if getattr(pt_lm_tokenizer, "is_fast", False) and flat:
+        piece_ids = pt_lm_tokenizer(flat, add_special_tokens=False, return_attention_mask=False,
+                                    return_token_type_ids=False)["input_ids"]
+    else:
+        piece_ids = [pt_lm_tokenizer.convert_tokens_to_ids(pt_lm_tokenizer.tokenize(s)) for s in flat]
+    docs_ids, docs_spans, cursor = [], [], 0
+    for d in docs:
+        ids, spans, used = [], [], 0
+        for k in range(len(d)):
+            p = piece_ids[cursor + k]
+            room = MAX_WORDPIECES - used
+            take = min(len(p), room)
+            if take > 0 or len(p) == 0:
+                spans.append((used + 1, used + 1 + take))  # +1: the [CLS] prepended below
+                ids.extend(p[:take])
+            if len(p) > room:
+                break
+            used += take
+        cursor += len(d)
+        docs_spans.append(spans[1:])  # the title is encoded but never pooled
+        docs_ids.append(_with_special_tokens(pt_lm_tokenizer, ids))
+    abs_lens = [len(s) for s in docs_spans]
+    for n in abs_lens:
+        assert (n > 0)
+    seq_lens = [len(x) for x in docs_ids]
+    width, pad = max(seq_lens), pt_lm_tokenizer.pad_token_id
+    tok = np.full((len(docs), width), pad, dtype=np.int64)
+    seg = np.full((len(docs), width), pad, dtype=np.int64)
+    att = np.full((len(docs), width), pad, dtype=np.int64)
+    span_arr = -np.ones((len(docs), max(abs_lens), 2), dtype=np.int32)
+    for b, (ids, spans) in enumerate(zip(docs_ids, docs_spans)):
+        tok[b, :len(ids)] = ids
+        seg[b, :len(ids)] = 0
+        att[b, :len(ids)] = 1
+        for s_, (st, en) in enumerate(spans):
+            if en > st:
+                span_arr[b, s_] = (st, en)
+    bert_batch = {'tokid_tt': torch.from_numpy(tok), 'seg_tt': torch.from_numpy(seg),
+                  'attnmask_tt': torch.from_numpy(att), 'seq_lens': seq_lens}
+    return bert_batch, abs_lens, torch.from_numpy(span_arr)
 
 
 def spans_from_token_idxs(sent_tok_idxs, max_sents):
@@ -182,7 +246,10 @@ class AspireConSent(nn.Module):
         max_sents = max(num_sents)
         tokid_tt, seg_tt, attnmask_tt = (bert_batch[k].to(dev, non_blocking=True)
                                          for k in ('tokid_tt', 'seg_tt', 'attnmask_tt'))
-        spans = spans_from_token_idxs(batch_senttok_idxs, max_sents).to(dev, non_blocking=True)
+        if isinstance(batch_senttok_idxs, torch.Tensor):  # a ready (start, end) table from prepare_abstracts_fast
+            spans = batch_senttok_idxs[:, :max_sents].to(device=dev, dtype=torch.int32, non_blocking=True)
+        else:
+            spans = spans_from_token_idxs(batch_senttok_idxs, max_sents).to(dev, non_blocking=True)
         hidden = self.encode_hidden(tokid_tt, seg_tt, attnmask_tt, seq_lens=bert_batch.get('seq_lens'))
         doc_cls_reps, sent_reps = span_mean_pool(hidden, spans)
         doc_cls_reps = doc_cls_reps.squeeze()  # reference :76 ([768] when B == 1; forward() re-expands)

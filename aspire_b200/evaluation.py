@@ -260,3 +260,27 @@ def rank_pool_sent(root_path, reps_path, dataset, data_to_read='sent', score_typ
             json.dump(ranked, fp)
         logging.info(f'Wrote: {out_fname}')
     return ranked
+
+
+def encode_stream(model, tokenizer, papers, batch_size=32, workers=2):
+    """Encode a list of {'TITLE', 'ABSTRACT'} papers with the host preparation of batch n+1 (tokenisation, span table:
+    ``prepare_abstracts_fast``) running on worker threads while the GPU encodes batch n -- the Rust tokenizers release
+    the GIL, and at 5-10 k documents/s on the device the tokeniser is otherwise the bottleneck of
+    ``AspireModel.encode`` / ``caching_encode`` (utils/models.py:199-209, disent_models.py:344-371).
+
+    ``model``: an AspireConSent.  Yields one fp32 CPU tensor [num_sents, 768] per paper, in input order.
+    """
+    from concurrent.futures import ThreadPoolExecutor
+    from .consent import prepare_abstracts_fast
+    chunks = [papers[s:s + batch_size] for s in range(0, len(papers), batch_size)]
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+        pending = [pool.submit(prepare_abstracts_fast, c, tokenizer) for c in chunks[:workers + 1]]
+        for k in range(len(chunks)):
+            bert_batch, abs_lens, spans = pending.pop(0).result()
+            nxt = k + workers + 1
+            if nxt < len(chunks):
+                pending.append(pool.submit(prepare_abstracts_fast, chunks[nxt], tokenizer))
+            with torch.no_grad():
+                _, reps = model.forward(bert_batch=bert_batch, abs_lens=abs_lens, sent_tok_idxs=spans)
+            for i, n in enumerate(abs_lens):
+                yield reps[i, :n]

@@ -101,3 +101,28 @@ def test_entity_augmented_models_encode_vs_reference_golden():
     # scoring an entity-augmented pair goes through the usual otAspire path
     s = m.get_similarity(reps[0], reps[1])
     assert np.isfinite(s) and s < 0
+
+
+def test_encode_stream_matches_batchwise_encode():
+    """Overlapped host preparation (span-table front end on worker threads) gives the same encodings as the
+    reference-shaped prepare_abstracts -> forward path, in input order."""
+    import transformers
+    from oracle.make_golden import README_ABSTRACTS
+    from aspire_b200.consent import AspireConSent, prepare_abstracts
+    from aspire_b200.evaluation import encode_stream
+    orig = transformers.AutoModel.from_pretrained
+    transformers.AutoModel.from_pretrained = staticmethod(lambda name, *a, **k: ref_shims.seeded_bert(0, num_hidden_layers=2))
+    try:
+        model = AspireConSent("allenai/aspire-contextualsentence-singlem-compsci")
+    finally:
+        transformers.AutoModel.from_pretrained = orig
+    tok = ref_shims.ToyTokenizer()
+    papers = [README_ABSTRACTS[i % 2] for i in range(7)]
+    got = list(encode_stream(model, tok, papers, batch_size=3, workers=2))
+    assert len(got) == 7
+    for s in range(0, 7, 3):
+        bb, al, sti = prepare_abstracts(batch_abs=papers[s:s + 3], pt_lm_tokenizer=tok)
+        with torch.no_grad():
+            _, reps = model.forward(bert_batch=bb, abs_lens=al, sent_tok_idxs=sti)
+        for i, n in enumerate(al):
+            assert torch.equal(got[s + i], reps[i, :n])

@@ -179,3 +179,64 @@ def test_ner_models_host_logic_vs_reference_golden():
         for facet in ("background", "method", "result"):
             assert m.get_faceted_encoding(enc, facet, paper)[:, 0].tolist() == z["faceted_rows"][f"{i}_{facet}"]
     assert type(_ner_model("aspire_ner_biomed")).__name__ == "AspireNER"
+
+
+@pytest.mark.needs_reference
+def test_prepare_abstracts_fuzz_vs_live_reference():
+    """Seeded random abstracts (1-40 sentences, 1-80 words, some far past the 500-piece budget) through the UNMODIFIED
+    reference's prepare_abstracts (examples/ex_aspire_consent.py:185-212) and through ours: every output identical."""
+    import random
+    ref_shims.install(bert_seed=0, bert_layers=2)
+    import ex_aspire_consent as ex_ref
+    from aspire_b200.consent import prepare_abstracts
+    rnd = random.Random(1234)
+    vocab = ["alpha", "beta", "gamma", "transformer", "optimal", "transport", "sentence", "x", "biomedical",
+             "representation", "learning", "a", "of", "the", "sinkhorn"]
+    tok = ref_shims.ToyTokenizer()
+    for trial in range(25):
+        batch = []
+        for _ in range(rnd.randint(1, 6)):
+            n_sents = rnd.randint(1, 40)
+            batch.append({"TITLE": " ".join(rnd.choice(vocab) for _ in range(rnd.randint(1, 30))),
+                          "ABSTRACT": [" ".join(rnd.choice(vocab) for _ in range(rnd.randint(1, 80))) for _ in range(n_sents)]})
+        try:
+            want = ex_ref.prepare_abstracts(batch_abs=batch, pt_lm_tokenizer=tok)
+        except AssertionError:
+            with pytest.raises(AssertionError):
+                prepare_abstracts(batch_abs=batch, pt_lm_tokenizer=tok)
+            continue
+        got = prepare_abstracts(batch_abs=batch, pt_lm_tokenizer=tok)
+        assert got[1] == want[1] and got[2] == want[2]
+        assert got[0]["seq_lens"] == want[0]["seq_lens"]
+        for k in ("tokid_tt", "seg_tt", "attnmask_tt"):
+            assert torch.equal(got[0][k], want[0][k]) and got[0][k].dtype == want[0][k].dtype
+
+
+def test_prepare_abstracts_fast_equals_per_sentence_protocol(tmp_path):
+    """The batch-tokenising front end (one Rust tokenizer call per batch, spans as an int32 table) against the
+    reference-shaped prepare_abstracts on the SAME BertTokenizerFast (built offline from a small word-piece vocab),
+    and against the ToyTokenizer fallback path."""
+    import random
+    from transformers import BertTokenizerFast
+    from aspire_b200.consent import prepare_abstracts, prepare_abstracts_fast, spans_from_token_idxs
+    words = ["optimal", "transport", "sentence", "paper", "graph", "neural", "network", "the", "of", "a", "we", "study",
+             "align", "##ment", "##s", "##ing", "bio", "##medical", "retrieval", ".", ","]
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(vocab) + "\n")
+    fast_tok = BertTokenizerFast(vocab_file=str(vf), do_lower_case=True)
+    assert fast_tok.is_fast
+    rnd = random.Random(7)
+    plain = ["optimal", "transport", "alignments", "aligning", "biomedical", "papers", "graphs", "the", "of", "we",
+             "study", "retrieval", "unknownword", ".", ","]
+    for tok in (fast_tok, ref_shims.ToyTokenizer()):
+        for _ in range(10):
+            batch = [{"TITLE": " ".join(rnd.choice(plain) for _ in range(rnd.randint(1, 12))),
+                      "ABSTRACT": [" ".join(rnd.choice(plain) for _ in range(rnd.randint(1, 120)))
+                                   for _ in range(rnd.randint(1, 25))]} for _ in range(rnd.randint(1, 5))]
+            bb, al, idxs = prepare_abstracts(batch_abs=batch, pt_lm_tokenizer=tok)
+            fb, fal, spans = prepare_abstracts_fast(batch_abs=batch, pt_lm_tokenizer=tok)
+            assert fal == al and fb["seq_lens"] == bb["seq_lens"]
+            for k in ("tokid_tt", "seg_tt", "attnmask_tt"):
+                assert torch.equal(fb[k], bb[k])
+            assert torch.equal(spans, spans_from_token_idxs(idxs, max(al)))
