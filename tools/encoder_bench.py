@@ -5,8 +5,16 @@ import time
 import numpy as np
 import torch
 sys.path.insert(0, ".")
-from oracle import ref_shims
 from aspire_b200.encoder import B200BertEncoder
+
+
+def seeded_bert(seed=0, vocab_size=31116, num_hidden_layers=12):
+    """Random-init BERT-base in eval mode (no HF weights offline)."""
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(seed)
+    model = BertModel(BertConfig(vocab_size=vocab_size, num_hidden_layers=num_hidden_layers))
+    model.eval()
+    return model
 
 
 def timeit(fn, iters=5, warm=2):
@@ -23,7 +31,7 @@ def timeit(fn, iters=5, warm=2):
 
 def main():
     quick = "--quick" in sys.argv
-    model = ref_shims.seeded_bert(seed=0, num_hidden_layers=12)
+    model = seeded_bert(seed=0, num_hidden_layers=12)
     enc = B200BertEncoder(model)
     hf32 = model.cuda().float()
     for B, L in ([(32, 256)] if quick else [(8, 256), (32, 256), (32, 512), (128, 256)]):
