@@ -7,23 +7,25 @@
 //   plan + primal value          pair_distances.py:76-85
 // for documents of at most kFT sentences (the reference's abstracts: 10-sentence synthetic config, CSFCube ~7).
 //
-// Work decomposition (every candidate row is read from HBM exactly once, 30 KB per pair, and only 4-8 bytes per pair
-// are written; the query never comes from memory in the inner loop at all):
-//   * ONE persistent CTA of 8 independent warps per SM; a warp takes tiles of <= 32 pairs from a global atomic
-//     counter (tile size chosen by the launcher so that the batch fills whole waves of warps);
-//   * phase 1 (streaming, FMA pipe): for each pair of its tile the two HALF-WARPS take 5 query rows each and their 16
-//     lanes split the embedding dimension.  Candidate rows are staged by cp.async through a per-warp shared-memory
-//     ring (4 slices = 10 KB in flight per warp, 80 KB per SM; the stream runs across pair boundaries) and read back
-//     with one 128-bit LDS per row.  The QUERY rows live in TENSOR MEMORY: each lane parks its 240 floats of the
-//     current query in its own TMEM lane once per (warp, query) with tcgen05.st and pulls one 20-float slice per step
-//     back with tcgen05.ld, one slice ahead -- no L1/L2 traffic and no LSU instruction for the query (the first
-//     version re-read it through L1 at a 5 % hit rate; that single stall was 22 % of the kernel).  The 5x10 Gram tile
-//     + squared norms accumulate in packed fp32 (FFMA2), are transpose-reduced over the 16 lanes and leave
-//     sqrt(max(|q|^2+|c|^2-2q.c, 1e-8)) in a shared cost tile [32][101] (odd stride: conflict-free in phase 2);
-//   * phase 2 (math, MUFU pipe): each THREAD solves one pair entirely in registers (ot_pair.cuh): one ex2 per (i,j)
-//     and step, no shuffles, no shared memory in the loop; full 10x10 tiles run a mask-free specialisation;
-//   * phase stagger: warps w and w+4 share a scheduler; w+4 starts after w's first phase 1, so that one of them is on
-//     the FMA pipe while the other is on the MUFU pipe instead of both queueing for the same one.
+// Every candidate row is read from HBM exactly once (30 KB per pair), only 4-8 bytes per pair are written, and the
+// query never comes from memory in the inner loop.  Two kernels share the phase-1 code below:
+//
+//   ot_fused_v7_kernel (default) -- 12 warps per SM, specialised by pipe and sized with setmaxnreg:
+//     * 8 Gram warps (two per scheduler, 200 registers), phase 1 on the FMA pipe: half-tiles of <= 16 pairs from a
+//       global atomic counter; per pair the two HALF-WARPS take 5 query rows each and their 16 lanes split the
+//       embedding dimension.  Candidate rows are staged by cp.async through a per-warp shared-memory ring (4 slices =
+//       10 KB in flight per warp, 80 KB per SM; the stream runs across pair boundaries) and read back with one
+//       128-bit LDS per row.  The QUERY rows live in TENSOR MEMORY: each lane parks its 240 floats of the current
+//       query in its own TMEM lane once per (warp, query) with tcgen05.st and pulls one 20-float slice per step back
+//       with tcgen05.ld, one slice ahead.  The 5x10 Gram tile + squared norms accumulate in packed fp32 (FFMA2), are
+//       transpose-reduced over the 16 lanes and leave sqrt(max(|q|^2+|c|^2-2q.c, 1e-8)) in a shared half-tile.
+//     * 4 Sinkhorn warps (one per scheduler, 104 registers), phase 2 on the MUFU pipe: one pair per THREAD, the cost
+//       tile streamed from shared memory every step (ot_pair.cuh: solve_pair_thread_stream), one ex2 per (i,j) and
+//       step; full 10x10 tiles run a mask-free specialisation.
+//     * hand-over: per scheduler a ring of four half-tiles, ticketed slots, full/empty mbarriers, parked waits.
+//   ot_fused_kernel (asp_set_option("ot_fused_mode", 0)) -- the previous design: 8 warps per SM, every warp runs
+//     phase 1 on a 32-pair tile and then phase 2 with the cost tile in registers (solve_pair_thread); warps w and w+4
+//     share a scheduler and are phase-staggered so that one is on the FMA pipe while the other is on the MUFU pipe.
 #include <algorithm>
 #include "bert/tc05.cuh"
 #include "gram.cuh"
