@@ -93,6 +93,10 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const float* gmem_
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const float* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
+// 16-byte cp.async that reads `bytes` (0 or 16) from global memory and zero-fills the rest of the destination
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const float* gmem_src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -188,10 +192,14 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
                     for (int m = 0; m < kHR; ++m) cp_async16(sdst + m * 512, gsrc + (size_t)(2 * m) * D);
                 }
             } else {
+                // ragged tile: rows the document does not have are ZERO-FILLED in the ring (src-size 0: nothing is read),
+                // so the consumer below runs the same unpredicated instruction stream as for full tiles
                 const int ncp = __shfl_sync(0xffffffffu, my_cl, ip);
 #pragma unroll
-                for (int m = 0; m < kHR; ++m)
-                    if (h + 2 * m < ncp) cp_async16(sdst + m * 512, gsrc + (size_t)(2 * m) * D);
+                for (int m = 0; m < kHR; ++m) {
+                    const bool ok = h + 2 * m < ncp;
+                    cp_async16_zfill(sdst + m * 512, gsrc + (ok ? (size_t)(2 * m) * D : (size_t)0), ok ? 16 : 0);
+                }
             }
             gsrc += 64;
             if (++iit == nit) {
@@ -222,8 +230,8 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
         float4 cv[kFT];
 #pragma unroll
         for (int j = 0; j < kHR; ++j) {
-            cv[j] = (FULL || kHR * h + j < nc_cur) ? cptr[rotA + j * 16] : zero4;
-            cv[kHR + j] = (FULL || kHR * (1 - h) + j < nc_cur) ? cptr[rotB + j * 16] : zero4;
+            cv[j] = cptr[rotA + j * 16];
+            cv[kHR + j] = cptr[rotB + j * 16];
         }
         cptr += kSliceFloats / 4;
         if (++cslot == kRing) {
