@@ -705,3 +705,21 @@ extern "C" int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, 
     if (rc) return rc;
     return asp::launch_sinkhorn(cost, q_lens, q_group, c_lens, B, Sq, Sc, sched, temp, o, (cudaStream_t)stream);
 }
+
+// Q x C all-pairs mode: every query document against every candidate document, dual values only.  One fused launch per
+// query on the caller's stream (the kernel is bound by fp32 issue, not by memory, so re-streaming the candidates for
+// every query costs nothing), scores[i * NC + j] = OT_eps(query i, candidate j).
+extern "C" int asp_ot_score_allpairs(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens,
+                                     int NC, int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp,
+                                     float* scores, void* workspace, size_t workspace_bytes, asp_stream_t stream) {
+    ASP_REQUIRE(scores, "asp_ot_score_allpairs: scores is NULL");
+    ASP_REQUIRE(NQ >= 0 && NC >= 0, "asp_ot_score_allpairs: bad shape NQ=%d NC=%d", NQ, NC);
+    for (int i = 0; i < NQ; ++i) {
+        asp_ot_outputs out = {};
+        out.dual = scores + (size_t)i * NC;
+        const int rc = asp_ot_score(q + (size_t)i * Sq * D, q_lens + i, NC > 0 ? NC : 1, c, c_lens, NC, Sq, Sc, D, eps_host,
+                                    n_eps, temp, &out, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+    }
+    return ASP_OK;
+}

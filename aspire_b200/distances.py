@@ -104,6 +104,27 @@ def ot_scores(q, q_lens, c, c_lens, eps_list, temp=1.0, want=("dual",), broadcas
     return res
 
 
+def ot_scores_allpairs(q, q_lens, c, c_lens, eps_list, temp=1.0, out=None):
+    """otAspire dual values of EVERY query document against EVERY candidate document (``asp_ot_score_allpairs``).
+
+    q [NQ,Sq,D], c [NC,Sc,D] contiguous fp32 CUDA, lens int32 CUDA.  Returns fp32 [NQ, NC] (distances; negate for
+    similarities).  One fused launch per query, all on the current stream."""
+    _abi.require_cuda(q, c, q_lens, c_lens)
+    NQ, Sq, D = q.shape
+    NC, Sc, _ = c.shape
+    assert q.is_contiguous() and c.is_contiguous() and q.dtype == c.dtype == torch.float32 and c.shape[2] == D
+    dev = c.device
+    scores = out if out is not None else torch.empty((NQ, NC), dtype=torch.float32, device=dev)
+    L = _abi.lib()
+    need = int(L.asp_ot_score_workspace_bytes(NC, Sq, Sc, D))
+    ws = torch.empty(max(need // 4, 1), dtype=torch.float32, device=dev) if need else None
+    eps32 = np.asarray(eps_list, dtype=np.float32)
+    _abi.check(L.asp_ot_score_allpairs(_abi.ptr(q), _abi.ptr(q_lens), NQ, _abi.ptr(c), _abi.ptr(c_lens), NC, Sq, Sc, D,
+                                       eps32.ctypes.data_as(_abi.c_float_p), len(eps32), float(temp), _abi.ptr(scores),
+                                       _abi.ptr(ws), need, _abi.stream_of(dev)), "asp_ot_score_allpairs")
+    return scores
+
+
 def l2max_scores(q, q_lens, c, c_lens, broadcast_query=False, want_pair_sims=False):
     """tsAspire on contiguous fp32 CUDA tensors: (best [B], flat argmax int32 [B], pair_sims or None)."""
     _abi.require_cuda(q, c, q_lens, c_lens)

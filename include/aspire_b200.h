@@ -201,6 +201,16 @@ int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, const float
 int asp_pair_heads(const float* cost, const int32_t* q_lens, int q_group, const int32_t* c_lens, int B, int Sq, int Sc,
                    float temp, float* top2, float* att, float* att_probs, asp_stream_t stream);
 
+/*
+ * Q x C all-pairs mode of asp_ot_score (dual values only): scores[i*NC + j] = OT_eps(query i, candidate j) for every
+ * query document i < NQ (q [NQ,Sq,D], q_lens [NQ]) and candidate document j < NC (c [NC,Sc,D], c_lens [NC]) -- the
+ * all-queries x whole-corpus use of compute_distance (pair_distances.py:21-92 reached from pp_gen_nearest.py:154-202
+ * for every query of a pool file).  One fused launch per query on `stream`; workspace as for asp_ot_score with B = NC.
+ */
+int asp_ot_score_allpairs(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens, int NC,
+                          int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp, float* scores,
+                          void* workspace, size_t workspace_bytes, asp_stream_t stream);
+
 /* Same solver on a precomputed cost tensor [B,Sq,Sc] (as written by asp_pair_cost). */
 int asp_ot_sinkhorn_from_cost(const float* cost, const int32_t* q_lens, int q_broadcast, const int32_t* c_lens,
                               int B, int Sq, int Sc, const float* eps_host, int n_eps, float temp,

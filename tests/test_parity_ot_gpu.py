@@ -326,3 +326,22 @@ def test_headline_shape_full_size_properties():
     sub = torch.arange(0, NQ * POOL, 128, device="cuda")
     ref = ar.ot_distance(q[sub // POOL].cpu(), [S] * len(sub), c[sub].cpu(), [S] * len(sub), diameter=65.0)
     assert rel_err(base[sub].cpu().numpy(), ref.numpy()).max() <= 1e-4
+
+
+def test_allpairs_mode_equals_per_query_calls():
+    """asp_ot_score_allpairs: [NQ, NC] dual values = one broadcast call per query (ragged documents, 12-sentence
+    candidates take the cost + warp-Sinkhorn path, 10-sentence ones the fused kernel)."""
+    from aspire_b200 import ot_scores, ot_scores_allpairs, epsilon_schedule
+    g = torch.Generator().manual_seed(5)
+    for Sc in (10, 12):
+        NQ, NC, Sq, D = 5, 700, 9, 256
+        q = (0.3 * torch.randn(NQ, Sq, D, generator=g)).cuda()
+        c = (0.3 * torch.randn(NC, Sc, D, generator=g)).cuda()
+        ql = torch.randint(1, Sq + 1, (NQ,), generator=g).int().cuda()
+        cl = torch.randint(1, Sc + 1, (NC,), generator=g).int().cuda()
+        eps = epsilon_schedule(30.0, 0.05, 0.9)
+        allp = ot_scores_allpairs(q, ql, c, cl, eps)
+        assert tuple(allp.shape) == (NQ, NC) and torch.isfinite(allp).all()
+        for i in range(NQ):
+            one = ot_scores(q[i:i + 1].contiguous(), ql[i:i + 1].contiguous(), c, cl, eps, broadcast_query=True)["dual"]
+            assert torch.equal(allp[i], one)
