@@ -121,6 +121,15 @@ __global__ void __launch_bounds__(512, 1) k_mma_tf32(float* out, int iters, int 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// how long does nanosleep(t) really suspend a warp?  (idle warps of the fused kernel poll an mbarrier)
+__global__ void k_nanosleep(unsigned long long* out, unsigned t, int reps) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int i = 0; i < reps; ++i) __nanosleep(t);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+}
+
 // mode bits: 1 = warps 0-3 run the FMA chain, 2 = warps 4-7 run the ex2 chain; kind 0 = FFMA2, 1 = FFMA, 2 = FFMA2+LOP3
 __global__ void __launch_bounds__(256, 1) k_spec(float* out, int mode, int kind, int it_fma, int it_ex2, float a, float b) {
     const int warp = threadIdx.x >> 5;
@@ -190,6 +199,14 @@ int main() {
             double clk = ms * 1e-3 * khz3 * 1e3 / mma_per_smsp;
             printf("mma.sync m16n8k8 tf32, %d warp(s) per scheduler: %.3f ms -> %.2f clk per MMA per scheduler = %.0f FMA/clk/SM\n",
                    wa / 4, ms, clk, 4.0 * 1024.0 / clk);
+        }
+    }
+    {
+        unsigned long long* o; cudaMalloc(&o, sizeof(unsigned long long) * sms);
+        for (unsigned t : {100u, 1000u, 10000u, 100000u}) {
+            k_nanosleep<<<sms, 32>>>(o, t, 200); cudaDeviceSynchronize();
+            unsigned long long h[4]; cudaMemcpy(h, o, sizeof(h), cudaMemcpyDeviceToHost);
+            printf("nanosleep(%u) x200: %.0f ns per call (globaltimer)\n", t, (double)h[0] / 200.0);
         }
     }
     // clocks per instruction for the single-warp-per-scheduler chains
