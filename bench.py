@@ -51,6 +51,27 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE the pinned
+    host buffers are allocated, so that with several ranks per box every rank's H2D traffic stays on its own socket."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{bdf}: {spec}"
+    except Exception as e:  # best effort: a container without sysfs PCI nodes simply keeps its affinity
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
 def ncu_traffic(pairs_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum of one ot_fused_kernel launch of this size, in GB, from the
     committed `ncu --set full` capture (profiles/ncu_traffic.json); None when no capture of that launch shape exists."""
@@ -212,6 +233,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _abi.lib()  # fail loudly if the CUDA library is missing
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     NQ = args.queries
@@ -354,7 +376,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "clocks": clocks,
         "e2e": {"value": NP * world * e2e_steps / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "cpu_affinity": numa,
                 "api": "aspire_b200.similarity.score_pools_host (pinned host tensors in, chunked H2D overlapped with "
                        "scoring, host scores out)"},
         "gpu_launches": int(launches),
