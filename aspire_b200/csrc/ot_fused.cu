@@ -459,7 +459,9 @@ constexpr int kV7Slots = 4;                 // half-tiles per scheduler
 constexpr int kV7SlotFloats = kV7Half * kV7Ld;
 // dynamic shared memory, floats: [4 schedulers][kV7Slots] half-tiles | per Gram warp: reduced values, query norms, ring
 constexpr int kV7GramSmem = 2 * kRedVals + 16 + kRing * kSliceFloats;
-constexpr int kV7Smem = 4 * kV7Slots * kV7SlotFloats + kV7Gram * kV7GramSmem;
+constexpr int kV7RowSlots = 3;               // pairs a Sinkhorn warp solves ten-lanes-per-pair when a pass is that small
+constexpr int kV7Scratch = kV7RowSlots * kV7Ld;  // floats of exponential scratch per Sinkhorn warp
+constexpr int kV7Smem = 4 * kV7Slots * kV7SlotFloats + kV7Gram * kV7GramSmem + 4 * kV7Scratch;
 static_assert((4 * kV7Slots * kV7SlotFloats) % 4 == 0 && (2 * kRedVals + 16) % 4 == 0 && kV7GramSmem % 4 == 0, "16-byte alignment");
 
 constexpr int kV7GramRegs = 200, kV7SinkRegs = 104;  // 8 x 200 + 4 x 104 = 2016 <= 2048 registers per lane slot
@@ -478,7 +480,10 @@ __device__ __forceinline__ void v7_phase2_full(float* Cs, int b, const float* ep
     solve_pair_thread_stream<kFT, kFT, true>(Cs, kFT, kFT, b, kFT, kFT, eps_s, n_eps, inv_temp, *out);
 }
 
-template <int DT>
+// ROWS: instantiation for launches of at most one pair per Gram warp (a single query against a <= 1k pool): the
+// Sinkhorn warps then solve with ten lanes per pair (solve_pairs_rows, ~1/3 shorter launch).  Kept out of the
+// large-batch instantiation, whose 104-register Sinkhorn loop it would crowd.
+template <int DT, bool ROWS>
 __global__ void __launch_bounds__(kV7Warps * 32, 1)
 ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     extern __shared__ float smem[];
@@ -592,7 +597,27 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
             }
             const int my_np = hsel ? np[1] : np[0], my_base = hsel ? base[1] : base[0];
             const int sl_mine = (t0 + hsel) % kV7Slots;
-            if (l16 < my_np) {
+            bool solved = false;
+            if (ROWS && np[0] + np[1] <= kV7RowSlots && np[0] + np[1] > 0) {
+                // low-latency path: ten lanes per pair (lanes 10p .. 10p+9 <-> the p-th pair of this pass)
+                const int p = lane / kFT, r = lane - p * kFT;
+                const bool active = p < np[0] + np[1];
+                const int from_b = (active && p >= np[0]) ? 1 : 0;            // which half-tile the pair sits in
+                const int idx = active ? (from_b ? p - np[0] : p) : 0;        // its index there
+                const int sl_p = (t0 + from_b) % kV7Slots;
+                const float* Cp = slots + sl_p * kV7SlotFloats + idx * kV7Ld;
+                const int b = (from_b ? base[1] : base[0]) + idx;
+                int ql = 0, cl = 0;
+                if (active) {
+                    ql = min(max(a.q_lens[b / a.q_group], 0), a.Sq);
+                    cl = min(max(a.c_lens[b], 0), a.Sc);
+                }
+                float* scratch = smem + 4 * kV7Slots * kV7SlotFloats + kV7Gram * kV7GramSmem + w * kV7Scratch +
+                                 (active ? p : 0) * kV7Ld;
+                solved = solve_pairs_rows<kFT>(Cp, ql, cl, b, a.Sq, a.Sc, active, min(p, kV7RowSlots - 1) * kFT, r, scratch,
+                                               eps_s, sched.n, a.inv_temp, out_s);
+            }
+            if (!solved && l16 < my_np) {
                 float* Cs = slots + sl_mine * kV7SlotFloats + l16 * kV7Ld;
                 const int b = my_base + l16;
                 // warp-uniform choice keeps the two specialisations from serialising inside a warp
@@ -636,8 +661,10 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
     if (attr_dev != dev) {
         ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v6));
         ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v6));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
         attr_dev = dev;
     }
     // Tile size: 32 pairs per warp once the batch can feed every resident warp; smaller batches are spread over more
@@ -657,10 +684,15 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
     const int ntiles = (B + tile_pairs - 1) / tile_pairs;
     const int ctas = std::min(max_ctas, (ntiles + per_cta - 1) / per_cta);
     if (v7) {
-        if (D == 768)
-            ot_fused_v7_kernel<768><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+        const bool rows = tile_pairs == 1;  // at most one pair per Gram warp: the low-latency instantiation
+        if (D == 768 && rows)
+            ot_fused_v7_kernel<768, true><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+        else if (D == 768)
+            ot_fused_v7_kernel<768, false><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+        else if (rows)
+            ot_fused_v7_kernel<0, true><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
         else
-            ot_fused_v7_kernel<0><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+            ot_fused_v7_kernel<0, false><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
     } else if (D == 768) {
         ot_fused_kernel<768><<<ctas, kFusedWarps * 32, smem, stream>>>(a, sched, out);
     } else {

@@ -512,3 +512,148 @@ __device__ __forceinline__ void solve_pair_thread_stream(float* Cs, int ql_in, i
 }
 
 }  // namespace asp
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Low-latency variant for passes that carry only a few pairs (a single query against a 1k pool leaves <= 2 pairs per
+// Sinkhorn warp): TEN LANES cooperate on one pair instead of one thread solving it alone.  Lane 10p + r of the warp owns
+// row r AND column r of pair slot p (p < 3): it keeps its cost row in registers, computes the ten shared exponentials
+// of its row per step, leaves them in a small shared scratch tile, and sums its column from there; potentials of the
+// other rows/columns travel by shuffle.  Same formulas as sinkhorn_step, ~12 MUFU per lane and step instead of 121, so
+// a solve takes ~1/6 of the thread-per-pair time when the warp is otherwise empty.  Returns false (nothing written)
+// if a sum left the fp32 range; the caller then falls back to the per-thread solver and its stabilised path.
+namespace asp {
+
+template <int T>  // tile is T x T (T = 10), cost stride T
+__device__ __forceinline__ bool solve_pairs_rows(const float* Cs_pair, int ql, int cl, int b, int Sq, int Sc, bool active,
+                                                 int group_base, int r, float* scratch, const float* eps_sched, int n_eps,
+                                                 float inv_temp, const OtOut& out) {
+    // `active`: this lane belongs to a pair slot that holds a pair; group_base = first lane of the slot; r = lane - base.
+    // scratch: T*T floats per slot (this slot's block), visible to the slot's ten lanes.
+    const unsigned full = 0xffffffffu;
+    const float kBig = 1.0e30f;
+    const bool row_ok = active && r < ql, col_ok = active && r < cl;
+    float C[T];
+#pragma unroll
+    for (int j = 0; j < T; ++j) C[j] = (row_ok && j < cl) ? Cs_pair[r * T + j] : kBig;
+    // marginals: row minimum is local, column minimum is read from the tile
+    float rmin = kBig, cmin = kBig;
+#pragma unroll
+    for (int j = 0; j < T; ++j) rmin = fminf(rmin, C[j]);
+    if (col_ok)
+#pragma unroll
+        for (int i = 0; i < T; ++i)
+            if (i < ql) cmin = fminf(cmin, Cs_pair[i * T + r]);
+    const float xr = row_ok ? -rmin * inv_temp : -INFINITY, xc = col_ok ? -cmin * inv_temp : -INFINITY;
+    float mr = -INFINITY, mc = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        mr = fmaxf(mr, __shfl_sync(full, xr, group_base + k));
+        mc = fmaxf(mc, __shfl_sync(full, xc, group_base + k));
+    }
+    const float er = row_ok ? expf(xr - mr) : 0.f, ec = col_ok ? expf(xc - mc) : 0.f;
+    float sr = 0.f, sc = 0.f;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        sr += __shfl_sync(full, er, group_base + k);
+        sc += __shfl_sync(full, ec, group_base + k);
+    }
+    const float alpha = row_ok ? expf(xr - (mr + logf(sr))) : 0.f, beta = col_ok ? expf(xc - (mc + logf(sc))) : 0.f;
+    const float la = (alpha > 0.f) ? log2f(alpha) : kLogZeroWeight * kLog2e;
+    const float lb = (beta > 0.f) ? log2f(beta) : kLogZeroWeight * kLog2e;
+#pragma unroll
+    for (int j = 0; j < T; ++j)
+        if (!(row_ok && j < cl)) C[j] = 0.f;  // padded entries: any finite value (their weight is 0)
+    float f = 0.f, g = 0.f;
+    bool ok = true;
+    if (__any_sync(full, active && ql > 0 && cl > 0)) {
+#pragma unroll 1
+        for (int k = -1; k <= n_eps; ++k) {
+            const float eps = eps_sched[min(max(k, 0), n_eps - 1)];
+            const float t = kLog2e / eps;
+            const bool plain = (k < 0) | (k == n_eps);
+            const float scale = (plain ? 1.0f : 0.5f) * eps * kLn2;
+            const float u = fmaf(f, t, la), v_own = fmaf(g, t, lb);
+            float Rx = 0.f, Ry = 0.f;  // even / odd columns, as the packed accumulator of the per-thread solver sums them
+#pragma unroll
+            for (int j = 0; j < T; ++j) {
+                const float vj = __shfl_sync(full, v_own, group_base + j);
+                const float e = ex2(fmaf(C[j], -t, u + vj));
+                if (j & 1) Ry += e; else Rx += e;
+                if (active) scratch[r * T + j] = e;
+            }
+            const float R = Rx + Ry;
+            __syncwarp();
+            float S = 0.f;
+            if (active)
+#pragma unroll
+                for (int i = 0; i < T; ++i) S += scratch[i * T + r];
+            __syncwarp();
+            const float lr = lg2(R), ls = lg2(S);
+            const bool bad = (row_ok && !(fabsf(lr) < 1e30f)) || (col_ok && !(fabsf(ls) < 1e30f));
+            if (__any_sync(full, bad && ql > 0 && cl > 0)) {
+                ok = false;
+                break;
+            }
+            f = row_ok ? fmaf(-scale, lr - la, f) : 0.f;
+            g = col_ok ? fmaf(-scale, ls - lb, g) : 0.f;
+        }
+    }
+    if (!ok) return false;
+    if (!(ql > 0 && cl > 0)) f = g = 0.f;
+    // outputs
+    // (same order of operations as the per-thread solver, so that a pair's values do not depend on the path taken)
+    float dual = 0.f;
+#pragma unroll
+    for (int k = 0; k < T; ++k) dual = fmaf(__shfl_sync(full, alpha, group_base + k), __shfl_sync(full, f, group_base + k), dual);
+#pragma unroll
+    for (int k = 0; k < T; ++k) dual = fmaf(__shfl_sync(full, beta, group_base + k), __shfl_sync(full, g, group_base + k), dual);
+    float primal = 0.f;
+    const bool want_mat = out.primal || out.plan || out.weighted || out.neg_cost;
+    if (want_mat) {
+        const float tf = kLog2e / eps_sched[n_eps - 1];
+        float w[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const float gj = __shfl_sync(full, g, group_base + j), bj = __shfl_sync(full, beta, group_base + j);
+            const bool valid = row_ok && j < cl;
+            const float p = valid ? ex2((f + gj - C[j]) * tf) * (alpha * bj) : 0.f;
+            const float negc = valid ? -C[j] : 0.f;
+            w[j] = p * negc;
+            if (active && r < Sq && j < Sc) {
+                const size_t o = (size_t)b * Sq * Sc + r * Sc + j;
+                if (out.neg_cost) out.neg_cost[o] = negc;
+                if (out.plan) out.plan[o] = p;
+                if (out.weighted) out.weighted[o] = w[j];
+            }
+        }
+        // row-major running sum handed from row to row (the per-thread solver adds the 100 products in that order)
+        float run = 0.f;
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const float prev = __shfl_sync(full, run, group_base + (i ? i - 1 : 0));
+            if (r == i) {
+                run = i ? prev : 0.f;
+#pragma unroll
+                for (int j = 0; j < T; ++j) run += w[j];
+            }
+        }
+        primal = __shfl_sync(full, run, group_base + T - 1);
+    }
+    if (active) {
+        if (r == 0) {
+            if (out.dual) out.dual[b] = dual;
+            if (out.primal) out.primal[b] = primal;
+        }
+        if (r < Sq) {
+            if (out.f) out.f[(size_t)b * Sq + r] = f;
+            if (out.alpha) out.alpha[(size_t)b * Sq + r] = alpha;
+        }
+        if (r < Sc) {
+            if (out.g) out.g[(size_t)b * Sc + r] = g;
+            if (out.beta) out.beta[(size_t)b * Sc + r] = beta;
+        }
+    }
+    return true;
+}
+
+}  // namespace asp
