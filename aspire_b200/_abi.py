@@ -62,6 +62,7 @@ def lib():
     L.asp_ot_score.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, ctypes.POINTER(AspOtOutputs), vp,
                                ctypes.c_size_t, vp]
     L.asp_ot_score_workspace_bytes.argtypes = [ci, ci, ci, ci]
+    L.asp_ot_score_indexed.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, ctypes.POINTER(AspOtOutputs), vp]
     L.asp_ot_score_allpairs.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, vp, vp, ctypes.c_size_t, vp]
     L.asp_ot_sinkhorn_from_cost.argtypes = [vp, vp, ci, vp, ci, ci, ci, c_float_p, ci, cf,
                                             ctypes.POINTER(AspOtOutputs), vp]

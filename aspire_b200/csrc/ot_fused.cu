@@ -57,6 +57,8 @@ struct FusedArgs {
     const int32_t* q_lens;
     const float* c;
     const int32_t* c_lens;
+    const int32_t* c_index;  // optional: pair b scores candidate document c_index[b] of a resident corpus (c, c_lens are
+                             // then indexed by document id); NULL = candidate b
     int q_group, B, Sq, Sc, D, slot;
     int stagger;     // 1: warp w+4 starts after warp w's first phase 1 (asp_set_option "ot_stagger")
     int tile_pairs;  // pairs per warp tile (<= 32; chosen by the launcher so that the tiles fill whole waves of warps)
@@ -156,7 +158,7 @@ __device__ __forceinline__ void query_to_tmem(const FusedArgs& a, int qidx, int 
 // Register plan per lane: 5x10 packed accumulators (100) + 10 packed candidate norms (20) + the current candidate
 // slice (40, one 128-bit LDS per row; lanes l and l+16 read the same address) + two 5-row query slices (40).
 template <int DT, bool FULL, int LD = kCostLd>
-__device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs, int my_ql, int my_cl, int lane, float* Cs,
+__device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs, int my_ql, int my_cl, int my_ci, int lane, float* Cs,
                                        float* red, float* qn_s, float* ring, uint32_t tq, const int* lut_s) {
     const int h = lane >> 4, l16 = lane & 15;
     const int D = DT ? DT : a.D, d4 = D >> 2;
@@ -175,7 +177,8 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
     // ---- producer side of the ring: slices are issued in stream order (pair ip, slice iit) ----
     // lane l copies the 16-byte piece (row (l>>4) + 2m, float4 column l&15) for m = 0..4
     int ip = 0, iit = 0, islot = 0;
-    const float* gsrc = a.c + (size_t)base * doc + (size_t)h * D + l16 * 4;
+    const size_t lane_off = (size_t)h * D + l16 * 4;
+    const float* gsrc = a.c + (size_t)__shfl_sync(0xffffffffu, my_ci, 0) * doc + lane_off;  // lane p holds pair p's document
     const uint32_t sring = tc::smem_u32(ring) + (uint32_t)lane * 16u;
     uint32_t sdst = sring;
     auto issue_next = [&]() {
@@ -202,10 +205,10 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
                 }
             }
             gsrc += 64;
-            if (++iit == nit) {
+            if (++iit == nit) {  // next document of the tile (consecutive without an index list, anywhere with one)
                 iit = 0;
                 ++ip;
-                gsrc += doc - D;
+                gsrc = a.c + (size_t)__shfl_sync(0xffffffffu, my_ci, min(ip, npairs - 1)) * doc + lane_off;
             }
         }
         cp_async_commit();  // always commit: the wait below counts groups
@@ -401,18 +404,19 @@ ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
         const int base = tile * a.tile_pairs;
         const int npairs = min(a.tile_pairs, a.B - base);
         // lane p keeps the lengths of pair base+p
-        int my_ql = 0, my_cl = 0;
+        int my_ql = 0, my_cl = 0, my_ci = 0;
         if (lane < npairs) {
+            my_ci = a.c_index ? a.c_index[base + lane] : base + lane;
             my_ql = min(max(a.q_lens[(base + lane) / a.q_group], 0), a.Sq);
-            my_cl = min(max(a.c_lens[base + lane], 0), a.Sc);
+            my_cl = min(max(a.c_lens[my_ci], 0), a.Sc);
         }
         // uniform fast path: every pair of the tile has all kFT x kFT sentences (no predicates, no zero fill)
         const bool full_tile = __all_sync(0xffffffffu, lane >= npairs || (my_ql == kFT && my_cl == kFT)) &&
                                a.Sq == kFT && a.Sc == kFT;
         if (full_tile)
-            phase1<DT, true>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
+            phase1<DT, true>(a, base, npairs, my_ql, my_cl, my_ci, lane, Cs, red, qn_s, ring, tq, lut_s);
         else
-            phase1<DT, false>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
+            phase1<DT, false>(a, base, npairs, my_ql, my_cl, my_ci, lane, Cs, red, qn_s, ring, tq, lut_s);
         __syncwarp();
         if (first && warp < 4) {
             if (lane == 0) stagger_s[warp] = 1;
@@ -549,18 +553,19 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
             }
             const int base = tile * a.tile_pairs;
             const int npairs = min(a.tile_pairs, a.B - base);
-            int my_ql = 0, my_cl = 0;
+            int my_ql = 0, my_cl = 0, my_ci = 0;
             if (lane < npairs) {
+                my_ci = a.c_index ? a.c_index[base + lane] : base + lane;
                 my_ql = min(max(a.q_lens[(base + lane) / a.q_group], 0), a.Sq);
-                my_cl = min(max(a.c_lens[base + lane], 0), a.Sc);
+                my_cl = min(max(a.c_lens[my_ci], 0), a.Sc);
             }
             const bool full_tile = __all_sync(0xffffffffu, lane >= npairs || (my_ql == kFT && my_cl == kFT)) &&
                                    a.Sq == kFT && a.Sc == kFT;
             float* Cs = slots + sl * kV7SlotFloats;
             if (full_tile)
-                phase1<DT, true, kV7Ld>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
+                phase1<DT, true, kV7Ld>(a, base, npairs, my_ql, my_cl, my_ci, lane, Cs, red, qn_s, ring, tq, lut_s);
             else
-                phase1<DT, false, kV7Ld>(a, base, npairs, my_ql, my_cl, lane, Cs, red, qn_s, ring, tq, lut_s);
+                phase1<DT, false, kV7Ld>(a, base, npairs, my_ql, my_cl, my_ci, lane, Cs, red, qn_s, ring, tq, lut_s);
             __syncwarp();
             if (lane == 0) {
                 meta_s[w][sl][0] = base;
@@ -610,7 +615,7 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
                 int ql = 0, cl = 0;
                 if (active) {
                     ql = min(max(a.q_lens[b / a.q_group], 0), a.Sq);
-                    cl = min(max(a.c_lens[b], 0), a.Sc);
+                    cl = min(max(a.c_lens[a.c_index ? a.c_index[b] : b], 0), a.Sc);
                 }
                 float* scratch = smem + 4 * kV7Slots * kV7SlotFloats + kV7Gram * kV7GramSmem + w * kV7Scratch +
                                  (active ? p : 0) * kV7Ld;
@@ -625,7 +630,7 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
                     v7_phase2_full(Cs, b, eps_s, sched.n, a.inv_temp, &out_s);
                 } else {
                     const int ql = min(max(a.q_lens[b / a.q_group], 0), a.Sq);
-                    const int cl = min(max(a.c_lens[b], 0), a.Sc);
+                    const int cl = min(max(a.c_lens[a.c_index ? a.c_index[b] : b], 0), a.Sc);
                     v7_phase2(Cs, ql, cl, b, a.Sq, a.Sc, eps_s, sched.n, a.inv_temp, &out_s);
                 }
             }
@@ -649,8 +654,9 @@ bool ot_fused_supported(int Sq, int Sc, int D) {
     return Sq <= kFT && Sc <= kFT && D >= 128 && (D % 128) == 0 && D <= kMaxFusedD;
 }
 
-int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens, int B,
-                    int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out, cudaStream_t stream) {
+int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
+                    const int32_t* c_index, int B, int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out,
+                    cudaStream_t stream) {
     static std::atomic<unsigned int> next_slot{0};
     const bool v7 = g_ot_fused_mode == 1;
     const int smem_v6 = kFusedWarps * kWarpSmem * (int)sizeof(float), smem_v7 = kV7Smem * (int)sizeof(float);
@@ -678,7 +684,7 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
     const int nwarps = max_ctas * per_cta;
     const int waves = (B + max_tile * nwarps - 1) / (max_tile * nwarps);
     const int tile_pairs = std::min(max_tile, std::max(1, (B + waves * nwarps - 1) / (waves * nwarps)));
-    FusedArgs a{q, q_lens, c, c_lens, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), g_ot_stagger,
+    FusedArgs a{q, q_lens, c, c_lens, c_index, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), g_ot_stagger,
                 tile_pairs,
                 1.0f / temp};
     const int ntiles = (B + tile_pairs - 1) / tile_pairs;
@@ -728,7 +734,8 @@ extern "C" int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, 
     if (B == 0) return ASP_OK;
     const asp::OtOut o = asp::to_out(out);
     if (asp::ot_fused_supported(Sq, Sc, D) && asp::g_ot_kernel != 1)
-        return asp::ot_fused_launch(q, q_lens, q_group, c, c_lens, B, Sq, Sc, D, sched, temp, o, (cudaStream_t)stream);
+        return asp::ot_fused_launch(q, q_lens, q_group, c, c_lens, nullptr, B, Sq, Sc, D, sched, temp, o,
+                                    (cudaStream_t)stream);
     const size_t need = (size_t)B * Sq * Sc * sizeof(float);
     ASP_REQUIRE(workspace && workspace_bytes >= need, "asp_ot_score: workspace of %zu bytes needed for %dx%d sentences",
                 need, Sq, Sc);
@@ -754,4 +761,26 @@ extern "C" int asp_ot_score_allpairs(const float* q, const int32_t* q_lens, int 
         if (rc) return rc;
     }
     return ASP_OK;
+}
+
+// Pools as index lists into a corpus that stays in HBM: pair b = (query b / q_group, corpus document c_index[b]).  c is
+// the WHOLE corpus [N,Sc,D] and c_lens its [N] lengths; nothing is gathered or copied -- the kernel's producer walks the
+// index list.  Fused shapes only (Sq, Sc <= 10, D % 128 == 0, D <= 768); other shapes: gather on the caller's side.
+extern "C" int asp_ot_score_indexed(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
+                                    const int32_t* c_index, int B, int Sq, int Sc, int D, const float* eps_host, int n_eps,
+                                    float temp, const asp_ot_outputs* out, asp_stream_t stream) {
+    if (B == 0) return ASP_OK;
+    int rc = asp::check_pair_args(q, q_lens, c, c_lens, B, Sq, Sc, D);
+    if (rc) return rc;
+    ASP_REQUIRE(out && c_index, "asp_ot_score_indexed: out / c_index is NULL");
+    ASP_REQUIRE(q_group >= 1 && temp > 0.f, "asp_ot_score_indexed: q_group >= 1 and temp > 0 required");
+    if (!asp::ot_fused_supported(Sq, Sc, D)) {
+        asp::set_error("asp_ot_score_indexed: %dx%d sentences, D=%d is not a fused shape", Sq, Sc, D);
+        return ASP_ERR_UNSUPPORTED;
+    }
+    asp::EpsSched sched;
+    rc = asp::make_sched(eps_host, n_eps, &sched);
+    if (rc) return rc;
+    return asp::ot_fused_launch(q, q_lens, q_group, c, c_lens, c_index, B, Sq, Sc, D, sched, temp, asp::to_out(out),
+                                (cudaStream_t)stream);
 }

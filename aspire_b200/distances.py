@@ -68,22 +68,35 @@ _OT_FIELDS = ("dual", "primal", "f", "g", "alpha", "beta", "neg_cost", "plan", "
 
 
 def ot_scores(q, q_lens, c, c_lens, eps_list, temp=1.0, want=("dual",), broadcast_query=False, cost_workspace=None,
-              q_group=None, out=None):
+              q_group=None, out=None, c_index=None):
     """Masked Sinkhorn OT on contiguous fp32 CUDA tensors through the fused entry point ``asp_ot_score``.
 
     c [B,Sc,D]; q [B,Sq,D] (paired, default), [1,Sq,D] with ``broadcast_query``, or [ceil(B/q_group),Sq,D] with
     ``q_group`` = number of consecutive candidates sharing one query (several query pools in one launch).
     lens: int32 CUDA tensors.  ``eps_list``: the epsilon schedule (python floats / float64).
     ``out``: optional dict of preallocated output tensors (reused across calls).  Returns a dict of outputs.
+    ``c_index``: optional int32 CUDA tensor [B] -- pair b scores corpus document ``c_index[b]``; ``c`` / ``c_lens`` are
+    then the whole resident corpus [N,Sc,D] / [N] and nothing is gathered (``asp_ot_score_indexed``; shapes the fused
+    kernel does not cover are gathered here and go through ``asp_ot_score``).
     """
     _abi.require_cuda(q, c, q_lens, c_lens)
-    B, Sc, D = c.shape
+    if c_index is not None:
+        _abi.require_cuda(c_index)
+        assert c_index.dtype == torch.int32 and c_index.is_contiguous()
+        N, Sc, D = c.shape
+        if _abi.lib().asp_ot_score_workspace_bytes(1, q.shape[1], Sc, D) != 0:  # not a fused shape: gather
+            idx = c_index.long()
+            return ot_scores(q, q_lens, c.index_select(0, idx).contiguous(), c_lens.index_select(0, idx).contiguous(),
+                             eps_list, temp=temp, want=want, broadcast_query=broadcast_query, q_group=q_group, out=out)
+        B = int(c_index.numel())
+    else:
+        B, Sc, D = c.shape
     Sq = q.shape[1]
     if q_group is None:
         q_group = max(B, 1) if broadcast_query else 1
     assert q_group >= 1 and q.shape[0] == max(-(-B // q_group), 1 if broadcast_query else 0), \
         "query batch does not match candidates / q_group"
-    assert q_lens.numel() == q.shape[0] and c_lens.numel() == B
+    assert q_lens.numel() == q.shape[0] and (c_index is not None or c_lens.numel() == B)
     assert q.is_contiguous() and c.is_contiguous() and q.dtype == c.dtype == torch.float32
     dev = c.device
     shapes = {"dual": (B,), "primal": (B,), "f": (B, Sq), "g": (B, Sc), "alpha": (B, Sq), "beta": (B, Sc),
@@ -92,6 +105,12 @@ def ot_scores(q, q_lens, c, c_lens, eps_list, temp=1.0, want=("dual",), broadcas
            for k in want}
     outs = _abi.AspOtOutputs(**{k: (res[k].data_ptr() if k in res else None) for k in _OT_FIELDS})
     L = _abi.lib()
+    if c_index is not None:
+        eps32 = np.asarray(eps_list, dtype=np.float32)
+        _abi.check(L.asp_ot_score_indexed(_abi.ptr(q), _abi.ptr(q_lens), int(q_group), _abi.ptr(c), _abi.ptr(c_lens),
+                                          _abi.ptr(c_index), B, Sq, Sc, D, eps32.ctypes.data_as(_abi.c_float_p), len(eps32),
+                                          float(temp), ctypes.byref(outs), _abi.stream_of(dev)), "asp_ot_score_indexed")
+        return res
     need = int(L.asp_ot_score_workspace_bytes(B, Sq, Sc, D))
     if need and (cost_workspace is None or cost_workspace.numel() * cost_workspace.element_size() < need):
         cost_workspace = torch.empty(need // 4, dtype=torch.float32, device=dev)

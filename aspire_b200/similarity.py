@@ -125,6 +125,49 @@ def pack_pool(cand_encs, device, max_sents=None):
     return host.to(device, non_blocking=True), torch.tensor(lens, dtype=torch.int32).to(device, non_blocking=True)
 
 
+class ResidentCorpus:
+    """All encodings of a dataset packed ONCE into HBM ([N, Smax, D] fp32 + lengths), pools addressed by paper id.
+
+    The reference keeps per-paper encodings in an h5py / joblib cache and re-packs every pool on the host
+    (utils/models.py:68-124, disent_models.py:274-290); here a query's pool is an int32 index list and
+    ``asp_ot_score_indexed`` walks it -- no gather, no host copy per query.  180 GB hold 5.8 M ten-sentence documents.
+    """
+
+    def __init__(self, pid2enc: Dict, device=None, max_sents=None):
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.pids = list(pid2enc)
+        self.row = {p: i for i, p in enumerate(self.pids)}
+        self.reps, self.lens = pack_pool([pid2enc[p] for p in self.pids], self.device, max_sents=max_sents)
+
+    def indices(self, pids):
+        return torch.tensor([self.row[p] for p in pids], dtype=torch.int32).to(self.device, non_blocking=True)
+
+    def score_pool(self, query_pid, cand_pids, model_hparams=None, diameter=None, score_aggregation='l2wasserstein'):
+        """Similarities (higher == closer) of paper ``query_pid`` against ``cand_pids``: fp32 CPU tensor [len(cand_pids)].
+        otAspire: -OT_eps with the schedule from ``diameter`` / ``geoml_diameter`` (default: the bounding box of the whole
+        corpus, computed once); ``score_aggregation='l2max'``: tsAspire."""
+        hp = dict(model_hparams or {})
+        qi = self.row[query_pid]
+        q = self.reps[qi:qi + 1]
+        q_lens = self.lens[qi:qi + 1]
+        idx = self.indices(cand_pids)
+        if score_aggregation == 'l2max':
+            c = self.reps.index_select(0, idx.long())
+            best, _i, _ = l2max_scores(q.contiguous(), q_lens.contiguous(), c, self.lens.index_select(0, idx.long()),
+                                       broadcast_query=True)
+            return best.cpu()
+        if diameter is None:
+            diameter = hp.get('geoml_diameter')
+        if diameter is None:
+            if not hasattr(self, "_diameter"):
+                self._diameter = bbox_diameter(self.reps, self.reps)
+            diameter = self._diameter
+        eps = epsilon_schedule(diameter, hp.get('geoml_blur', 0.05), hp.get('geoml_scaling', 0.9))
+        res = ot_scores(q.contiguous(), q_lens.contiguous(), self.reps, self.lens, eps, temp=hp.get('sent_sm_temp', 1.0),
+                        want=("dual",), q_group=max(len(cand_pids), 1), c_index=idx)
+        return (-res["dual"]).cpu()
+
+
 _HOST_PIPE = {}
 
 

@@ -211,6 +211,17 @@ int asp_ot_score_allpairs(const float* q, const int32_t* q_lens, int NQ, const f
                           int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp, float* scores,
                           void* workspace, size_t workspace_bytes, asp_stream_t stream);
 
+/*
+ * asp_ot_score with the candidates given as an index list into a corpus that stays in device memory: pair b scores
+ * query b / q_group against corpus document c_index[b]; c [N,Sc,D] and c_lens [N] describe the WHOLE corpus, c_index
+ * is int32 [B] on the device.  Nothing is gathered: the kernel walks the list.  This is how src/evaluation/evaluate.py:
+ * 62-74 and pp_gen_nearest.py:154-202 present their pools (candidate id lists into one encodings cache).  Fused shapes
+ * only (Sq, Sc <= 10, D % 128 == 0, D <= 768; ASP_ERR_UNSUPPORTED otherwise -- gather and call asp_ot_score).
+ */
+int asp_ot_score_indexed(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
+                         const int32_t* c_index, int B, int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp,
+                         const asp_ot_outputs* out, asp_stream_t stream);
+
 /* Same solver on a precomputed cost tensor [B,Sq,Sc] (as written by asp_pair_cost). */
 int asp_ot_sinkhorn_from_cost(const float* cost, const int32_t* q_lens, int q_broadcast, const int32_t* c_lens,
                               int B, int Sq, int Sc, const float* eps_host, int n_eps, float temp,

@@ -131,3 +131,25 @@ def test_rank_pool_sent_from_npy_reps_vs_float64_numpy_path(tmp_path):
                 assert abs(-neg_sim - want[cpid]) <= 3e-5 * max(1.0, abs(want[cpid])), (score_type, qpid, cpid)
             vals = [v for _, v in ranked]
             assert vals == sorted(vals)
+
+
+def test_resident_corpus_indexed_pools_match_packed_pools():
+    """Pools as index lists into a corpus kept in HBM (asp_ot_score_indexed): identical scores to packing each pool and
+    calling the plain entry point with the same schedule; ragged documents, repeated and out-of-order candidates."""
+    from aspire_b200 import ot_scores, epsilon_schedule
+    from aspire_b200.similarity import ResidentCorpus, pack_pool
+    rng = np.random.RandomState(11)
+    D = 768
+    pid2enc = {f"p{i}": (0.3 * rng.randn(rng.randint(1, 11), D)).astype(np.float32) for i in range(300)}
+    corpus = ResidentCorpus(pid2enc)
+    hp = {"geoml_diameter": 50.0}
+    for qpid, n in (("p7", 250), ("p123", 1), ("p0", 1500)):
+        cands = [f"p{j}" for j in rng.randint(0, 300, n)]
+        got = corpus.score_pool(qpid, cands, model_hparams=hp)
+        c, cl = pack_pool([pid2enc[p] for p in cands], corpus.device, max_sents=corpus.reps.shape[1])
+        q, ql = pack_pool([pid2enc[qpid]], corpus.device, max_sents=corpus.reps.shape[1])
+        eps = epsilon_schedule(50.0, 0.05, 0.9)
+        want = -ot_scores(q, ql, c, cl, eps, broadcast_query=True)["dual"].cpu()
+        assert torch.equal(got, want)
+        ts = corpus.score_pool(qpid, cands, score_aggregation='l2max')
+        assert ts.shape == (n,) and torch.isfinite(ts).all()
