@@ -66,6 +66,11 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_ot_stagger = value != 0;
         return ASP_OK;
     }
+    if (strcmp(key, "gemm_kernel") == 0) {  // developer switch: see bert/gemm.cu
+        ASP_REQUIRE(value >= 0 && value <= 3, "asp_set_option: gemm_kernel must be 0..3");
+        asp::g_gemm_kernel = value;
+        return ASP_OK;
+    }
     asp::set_error("asp_set_option: unknown key '%s'", key);
     return ASP_ERR_INVALID;
 }

@@ -16,6 +16,7 @@
 // fp32-equivalent mode ("bf16x3"): every fp32 operand x is carried as hi = bf16(x), lo = bf16(x - hi); the main loop
 // then runs three passes per K block into the SAME accumulator: hi.hi + hi.lo + lo.hi (the lo.lo term is below fp32
 // resolution).  The producer simply picks the tensor map of the pass; nothing else changes.
+#include <algorithm>
 #include "../common.cuh"
 #include "tc05.cuh"
 
@@ -47,7 +48,68 @@ struct GemmSmem {
     static constexpr int kTotal = kBarOff + 128 + 1024;  // barriers + slack for the 1024-byte alignment
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) -- the exact (erf) form HF BERT uses.  erf by Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7, i.e. at fp32 rounding level): one MUFU.RCP, one MUFU.EX2 and 14 FP32 ops per element, about half
+// of libdevice's branch-free erff; the epilogue of the FFN1 GEMM evaluates it 16k times per tile.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    const float r = p * t * e;  // 1 - erf(|x| / sqrt 2)
+    const float h = 0.5f * x;
+    return fmaf(fabsf(h), 1.0f - r, h);  // h (1 + sign(x) erf(|z|))
+}
+
+// Epilogue of 32 consecutive columns of one output row: bias, GELU / residual, stores (hi and optional lo halves).
+template <int EPI>
+__device__ __forceinline__ void epilogue_store32(const GemmArgs& g, float (&v)[32], bool row_ok, size_t off, int col) {
+    if (g.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + i));
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+    }
+    if (!row_ok) return;
+    if (EPI == EPI_GELU_BF16) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+        float4* o = reinterpret_cast<float4*>(g.out_f32 + off);
+        const float4* r = (EPI == EPI_RESID_F32) ? reinterpret_cast<const float4*>(g.residual + off) : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (EPI == EPI_RESID_F32) {
+                const float4 rr = __ldg(r + i / 4);
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            }
+            o[i / 4] = x;
+        }
+    } else {
+        uint4* oh = reinterpret_cast<uint4*>(g.out_hi + off);
+        uint4* ol = g.out_lo ? reinterpret_cast<uint4*>(g.out_lo + off) : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            __nv_bfloat162 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float a = v[i + 2 * j], b = v[i + 2 * j + 1];
+                h[j] = __floats2bfloat162_rn(a, b);
+                l[j] = __floats2bfloat162_rn(a - __low2float(h[j]), b - __high2float(h[j]));
+            }
+            oh[i / 8] = *reinterpret_cast<uint4*>(h);
+            if (ol) ol[i / 8] = *reinterpret_cast<uint4*>(l);
+        }
+    }
+}
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(128)
@@ -120,52 +182,149 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-        if (g.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c0 + i));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-            }
-        }
-        if (row_ok) {  // no early 'continue': every lane must reach the next tcgen05.ld converged
-        if (EPI == EPI_GELU_BF16) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        }
-        if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
-            float4* o = reinterpret_cast<float4*>(g.out_f32 + row_off + c0);
-            const float4* r = (EPI == EPI_RESID_F32) ? reinterpret_cast<const float4*>(g.residual + row_off + c0) : nullptr;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (EPI == EPI_RESID_F32) {
-                    const float4 rr = __ldg(r + i / 4);
-                    x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-                }
-                o[i / 4] = x;
-            }
-        } else {
-            uint4* oh = reinterpret_cast<uint4*>(g.out_hi + row_off + c0);
-            uint4* ol = g.out_lo ? reinterpret_cast<uint4*>(g.out_lo + row_off + c0) : nullptr;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                __nv_bfloat162 h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float a = v[i + 2 * j], b = v[i + 2 * j + 1];
-                    h[j] = __floats2bfloat162_rn(a, b);
-                    l[j] = __floats2bfloat162_rn(a - __low2float(h[j]), b - __high2float(h[j]));
-                }
-                oh[i / 8] = *reinterpret_cast<uint4*>(h);
-                if (ol) ol[i / 8] = *reinterpret_cast<uint4*>(l);
-            }
-        }
-        }
+        epilogue_store32<EPI>(g, v, row_ok, row_off + c0, n0 + c0);  // no early exit before this: tcgen05.ld is warp-wide
         __syncwarp();
     }
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// ---- persistent variant -------------------------------------------------------------------------------------------
+// One CTA per SM walks the output tiles (tile = blockIdx.x + i * gridDim.x, N fastest so the CTAs of a wave share
+// A row blocks and all of W in L2).  Three roles, three pipelines:
+//   * warp 0 / lane 0 -- TMA producer, a kStages-deep ring that runs ahead ACROSS tiles (the next tile's first K blocks
+//                        load while the current tile's last MMAs and epilogue run);
+//   * warp 1 / lane 0 -- MMA issuer; the fp32 accumulator is double buffered in TMEM (2 x BLOCK_N columns), so tile
+//                        t+1's main loop overlaps tile t's epilogue (tmem_full / tmem_empty mbarriers);
+//   * warps 2..9      -- epilogue: warp w reads TMEM lane quadrant w % 4 (the hardware's per-warp lane window) and
+//                        column half (w - 2) / 4 of the tile.
+// The one-tile-per-CTA kernel above pays TMEM allocation, barrier set-up, a cold TMA pipeline and a serial epilogue per
+// tile; here they are paid once per SM.  192 KB of operand ring per SM (6 x 32 KB or 4 x 48 KB).
+constexpr int kPersistEpiWarps = 8;
+constexpr int kPersistThreads = 64 + 32 * kPersistEpiWarps;
+
+template <int BLOCK_N>
+struct PersistSmem {
+    static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kBarOff = kStages * kStage;
+    static constexpr int kTotal = kBarOff + 256 + 1024;
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
+                          const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo,
+                          const GemmArgs g) {
+    using S = PersistSmem<BLOCK_N>;
+    constexpr int kStages = S::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+    uint64_t* empty = full + kStages;
+    uint64_t* tmem_full = empty + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = g.N / BLOCK_N, m_tiles = (g.M + kBlockM - 1) / kBlockM;
+    const int tiles = n_tiles * m_tiles;
+    const int per_tile = (g.K / kBlockK) * g.nterms;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&ta_hi);
+        tma_prefetch_desc(&tb_hi);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], kPersistEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            int it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * BLOCK_N;
+                for (int k = 0; k < per_tile; ++k, ++it) {
+                    const int s = it % kStages, ph = (it / kStages) & 1;
+                    const int kb = k / g.nterms, term = k - kb * g.nterms;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], S::kStage);
+                    uint8_t* sa = smem + s * S::kStage;
+                    tma_load_2d(sa, term == 2 ? &ta_lo : &ta_hi, &full[s], kb * kBlockK, m0);
+                    tma_load_2d(sa + S::kABytes, term == 1 ? &tb_lo : &tb_hi, &full[s], kb * kBlockK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
+                const int buf = t & 1;
+                mbar_wait(&tmem_empty[buf], ((t >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+                tc_fence_after_sync();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BLOCK_N);
+                for (int k = 0; k < per_tile; ++k, ++it) {
+                    const int s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t sa = smem_u32(smem + s * S::kStage);
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + S::kABytes);
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / 16; ++kk)
+                        umma_bf16(acc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue warps ----------------
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        constexpr int kCols = BLOCK_N / 2;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
+            const int buf = t & 1;
+            const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * BLOCK_N + half * kCols;
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < g.M;
+            const size_t row_off = (size_t)row * g.N + n0;
+            mbar_wait(&tmem_full[buf], (t >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N + half * kCols);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kCols; c0 += 32) {
+                float v[32];
+                tmem_ld32(acc + (uint32_t)c0, v);
+                if (c0 + 32 == kCols) {  // last read of this accumulator: hand it back before the stores
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                }
+                epilogue_store32<EPI>(g, v, row_ok, row_off + c0, n0 + c0);
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
@@ -246,6 +405,43 @@ static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
     return ASP_OK;
 }
 
+template <int BLOCK_N, int EPI>
+static int launch_gemm_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                                  const CUtensorMap& tb_lo, const GemmArgs& g, cudaStream_t stream) {
+    using S = PersistSmem<BLOCK_N>;
+    static thread_local int attr_dev = -1, sms = 0;
+    int dev = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        ASP_CUDA(cudaFuncSetAttribute(gemm_tn_persistent_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      S::kTotal));
+        ASP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_dev = dev;
+    }
+    const int tiles = (g.N / BLOCK_N) * ((g.M + kBlockM - 1) / kBlockM);
+    gemm_tn_persistent_kernel<BLOCK_N, EPI><<<std::min(tiles, sms), kPersistThreads, S::kTotal, stream>>>(ta_hi, ta_lo, tb_hi,
+                                                                                                       tb_lo, g);
+    ASP_LAUNCH_CHECK("gemm_tn_persistent_kernel");
+    return ASP_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                               const CUtensorMap& tb_lo, const GemmArgs& g, int epilogue, cudaStream_t stream) {
+    switch (epilogue) {
+        case EPI_BF16: return launch_gemm_persistent<BLOCK_N, EPI_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_GELU_BF16: return launch_gemm_persistent<BLOCK_N, EPI_GELU_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_RESID_F32: return launch_gemm_persistent<BLOCK_N, EPI_RESID_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_F32: return launch_gemm_persistent<BLOCK_N, EPI_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+    }
+    set_error("gemm: unknown epilogue %d", epilogue);
+    return ASP_ERR_INVALID;
+}
+
+// asp_set_option("gemm_kernel"): 0 one tile per CTA, 1 persistent with 128-wide tiles, 2 persistent with 256-wide tiles
+// where N allows, 3 (default) persistent, tile width picked per shape.
+int g_gemm_kernel = 3;
+
 int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                  const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo, float* out_f32,
                  cudaStream_t stream) {
@@ -260,11 +456,25 @@ int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const voi
     if (epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16) ASP_REQUIRE(out_hi, "gemm: bf16 epilogue needs out_hi");
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
+    // tile width of the persistent kernel: 256 halves the A re-reads, but only pays while the 256-wide tiles still fill
+    // the machine for three waves or more (measured on the BERT-base shapes: tools/gemm_bench.py)
+    int bn = BN;
+    if (g_gemm_kernel >= 2 && (N % 256) == 0) {
+        int dev = 0, sms = 148;
+        ASP_CUDA(cudaGetDevice(&dev));
+        ASP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const long m_tiles = (M + kBlockM - 1) / kBlockM;
+        if (g_gemm_kernel == 2 || m_tiles * (N / 256) >= 3L * sms) bn = 256;
+    }
     if ((rc = make_tmap_bf16(&ta_hi, a_hi, M, K, kBlockM))) return rc;
-    if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, BN))) return rc;
+    if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, bn))) return rc;
     if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;
-    if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, BN))) return rc;
+    if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, bn))) return rc;
     GemmArgs g{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32};
+    if (g_gemm_kernel >= 1) {
+        if (bn == 256) return dispatch_persistent<256>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+        return dispatch_persistent<128>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+    }
     switch (epilogue) {
         case EPI_BF16: return launch_gemm<BN, EPI_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
         case EPI_GELU_BF16: return launch_gemm<BN, EPI_GELU_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
