@@ -71,6 +71,11 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_gemm_kernel = value;
         return ASP_OK;
     }
+    if (strcmp(key, "gemm_cluster") == 0) {
+        ASP_REQUIRE(value == 1 || value == 2 || value == 4, "asp_set_option: gemm_cluster must be 1, 2 or 4");
+        asp::g_gemm_cluster = value;
+        return ASP_OK;
+    }
     asp::set_error("asp_set_option: unknown key '%s'", key);
     return ASP_ERR_INVALID;
 }

@@ -190,6 +190,86 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
     if (warp == 2) tmem_dealloc(tmem_base, BLOCK_N);
 }
 
+// Coalesced variant for the persistent kernel.  TMEM hands every lane one ROW of the tile, so storing straight from
+// registers makes each warp-wide 16-byte store touch 32 different lines with a quarter sector each; at 64 KB per tile
+// that alone took twice as long as the tile's main loop.  Here the 32x32 chunk is turned through a per-warp staging
+// buffer (80-byte row pitch: 64 data bytes + 16 pad, conflict-free 16-byte writes) so that afterwards four adjacent
+// lanes own 64 consecutive bytes of one row: every store instruction writes whole sectors of 8 rows, and the residual
+// is read the same way.  bf16 outputs pass the chunk through once per half (hi, lo); fp32 outputs in two 16-column
+// halves.
+constexpr int kEpiPitch = 80;
+constexpr int kEpiBytesPerWarp = 32 * kEpiPitch;
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float (&v)[32], uint8_t* stage, int lane, int row0,
+                                                        int col) {
+    if (g.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col + i));
+            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
+    }
+    if (EPI == EPI_GELU_BF16) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    const int r_sub = lane >> 2, c_sub = lane & 3;
+    uint8_t* wr = stage + lane * kEpiPitch;
+    const uint8_t* rd = stage + r_sub * kEpiPitch + c_sub * 16;
+    if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(wr + 16 * j) =
+                    make_float4(v[16 * h + 4 * j], v[16 * h + 4 * j + 1], v[16 * h + 4 * j + 2], v[16 * h + 4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = row0 + 8 * i + r_sub;
+                float4 x = *reinterpret_cast<const float4*>(rd + 8 * i * kEpiPitch);
+                if (row < g.M) {
+                    const size_t off = (size_t)row * g.N + col + 16 * h + 4 * c_sub;
+                    if (EPI == EPI_RESID_F32) {
+                        const float4 rr = __ldg(reinterpret_cast<const float4*>(g.residual + off));
+                        x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                    }
+                    *reinterpret_cast<float4*>(g.out_f32 + off) = x;
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float a = v[2 * j], b = v[2 * j + 1];
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __low2float(h2), b - __high2float(h2));
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            __nv_bfloat16* out = pass == 0 ? g.out_hi : g.out_lo;
+            if (out == nullptr) break;  // warp-uniform
+            const uint32_t(&w)[16] = pass == 0 ? hi : lo;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(wr + 16 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = row0 + 8 * i + r_sub;
+                const uint4 x = *reinterpret_cast<const uint4*>(rd + 8 * i * kEpiPitch);
+                if (row < g.M) *reinterpret_cast<uint4*>(out + (size_t)row * g.N + col + 8 * c_sub) = x;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ---- persistent variant -------------------------------------------------------------------------------------------
 // One CTA per SM walks the output tiles (tile = blockIdx.x + i * gridDim.x, N fastest so the CTAs of a wave share
 // A row blocks and all of W in L2).  Three roles, three pipelines:
@@ -211,10 +291,11 @@ struct PersistSmem {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStage = kABytes + kBBytes;
     static constexpr int kBarOff = kStages * kStage;
-    static constexpr int kTotal = kBarOff + 256 + 1024;
+    static constexpr int kEpiOff = kBarOff + 256;  // per-warp staging buffers of the epilogue
+    static constexpr int kTotal = kEpiOff + kPersistEpiWarps * kEpiBytesPerWarp + 1024;
 };
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CL>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
                           const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo,
@@ -230,8 +311,15 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CL > 1: a cluster of CL CTAs works on CL vertically adjacent tiles (same W tile, CL different A row blocks); each
+    // CTA fetches 1/CL of the W tile and multicasts it to the whole cluster, so W costs one L2 read per cluster.  A
+    // stage may only be refilled once EVERY CTA's MMAs have consumed it: the release commit is multicast too.
+    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int group = blockIdx.x / CL, groups = gridDim.x / CL;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    constexpr int kSliceRows = BLOCK_N / CL;
     const int n_tiles = g.N / BLOCK_N, m_tiles = (g.M + kBlockM - 1) / kBlockM;
-    const int tiles = n_tiles * m_tiles;
+    const int tiles = n_tiles * ((m_tiles + CL - 1) / CL);  // per cluster
     const int per_tile = (g.K / kBlockK) * g.nterms;
 
     if (threadIdx.x == 0) {
@@ -239,7 +327,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
         tma_prefetch_desc(&tb_hi);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
@@ -250,6 +338,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
     if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer multicasts into them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -257,16 +346,20 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             int it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * BLOCK_N;
+            for (int tile = group; tile < tiles; tile += groups) {
+                const int m0 = ((tile / n_tiles) * CL + rank) * kBlockM, n0 = (tile % n_tiles) * BLOCK_N;
                 for (int k = 0; k < per_tile; ++k, ++it) {
                     const int s = it % kStages, ph = (it / kStages) & 1;
                     const int kb = k / g.nterms, term = k - kb * g.nterms;
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], S::kStage);
                     uint8_t* sa = smem + s * S::kStage;
-                    tma_load_2d(sa, term == 2 ? &ta_lo : &ta_hi, &full[s], kb * kBlockK, m0);
-                    tma_load_2d(sa + S::kABytes, term == 1 ? &tb_lo : &tb_hi, &full[s], kb * kBlockK, n0);
+                    tma_load_2d(sa, term == 2 ? &ta_lo : &ta_hi, &full[s], kb * kBlockK, m0);  // rows past M read as zero
+                    if (CL == 1)
+                        tma_load_2d(sa + S::kABytes, term == 1 ? &tb_lo : &tb_hi, &full[s], kb * kBlockK, n0);
+                    else
+                        tma_load_2d_multicast(sa + S::kABytes + rank * (kSliceRows * kBlockK * 2), term == 1 ? &tb_lo : &tb_hi,
+                                              &full[s], kb * kBlockK, n0 + rank * kSliceRows, kMask);
                 }
             }
         }
@@ -275,7 +368,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
             // ---------------- MMA issuer ----------------
             constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
             int it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
+            for (int tile = group; tile < tiles; tile += groups, ++t) {
                 const int buf = t & 1;
                 mbar_wait(&tmem_empty[buf], ((t >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
                 tc_fence_after_sync();
@@ -289,7 +382,10 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
 #pragma unroll
                     for (int kk = 0; kk < kBlockK / 16; ++kk)
                         umma_bf16(acc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
-                    umma_commit(&empty[s]);
+                    if (CL == 1)
+                        umma_commit(&empty[s]);
+                    else
+                        umma_commit_multicast(&empty[s], kMask);
                 }
                 umma_commit(&tmem_full[buf]);
             }
@@ -298,32 +394,38 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
         // ---------------- epilogue warps ----------------
         const int quad = warp & 3, half = (warp - 2) >> 2;
         constexpr int kCols = BLOCK_N / 2;
+        uint8_t* stage = smem + S::kEpiOff + (warp - 2) * kEpiBytesPerWarp;
         int t = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++t) {
+        for (int tile = group; tile < tiles; tile += groups, ++t) {
             const int buf = t & 1;
-            const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * BLOCK_N + half * kCols;
-            const int row = m0 + quad * 32 + lane;
-            const bool row_ok = row < g.M;
-            const size_t row_off = (size_t)row * g.N + n0;
+            const int row0 = ((tile / n_tiles) * CL + rank) * kBlockM + quad * 32;
+            const int n0 = (tile % n_tiles) * BLOCK_N + half * kCols;
             mbar_wait(&tmem_full[buf], (t >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N + half * kCols);
+            // two chunks per round, the second one's TMEM load in flight under the first one's stores
+            float va[32], vb[32];
+            tmem_ld32_issue(acc, va);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kCols; c0 += 32) {
-                float v[32];
-                tmem_ld32(acc + (uint32_t)c0, v);
-                if (c0 + 32 == kCols) {  // last read of this accumulator: hand it back before the stores
+            for (int c0 = 0; c0 < kCols; c0 += 64) {
+                tmem_ld32_wait(va);
+                tmem_ld32_issue(acc + (uint32_t)(c0 + 32), vb);
+                epilogue_store32_staged<EPI>(g, va, stage, lane, row0, n0 + c0);
+                tmem_ld32_wait(vb);
+                if (c0 + 64 < kCols) {
+                    tmem_ld32_issue(acc + (uint32_t)(c0 + 64), va);
+                } else {  // last read of this accumulator: hand it back before the stores
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[buf]);
                 }
-                epilogue_store32<EPI>(g, v, row_ok, row_off + c0, n0 + c0);
-                __syncwarp();
+                epilogue_store32_staged<EPI>(g, vb, stage, lane, row0, n0 + c0 + 32);
             }
         }
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still write its shared memory or barriers
     if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 
@@ -405,34 +507,55 @@ static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
     return ASP_OK;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int CL>
 static int launch_gemm_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                                   const CUtensorMap& tb_lo, const GemmArgs& g, cudaStream_t stream) {
     using S = PersistSmem<BLOCK_N>;
-    static thread_local int attr_dev = -1, sms = 0;
+    static thread_local int attr_dev = -1, groups_max = 0;
     int dev = 0;
     ASP_CUDA(cudaGetDevice(&dev));
+    auto kernel = gemm_tn_persistent_kernel<BLOCK_N, EPI, CL>;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kPersistThreads);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
     if (attr_dev != dev) {
-        ASP_CUDA(cudaFuncSetAttribute(gemm_tn_persistent_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      S::kTotal));
+        int sms = 0;
+        ASP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         ASP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        groups_max = sms / CL;
+        if (CL > 1) {  // clusters cannot straddle a GPC: ask how many fit at once
+            cfg.gridDim = dim3(sms / CL * CL);
+            int n = 0;
+            ASP_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+            ASP_REQUIRE(n >= 1, "gemm: a cluster of %d CTAs does not fit on this device", CL);
+            groups_max = std::min(groups_max, n);
+        }
         attr_dev = dev;
     }
-    const int tiles = (g.N / BLOCK_N) * ((g.M + kBlockM - 1) / kBlockM);
-    gemm_tn_persistent_kernel<BLOCK_N, EPI><<<std::min(tiles, sms), kPersistThreads, S::kTotal, stream>>>(ta_hi, ta_lo, tb_hi,
-                                                                                                       tb_lo, g);
+    const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
+    const int tiles = (g.N / BLOCK_N) * ((m_tiles + CL - 1) / CL);
+    cfg.gridDim = dim3(CL * std::min(tiles, groups_max));
+    ASP_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, g));
     ASP_LAUNCH_CHECK("gemm_tn_persistent_kernel");
     return ASP_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CL>
 static int dispatch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                                const CUtensorMap& tb_lo, const GemmArgs& g, int epilogue, cudaStream_t stream) {
     switch (epilogue) {
-        case EPI_BF16: return launch_gemm_persistent<BLOCK_N, EPI_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
-        case EPI_GELU_BF16: return launch_gemm_persistent<BLOCK_N, EPI_GELU_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
-        case EPI_RESID_F32: return launch_gemm_persistent<BLOCK_N, EPI_RESID_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
-        case EPI_F32: return launch_gemm_persistent<BLOCK_N, EPI_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_BF16: return launch_gemm_persistent<BLOCK_N, EPI_BF16, CL>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_GELU_BF16: return launch_gemm_persistent<BLOCK_N, EPI_GELU_BF16, CL>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_RESID_F32: return launch_gemm_persistent<BLOCK_N, EPI_RESID_F32, CL>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_F32: return launch_gemm_persistent<BLOCK_N, EPI_F32, CL>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
     }
     set_error("gemm: unknown epilogue %d", epilogue);
     return ASP_ERR_INVALID;
@@ -440,7 +563,9 @@ static int dispatch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_l
 
 // asp_set_option("gemm_kernel"): 0 one tile per CTA, 1 persistent with 128-wide tiles, 2 persistent with 256-wide tiles
 // where N allows, 3 (default) persistent, tile width picked per shape.
+// asp_set_option("gemm_cluster"): 1, 2 or 4 CTAs per cluster sharing each W tile by TMA multicast (persistent kernels).
 int g_gemm_kernel = 3;
+int g_gemm_cluster = 1;
 
 int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                  const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo, float* out_f32,
@@ -456,24 +581,36 @@ int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const voi
     if (epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16) ASP_REQUIRE(out_hi, "gemm: bf16 epilogue needs out_hi");
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
-    // tile width of the persistent kernel: 256 halves the A re-reads, but only pays while the 256-wide tiles still fill
-    // the machine for three waves or more (measured on the BERT-base shapes: tools/gemm_bench.py)
+    // Tile width of the persistent kernel.  A 128x256 tile needs 48 KB of operands per 4 MMAs where two 128x128 tiles
+    // need 64 KB, and the operand feed (not the tensor pipe) is what bounds the 128-wide main loop (547 vs 690 clk per K
+    // block of twice the work, tools/gemm_bench.py).  It pays once the wide tiles still fill about one wave; the fp32 +
+    // residual epilogue is twice as long per tile, so those shapes want three waves unless the main loop is the 3-pass
+    // bf16x3 one.
     int bn = BN;
     if (g_gemm_kernel >= 2 && (N % 256) == 0) {
         int dev = 0, sms = 148;
         ASP_CUDA(cudaGetDevice(&dev));
         ASP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const long m_tiles = (M + kBlockM - 1) / kBlockM;
-        if (g_gemm_kernel == 2 || m_tiles * (N / 256) >= 3L * sms) bn = 256;
+        const long tiles256 = (long)((M + kBlockM - 1) / kBlockM) * (N / 256);
+        const bool bf16_out = epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16;
+        if (g_gemm_kernel == 2 || (10 * tiles256 >= 9L * sms && (bf16_out || a_lo != nullptr || tiles256 >= 3L * sms))) bn = 256;
     }
     if ((rc = make_tmap_bf16(&ta_hi, a_hi, M, K, kBlockM))) return rc;
-    if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, bn))) return rc;
+    const int w_box = g_gemm_kernel >= 1 ? bn / g_gemm_cluster : bn;  // each CTA of a cluster fetches its slice of the W tile
+    if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, w_box))) return rc;
     if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;
-    if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, bn))) return rc;
+    if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, w_box))) return rc;
     GemmArgs g{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32};
     if (g_gemm_kernel >= 1) {
-        if (bn == 256) return dispatch_persistent<256>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
-        return dispatch_persistent<128>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+        const int cl = g_gemm_cluster;
+        if (bn == 256) {
+            if (cl == 4) return dispatch_persistent<256, 4>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+            if (cl == 2) return dispatch_persistent<256, 2>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+            return dispatch_persistent<256, 1>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+        }
+        if (cl == 4) return dispatch_persistent<128, 4>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+        if (cl == 2) return dispatch_persistent<128, 2>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
+        return dispatch_persistent<128, 1>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
     }
     switch (epilogue) {
         case EPI_BF16: return launch_gemm<BN, EPI_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);

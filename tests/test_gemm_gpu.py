@@ -82,3 +82,38 @@ def test_gemm_bf16x3_is_fp32_equivalent(M, N, K):
     rel1 = ((out1.double() - ref).abs() / scale).max().item()
     assert rel <= 3e-5, f"bf16x3 rel err {rel}"
     assert rel1 > 10 * rel, f"plain bf16 ({rel1}) should be far less accurate than bf16x3 ({rel})"
+
+
+@pytest.mark.parametrize("epi", [EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32])
+def test_gemm_kernel_variants_agree(epi):
+    """Every kernel choice (one tile per CTA, persistent 128- / 256-wide, 1/2/4-CTA clusters sharing W by TMA multicast)
+    runs the same K order into the same fp32 accumulator, so the results must agree to the last bit -- including the
+    ragged last row block (M = 1000) and the cluster ranks whose row block lies entirely past M."""
+    from aspire_b200 import _abi
+    M, N, K = 1000, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(23)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    a_hi, a_lo = _split(a)
+    w_hi, w_lo = _split(w)
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) if epi == EPI_RESID else None
+    try:
+        base = None
+        for mode, cluster in [(0, 1), (1, 1), (2, 1), (1, 2), (2, 2), (1, 4), (2, 4), (3, 1)]:
+            _abi.set_option("gemm_kernel", mode)
+            _abi.set_option("gemm_cluster", cluster)
+            for lo in (False, True):
+                out = _gemm(a_hi, a_lo if lo else None, w_hi, w_lo if lo else None, bias, resid, epi, want_lo=lo)
+                got = [t.clone() for t in out if t is not None]
+                key = (lo,)
+                if base is None:
+                    base = {}
+                if key not in base:
+                    base[key] = got
+                else:
+                    for x, y in zip(base[key], got):
+                        assert torch.equal(x, y), f"mode {mode} cluster {cluster} lo={lo} differs from the one-tile kernel"
+    finally:
+        _abi.set_option("gemm_kernel", 3)
+        _abi.set_option("gemm_cluster", 1)

@@ -18,12 +18,16 @@ def main():
     ap.add_argument("--tokens", type=int, nargs="+", default=[8192, 2048])
     ap.add_argument("--x3", action="store_true")
     ap.add_argument("--modes", type=int, nargs="+", default=[0, 1, 2, 3])
+    ap.add_argument("--shapes", nargs="+", default=None, help="custom shapes as N,K,epilogue (instead of the BERT set)")
+    ap.add_argument("--clusters", type=int, nargs="+", default=[1], help="CTAs per cluster sharing W by TMA multicast")
     ap.add_argument("--reps", type=int, default=8, help="timed repetitions (0: one checked launch only, for ncu)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(1)
     shapes = [("qkv", 2304, 768, EPI_BF16), ("attn_out", 768, 768, EPI_RESID), ("ffn1", 3072, 768, EPI_GELU),
               ("ffn2", 768, 3072, EPI_RESID)]
+    if a.shapes:
+        shapes = [(f"n{n}k{k}e{e}", n, k, e) for n, k, e in (map(int, x.split(",")) for x in a.shapes)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for M in a.tokens:
         for name, N, K, epi in shapes:
@@ -45,8 +49,9 @@ def main():
             elif epi == EPI_RESID:
                 ref = ref + resid.double()
             line = f"M={M:5d} {name:8s} N={N:4d} K={K:4d}"
-            for mode in a.modes:
+            for mode, cl in [(m, c) for m in a.modes for c in (a.clusters if m else [1])]:
                 _abi.set_option("gemm_kernel", mode)
+                _abi.set_option("gemm_cluster", cl)
 
                 def run():
                     _abi.check(_abi.lib().asp_gemm_bf16_tn(
@@ -60,7 +65,7 @@ def main():
                 got = (out_hi if epi in (EPI_BF16, EPI_GELU) else out_f).double()
                 err = ((got - ref).abs().max() / ref.abs().max()).item()
                 if a.reps == 0:
-                    line += f" | m{mode}: err {err:.1e}"
+                    line += f" | m{mode}c{cl}: err {err:.1e}"
                     continue
                 ts = []
                 for _ in range(a.reps):
@@ -71,9 +76,10 @@ def main():
                 ts.sort()
                 us = ts[len(ts) // 2]
                 tf = 2.0 * M * N * K * (3 if a.x3 else 1) / us / 1e6
-                line += f" | m{mode}: {us:7.1f} us {tf:6.0f} TF err {err:.1e}"
+                line += f" | m{mode}c{cl}: {us:6.1f} us {tf:5.0f} TF err {err:.0e}"
             print(line, flush=True)
     _abi.set_option("gemm_kernel", 3)
+    _abi.set_option("gemm_cluster", 1)
 
 
 if __name__ == "__main__":
