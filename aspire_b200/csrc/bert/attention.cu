@@ -1,8 +1,9 @@
 // K0 self-attention of the encoder: softmax(Q K^T / sqrt(64) + key-padding mask) V per (document, head).
 //
 // Replaces BertSelfAttention as reached from examples/ex_aspire_consent.py:72 (12 heads x 64, L <= 512, additive
-// mask that removes padded keys).  Flash-style: one CTA = 64 query rows of one (document, head); K/V tiles of 64 keys
-// are staged in shared memory, scores / probabilities never leave registers, online softmax in fp32.
+// mask that removes padded keys).  Flash-style: one CTA = 16 * QW query rows (QW = 4 warps) of one
+// (document, head); K/V tiles of 64 keys stream through a two-stage cp.async ring in shared memory (tile j+1 loads
+// while tile j is multiplied), scores / probabilities never leave registers, online softmax in fp32.
 // The two small contractions (64x64x64 per tile) run on mma.sync.m16n8k16 bf16 tensor-core fragments: at L <= 512
 // attention is ~3-6 % of the encoder FLOPs, the tcgen05 budget goes to the GEMMs (gemm.cu).
 // PRECISE ("bf16x3"): Q, K, V and P are carried as (hi, lo) bf16 pairs and every product is hi.hi + hi.lo + lo.hi,
@@ -13,7 +14,7 @@
 namespace asp {
 
 constexpr int kHeadDim = 64;
-constexpr int kAttnTile = 64;   // queries per CTA and keys per staged tile
+constexpr int kAttnTile = 64;   // keys per staged tile
 constexpr int kAttnLd = 72;     // bf16 row stride of the staged tiles (144 B: conflict-free fragment loads)
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -38,15 +39,28 @@ __device__ __forceinline__ void split_bf16(float a, float b, uint32_t& hi, uint3
     lo = pack_bf16(a - __low2float(h), b - __high2float(h));
 }
 
-template <bool PRECISE>
-__global__ void __launch_bounds__(128)
+// 16-byte global -> shared copy without a register round trip; src_bytes = 0 writes zeros (keys past the sequence).
+__device__ __forceinline__ void attn_cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+
+template <int NP>
+struct AttnSmem {
+    __nv_bfloat16 k[2][NP][kAttnTile][kAttnLd];
+    __nv_bfloat16 v[2][NP][kAttnTile][kAttnLd];
+};
+
+template <bool PRECISE, int QW>
+__global__ void __launch_bounds__(32 * QW)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo,
                  const int32_t* __restrict__ seq_lens, int L, int H, __nv_bfloat16* __restrict__ ctx_hi,
                  __nv_bfloat16* __restrict__ ctx_lo) {
     constexpr int NP = PRECISE ? 2 : 1;
-    __shared__ __align__(16) __nv_bfloat16 Ks[NP][kAttnTile][kAttnLd];
-    __shared__ __align__(16) __nv_bfloat16 Vs[NP][kAttnTile][kAttnLd];
-    const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kAttnTile;
+    extern __shared__ __align__(16) uint8_t attn_smem_raw[];
+    AttnSmem<NP>& sm = *reinterpret_cast<AttnSmem<NP>*>(attn_smem_raw);
+    const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * (16 * QW);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int kv_len = min(max(seq_lens[b], 1), L);
     const size_t ld = (size_t)3 * H;
@@ -73,17 +87,24 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     const float sc = 0.125f * kLog2e;  // 1/sqrt(64), base-2 exponent
 
-    for (int j0 = 0; j0 < kv_len; j0 += kAttnTile) {
-        __syncthreads();  // previous tile fully consumed
-        // stage K and V rows j0..j0+63 (128-bit loads; rows >= L are zero)
-        for (int e = threadIdx.x; e < NP * 2 * kAttnTile * 8; e += 128) {
+    // K and V rows j0..j0+63 of both halves into ring stage st (keys >= L are zero-filled, never read from memory)
+    auto stage_tile = [&](int j0, int st) {
+        for (int e = threadIdx.x; e < NP * 2 * kAttnTile * 8; e += 32 * QW) {
             const int c8 = e & 7, row = (e >> 3) & 63, which = (e >> 9) & 1, p = e >> 10;
             const int key = j0 + row;
-            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-            if (key < L) val = *reinterpret_cast<const uint4*>(base[p] + (size_t)key * ld + (which + 1) * H + c8 * 8);
-            *reinterpret_cast<uint4*>(which ? &Vs[p][row][c8 * 8] : &Ks[p][row][c8 * 8]) = val;
+            const __nv_bfloat16* src = (p ? base[NP - 1] : base[0]) + (size_t)min(key, L - 1) * ld + (which + 1) * H + c8 * 8;
+            attn_cp_async16(which ? &sm.v[st][p][row][c8 * 8] : &sm.k[st][p][row][c8 * 8], src, key < L ? 16u : 0u);
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_tile(0, 0);
+
+    for (int j0 = 0, st = 0; j0 < kv_len; j0 += kAttnTile, st ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // tile j0 is visible to every warp, and every warp is done with the stage refilled next
+        if (j0 + kAttnTile < kv_len) stage_tile(j0 + kAttnTile, st ^ 1);
+        const auto& Ks = sm.k[st];
+        const auto& Vs = sm.v[st];
 
         // ---- S = Q K^T ----
         float s[8][4];
@@ -192,18 +213,32 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
     }
 }
 
+template <bool PRECISE, int QW>
+static int attention_launch_as(const void* qkv_hi, const void* qkv_lo, const int32_t* seq_lens, int B, int L, int H, int heads,
+                               void* ctx_hi, void* ctx_lo, cudaStream_t stream) {
+    constexpr int kSmem = (int)sizeof(AttnSmem<PRECISE ? 2 : 1>);
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        ASP_CUDA(cudaFuncSetAttribute(attention_kernel<PRECISE, QW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_dev = dev;
+    }
+    dim3 grid((L + 16 * QW - 1) / (16 * QW), heads, B);
+    attention_kernel<PRECISE, QW><<<grid, 32 * QW, kSmem, stream>>>((const __nv_bfloat16*)qkv_hi, (const __nv_bfloat16*)qkv_lo,
+                                                                   seq_lens, L, H, (__nv_bfloat16*)ctx_hi,
+                                                                   (__nv_bfloat16*)ctx_lo);
+    ASP_LAUNCH_CHECK("attention_kernel");
+    return ASP_OK;
+}
+
 int attention_launch(const void* qkv_hi, const void* qkv_lo, const int32_t* seq_lens, int B, int L, int H, int heads,
                      void* ctx_hi, void* ctx_lo, cudaStream_t stream) {
     ASP_REQUIRE(H == heads * kHeadDim, "attention: head size must be 64 (hidden %d, heads %d)", H, heads);
-    dim3 grid((L + kAttnTile - 1) / kAttnTile, heads, B);
-    if (qkv_lo)
-        attention_kernel<true><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)qkv_hi, (const __nv_bfloat16*)qkv_lo, seq_lens, L,
-                                                         H, (__nv_bfloat16*)ctx_hi, (__nv_bfloat16*)ctx_lo);
-    else
-        attention_kernel<false><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)qkv_hi, nullptr, seq_lens, L, H,
-                                                          (__nv_bfloat16*)ctx_hi, nullptr);
-    ASP_LAUNCH_CHECK("attention_kernel");
-    return ASP_OK;
+    // (128 query rows per CTA -- QW = 8 -- halve the K/V staging per query but measured 1 % slower at B=32, L=256: two
+    // 8-warp CTAs per SM hide the softmax latency worse than four 4-warp ones.)
+    if (qkv_lo) return attention_launch_as<true, 4>(qkv_hi, qkv_lo, seq_lens, B, L, H, heads, ctx_hi, ctx_lo, stream);
+    return attention_launch_as<false, 4>(qkv_hi, nullptr, seq_lens, B, L, H, heads, ctx_hi, nullptr, stream);
 }
 
 }  // namespace asp

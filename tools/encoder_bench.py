@@ -31,6 +31,11 @@ def timeit(fn, iters=5, warm=2):
 
 def main():
     quick = "--quick" in sys.argv
+    for arg in sys.argv[1:]:  # developer switches: --opt key=value -> asp_set_option
+        if arg.startswith("--opt="):
+            from aspire_b200 import _abi
+            k, v = arg[6:].split("=")
+            _abi.set_option(k, int(v))
     model = seeded_bert(seed=0, num_hidden_layers=12)
     enc = B200BertEncoder(model)
     hf32 = model.cuda().float()
