@@ -71,6 +71,10 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_gemm_kernel = value;
         return ASP_OK;
     }
+    if (strcmp(key, "pdl") == 0) {  // developer switch: programmatic dependent launch between the encoder's kernels
+        asp::g_pdl = value != 0;
+        return ASP_OK;
+    }
     if (strcmp(key, "gemm_cluster") == 0) {
         ASP_REQUIRE(value == 1 || value == 2 || value == 4, "asp_set_option: gemm_cluster must be 1, 2 or 4");
         asp::g_gemm_cluster = value;

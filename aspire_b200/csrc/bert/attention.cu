@@ -60,6 +60,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
     constexpr int NP = PRECISE ? 2 : 1;
     extern __shared__ __align__(16) uint8_t attn_smem_raw[];
     AttnSmem<NP>& sm = *reinterpret_cast<AttnSmem<NP>*>(attn_smem_raw);
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * (16 * QW);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int kv_len = min(max(seq_lens[b], 1), L);
@@ -225,9 +227,8 @@ static int attention_launch_as(const void* qkv_hi, const void* qkv_lo, const int
         attr_dev = dev;
     }
     dim3 grid((L + 16 * QW - 1) / (16 * QW), heads, B);
-    attention_kernel<PRECISE, QW><<<grid, 32 * QW, kSmem, stream>>>((const __nv_bfloat16*)qkv_hi, (const __nv_bfloat16*)qkv_lo,
-                                                                   seq_lens, L, H, (__nv_bfloat16*)ctx_hi,
-                                                                   (__nv_bfloat16*)ctx_lo);
+    ASP_CUDA(launch_pdl(attention_kernel<PRECISE, QW>, grid, dim3(32 * QW), kSmem, stream, (const __nv_bfloat16*)qkv_hi,
+                        (const __nv_bfloat16*)qkv_lo, seq_lens, L, H, (__nv_bfloat16*)ctx_hi, (__nv_bfloat16*)ctx_lo));
     ASP_LAUNCH_CHECK("attention_kernel");
     return ASP_OK;
 }

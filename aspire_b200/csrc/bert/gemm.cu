@@ -341,6 +341,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
     if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer multicasts into them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();  // everything above overlapped the previous kernel's tail; from here on its outputs are read
 
     if (warp == 0) {
         if (lane == 0) {
@@ -516,7 +518,7 @@ static int launch_gemm_persistent(const CUtensorMap& ta_hi, const CUtensorMap& t
     ASP_CUDA(cudaGetDevice(&dev));
     auto kernel = gemm_tn_persistent_kernel<BLOCK_N, EPI, CL>;
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
@@ -524,8 +526,15 @@ static int launch_gemm_persistent(const CUtensorMap& ta_hi, const CUtensorMap& t
     cfg.blockDim = dim3(kPersistThreads);
     cfg.dynamicSmemBytes = S::kTotal;
     cfg.stream = stream;
+    int n_attr = 0;
+    if (CL > 1) ++n_attr;
+    if (g_pdl) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CL > 1 ? 1 : 0;
+    cfg.numAttrs = n_attr;
     if (attr_dev != dev) {
         int sms = 0;
         ASP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -566,6 +575,7 @@ static int dispatch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_l
 // asp_set_option("gemm_cluster"): 1, 2 or 4 CTAs per cluster sharing each W tile by TMA multicast (persistent kernels).
 int g_gemm_kernel = 3;
 int g_gemm_cluster = 1;
+int g_pdl = 1;
 
 int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                  const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo, float* out_f32,

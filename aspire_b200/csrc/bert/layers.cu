@@ -62,6 +62,8 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ typ
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
                 __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
     constexpr int H = 128 * VPL;
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= T) return;
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(128)
 ln_kernel(const float* in, int T, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* out_f32,
           __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
     constexpr int H = 128 * VPL;
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= T) return;
@@ -104,8 +108,8 @@ int embed_ln_launch(const int32_t* ids, const int32_t* type_ids, int T, int L, i
                     float eps, float* out_f32, void* out_hi, void* out_lo, cudaStream_t stream) {
     ASP_REQUIRE(H == 768, "encoder: hidden size %d not built (768 only)", H);
     const int wpb = 4, blocks = (T + wpb - 1) / wpb;
-    embed_ln_kernel<6><<<blocks, wpb * 32, 0, stream>>>(ids, type_ids, T, L, vocab, max_pos, word_emb, pos_emb, type_emb, gamma,
-                                                        beta, eps, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+    ASP_CUDA(launch_pdl(embed_ln_kernel<6>, dim3(blocks), dim3(wpb * 32), 0, stream, ids, type_ids, T, L, vocab, max_pos, word_emb,
+                        pos_emb, type_emb, gamma, beta, eps, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo));
     ASP_LAUNCH_CHECK("embed_ln_kernel");
     return ASP_OK;
 }
@@ -114,8 +118,8 @@ int ln_launch(const float* in, int T, int H, const float* gamma, const float* be
               void* out_lo, cudaStream_t stream) {
     ASP_REQUIRE(H == 768, "encoder: hidden size %d not built (768 only)", H);
     const int wpb = 4, blocks = (T + wpb - 1) / wpb;
-    ln_kernel<6><<<blocks, wpb * 32, 0, stream>>>(in, T, gamma, beta, eps, out_f32, (__nv_bfloat16*)out_hi,
-                                                  (__nv_bfloat16*)out_lo);
+    ASP_CUDA(launch_pdl(ln_kernel<6>, dim3(blocks), dim3(wpb * 32), 0, stream, in, T, gamma, beta, eps, out_f32,
+                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo));
     ASP_LAUNCH_CHECK("ln_kernel");
     return ASP_OK;
 }

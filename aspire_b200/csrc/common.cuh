@@ -34,6 +34,34 @@ void count_launch();  // every kernel launch of this library is counted (asp_lau
         ::asp::count_launch();                                               \
     } while (0)
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// The encoder is ~85 dependent kernels on one stream.  Launched with the programmatic-serialization attribute, kernel
+// n+1 is placed on the SMs while kernel n drains, runs its prologue (barrier set-up, TMEM allocation, descriptor
+// prefetch) and then blocks in pdl_wait() until kernel n has completed and its writes are visible.  Every kernel
+// launched through launch_pdl() MUST call pdl_wait() before its first access to global data another kernel writes or
+// reads; pdl_trigger() (all threads, at the top) lets the next kernel be placed as soon as every CTA of this one has
+// started.  A kernel that follows a plain launch simply starts after it, as usual.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+extern int g_pdl;  // asp_set_option("pdl"): 1 (default) on, 0 plain stream order
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int sm_count();
 extern int g_ot_kernel;  // asp_set_option("ot_kernel")
