@@ -126,15 +126,20 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
                     mma_bf16(s[n], qa[NP - 1][kk], b0, b1);   // lo . hi
                 }
             }
-        // ---- scale, mask padded keys, online softmax (rows g and g+8 of this warp's 16) ----
+        // ---- mask padded keys (last tile only), online softmax (rows g and g+8 of this warp's 16) ----
+        // The 1/sqrt(64) scale and the base-2 conversion ride in the exponent's FFMA: the running maximum is kept on
+        // the raw scores (the scale is positive), p = exp2(s * sc - m * sc).
+        if (j0 + kAttnTile > kv_len) {  // block-uniform
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                const int key = j0 + n * 8 + 2 * t;
+                if (key >= kv_len) s[n][0] = s[n][2] = -INFINITY;
+                if (key + 1 >= kv_len) s[n][1] = s[n][3] = -INFINITY;
+            }
+        }
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const int key = j0 + n * 8 + 2 * t;
-            s[n][0] = key < kv_len ? s[n][0] * sc : -INFINITY;
-            s[n][1] = key + 1 < kv_len ? s[n][1] * sc : -INFINITY;
-            s[n][2] = key < kv_len ? s[n][2] * sc : -INFINITY;
-            s[n][3] = key + 1 < kv_len ? s[n][3] * sc : -INFINITY;
             mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
             mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
         }
@@ -143,16 +148,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* 
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every tile holds >= 1 valid key
-        const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+        const float a0 = exp2f((m0 - mn0) * sc), a1 = exp2f((m1 - mn1) * sc);
         m0 = mn0;
         m1 = mn1;
+        const float ms0 = -mn0 * sc, ms1 = -mn1 * sc;
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            s[n][0] = exp2f(s[n][0] - mn0);
-            s[n][1] = exp2f(s[n][1] - mn0);
-            s[n][2] = exp2f(s[n][2] - mn1);
-            s[n][3] = exp2f(s[n][3] - mn1);
+            s[n][0] = exp2f(fmaf(s[n][0], sc, ms0));
+            s[n][1] = exp2f(fmaf(s[n][1], sc, ms0));
+            s[n][2] = exp2f(fmaf(s[n][2], sc, ms1));
+            s[n][3] = exp2f(fmaf(s[n][3], sc, ms1));
             sum0 += s[n][0] + s[n][1];
             sum1 += s[n][2] + s[n][3];
             o[n][0] *= a0; o[n][1] *= a0; o[n][2] *= a1; o[n][3] *= a1;

@@ -49,21 +49,28 @@ struct GemmSmem {
 };
 
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) -- the exact (erf) form HF BERT uses.  erf by Abramowitz & Stegun 7.1.26
-// (|error| <= 1.5e-7, i.e. at fp32 rounding level): one MUFU.RCP, one MUFU.EX2 and 14 FP32 ops per element, about half
-// of libdevice's branch-free erff; the epilogue of the FFN1 GEMM evaluates it 16k times per tile.
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-    const float r = p * t * e;  // 1 - erf(|x| / sqrt 2)
-    const float h = 0.5f * x;
-    return fmaf(fabsf(h), 1.0f - r, h);  // h (1 + sign(x) erf(|z|))
+// (|error| <= 1.5e-7, i.e. at fp32 rounding level; libdevice's branch-free erff costs about twice as much, and the
+// epilogue of the FFN1 GEMM evaluates it 16k-32k times per tile).  Two values at a time on the packed fp32 pipe
+// (FFMA2 / FMUL2 / FADD2): 13 packed instructions and 4 MUFU per pair; with the scalar form the FFN1 epilogue was
+// issue-bound (issue slots 49 % busy, tile time 1.25x the QKV GEMM's at equal main loops).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+    const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+    const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+    float2 t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+    float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+    p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+    p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+    p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+    const float2 w = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(w.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(w.y));
+    const float2 r = __fmul2_rn(__fmul2_rn(p, t), e);
+    const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+    const float2 one_minus_r = __fadd2_rn(make_float2(1.0f, 1.0f), make_float2(-r.x, -r.y));
+    return __ffma2_rn(make_float2(fabsf(h.x), fabsf(h.y)), one_minus_r, h);
 }
 
 // Epilogue of 32 consecutive columns of one output row: bias, GELU / residual, stores (hi and optional lo halves).
@@ -79,7 +86,11 @@ __device__ __forceinline__ void epilogue_store32(const GemmArgs& g, float (&v)[3
     if (!row_ok) return;
     if (EPI == EPI_GELU_BF16) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 32; i += 2) {
+            const float2 y = gelu_erf2(make_float2(v[i], v[i + 1]));
+            v[i] = y.x;
+            v[i + 1] = y.y;
+        }
     }
     if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
         float4* o = reinterpret_cast<float4*>(g.out_f32 + off);
@@ -212,7 +223,11 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
     }
     if (EPI == EPI_GELU_BF16) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 32; i += 2) {
+            const float2 y = gelu_erf2(make_float2(v[i], v[i + 1]));
+            v[i] = y.x;
+            v[i + 1] = y.y;
+        }
     }
     const int r_sub = lane >> 2, c_sub = lane & 3;
     uint8_t* wr = stage + lane * kEpiPitch;
