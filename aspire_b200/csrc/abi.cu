@@ -67,12 +67,17 @@ extern "C" int asp_set_option(const char* key, int value) {
         return ASP_OK;
     }
     if (strcmp(key, "gemm_kernel") == 0) {  // developer switch: see bert/gemm.cu
-        ASP_REQUIRE(value >= 0 && value <= 3, "asp_set_option: gemm_kernel must be 0..3");
+        ASP_REQUIRE(value >= 0 && value <= 4, "asp_set_option: gemm_kernel must be 0..4");
         asp::g_gemm_kernel = value;
         return ASP_OK;
     }
     if (strcmp(key, "pdl") == 0) {  // developer switch: programmatic dependent launch between the encoder's kernels
         asp::g_pdl = value != 0;
+        return ASP_OK;
+    }
+    if (strcmp(key, "gemm_pair") == 0) {
+        ASP_REQUIRE(value >= 0 && value <= 2, "asp_set_option: gemm_pair must be 0, 1 or 2");
+        asp::g_gemm_pair = value;
         return ASP_OK;
     }
     if (strcmp(key, "gemm_cluster") == 0) {

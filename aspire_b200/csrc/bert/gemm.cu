@@ -301,7 +301,8 @@ constexpr int kPersistThreads = 64 + 32 * kPersistEpiWarps;
 
 template <int BLOCK_N>
 struct PersistSmem {
-    static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;
+    static constexpr int kStages = BLOCK_N == 256 ? 4 : BLOCK_N == 192 ? 5 : 6;  // 4 x 48 KB, 5 x 40 KB, 6 x 32 KB
+    static constexpr int kTmemCols = BLOCK_N == 128 ? 256 : 512;                 // two accumulators, power of two
     static constexpr int kABytes = kBlockM * kBlockK * 2;
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStage = kABytes + kBBytes;
@@ -350,7 +351,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    if (warp == 1) tmem_alloc(tmem_slot, S::kTmemCols);
     tc_fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer multicasts into them
@@ -420,7 +421,159 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
             mbar_wait(&tmem_full[buf], (t >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N + half * kCols);
-            // two chunks per round, the second one's TMEM load in flight under the first one's stores
+            // two chunks per round, the second one's TMEM load in flight under the first one's stores; the accumulator is
+            // handed back to the MMA warp right after its last read (kCols = 64, 96 or 128)
+            auto release = [&]() {
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            };
+            float va[32], vb[32];
+            tmem_ld32_issue(acc, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kCols; c0 += 64) {
+                const bool second = c0 + 32 < kCols;  // warp-uniform
+                tmem_ld32_wait(va);
+                if (second)
+                    tmem_ld32_issue(acc + (uint32_t)(c0 + 32), vb);
+                else
+                    release();
+                epilogue_store32_staged<EPI>(g, va, stage, lane, row0, n0 + c0);
+                if (second) {
+                    tmem_ld32_wait(vb);
+                    if (c0 + 64 < kCols)
+                        tmem_ld32_issue(acc + (uint32_t)(c0 + 64), va);
+                    else
+                        release();
+                    epilogue_store32_staged<EPI>(g, vb, stage, lane, row0, n0 + c0 + 32);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still write its shared memory or barriers
+    if (warp == 1) tmem_dealloc(tmem_base, S::kTmemCols);
+}
+
+// ---- CTA-pair variant (cta_group::2) ---------------------------------------------------------------------------------
+// Same roles and pipelines as the persistent kernel, but two CTAs on the two SMs of a TPC share one 256 x BLOCK_N tile:
+// each loads its own 128 rows of A and only HALF of the W tile (BLOCK_N / 2 rows), the leader's MMA thread issues
+// M = 256 tcgen05.mma.cta_group::2 instructions that read both halves, and each CTA's TMEM receives its own 128
+// accumulator rows.  What this buys is bytes INTO each SM per MMA: 32 KB instead of 48 KB per K block at BLOCK_N = 256,
+// 24 KB instead of 32 KB at BLOCK_N = 128 -- the quantity that bounds the single-CTA kernel.
+template <int BLOCK_N>
+struct PairSmem {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kStages = (192 * 1024) / kStage;
+    static constexpr int kBarOff = kStages * kStage;
+    static constexpr int kEpiOff = kBarOff + 256;
+    static constexpr int kTotal = kEpiOff + kPersistEpiWarps * kEpiBytesPerWarp + 1024;
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_lo,
+                    const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_lo, const GemmArgs g) {
+    using S = PairSmem<BLOCK_N>;
+    constexpr int kStages = S::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);  // used in the leader only
+    uint64_t* empty = full + kStages;
+    uint64_t* tmem_full = empty + kStages;
+    uint64_t* tmem_empty = tmem_full + 2;  // used in the leader only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const bool leader = rank == 0;
+    const int group = blockIdx.x / 2, groups = gridDim.x / 2;
+    const int n_tiles = g.N / BLOCK_N, m_tiles = (g.M + kBlockM - 1) / kBlockM;
+    const int tiles = n_tiles * ((m_tiles + 1) / 2);  // per pair
+    const int per_tile = (g.K / kBlockK) * g.nterms;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&ta_hi);
+        tma_prefetch_desc(&tb_hi);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 2 * kPersistEpiWarps);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers exist before the pair-scoped allocation and any remote arrival
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * BLOCK_N);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer (both CTAs; bytes are counted on the leader's barrier) ----------------
+            int it = 0;
+            for (int tile = group; tile < tiles; tile += groups) {
+                const int m0 = ((tile / n_tiles) * 2 + rank) * kBlockM;
+                const int n0 = (tile % n_tiles) * BLOCK_N + rank * (BLOCK_N / 2);
+                for (int k = 0; k < per_tile; ++k, ++it) {
+                    const int s = it % kStages, ph = (it / kStages) & 1;
+                    const int kb = k / g.nterms, term = k - kb * g.nterms;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&full[s], 2 * S::kStage);
+                    uint8_t* sa = smem + s * S::kStage;
+                    const uint32_t leader_full = cluster_map_addr(&full[s], 0);
+                    tma_load_2d_pair(sa, term == 2 ? &ta_lo : &ta_hi, leader_full, kb * kBlockK, m0);
+                    tma_load_2d_pair(sa + S::kABytes, term == 1 ? &tb_lo : &tb_hi, leader_full, kb * kBlockK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ---------------- MMA issuer (leader only, for both CTAs) ----------------
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
+            int it = 0, t = 0;
+            for (int tile = group; tile < tiles; tile += groups, ++t) {
+                const int buf = t & 1;
+                mbar_wait(&tmem_empty[buf], ((t >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator
+                tc_fence_after_sync();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BLOCK_N);
+                for (int k = 0; k < per_tile; ++k, ++it) {
+                    const int s = it % kStages, ph = (it / kStages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after_sync();
+                    const uint32_t sa = smem_u32(smem + s * S::kStage);
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + S::kABytes);
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / 16; ++kk)
+                        umma_bf16_pair(acc, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+                    umma_commit_pair(&empty[s]);
+                }
+                umma_commit_pair(&tmem_full[buf]);
+            }
+        }
+    } else {
+        // ---------------- epilogue warps (both CTAs, own 128 rows) ----------------
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        constexpr int kCols = BLOCK_N / 2;
+        uint8_t* stage = smem + S::kEpiOff + (warp - 2) * kEpiBytesPerWarp;
+        int t = 0;
+        for (int tile = group; tile < tiles; tile += groups, ++t) {
+            const int buf = t & 1;
+            const int row0 = ((tile / n_tiles) * 2 + rank) * kBlockM + quad * 32;
+            const int n0 = (tile % n_tiles) * BLOCK_N + half * kCols;
+            mbar_wait(&tmem_full[buf], (t >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N + half * kCols);
             float va[32], vb[32];
             tmem_ld32_issue(acc, va);
 #pragma unroll 1
@@ -431,10 +584,10 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
                 tmem_ld32_wait(vb);
                 if (c0 + 64 < kCols) {
                     tmem_ld32_issue(acc + (uint32_t)(c0 + 64), va);
-                } else {  // last read of this accumulator: hand it back before the stores
+                } else {
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+                    if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0);  // the leader's barrier, from either CTA
                 }
                 epilogue_store32_staged<EPI>(g, vb, stage, lane, row0, n0 + c0 + 32);
             }
@@ -442,8 +595,8 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still write its shared memory or barriers
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other can still touch its memory or barriers
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 2 * BLOCK_N);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
@@ -585,11 +738,71 @@ static int dispatch_persistent(const CUtensorMap& ta_hi, const CUtensorMap& ta_l
     return ASP_ERR_INVALID;
 }
 
-// asp_set_option("gemm_kernel"): 0 one tile per CTA, 1 persistent with 128-wide tiles, 2 persistent with 256-wide tiles
-// where N allows, 3 (default) persistent, tile width picked per shape.
+template <int BLOCK_N, int EPI>
+static int launch_gemm_pair(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                            const CUtensorMap& tb_lo, const GemmArgs& g, cudaStream_t stream) {
+    using S = PairSmem<BLOCK_N>;
+    static thread_local int attr_dev = -1, pairs_max = 0;
+    int dev = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    auto kernel = gemm_tn_pair_kernel<BLOCK_N, EPI>;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    int n_attr = 1;
+    if (g_pdl) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    cfg.blockDim = dim3(kPersistThreads);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    if (attr_dev != dev) {
+        int sms = 0, n = 0;
+        ASP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        ASP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cfg.gridDim = dim3(sms / 2 * 2);
+        ASP_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+        ASP_REQUIRE(n >= 1, "gemm: a CTA pair does not fit on this device");
+        pairs_max = std::min(sms / 2, n);
+        attr_dev = dev;
+    }
+    const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
+    const int tiles = (g.N / BLOCK_N) * ((m_tiles + 1) / 2);
+    cfg.gridDim = dim3(2 * std::min(tiles, pairs_max));
+    ASP_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta_hi, ta_lo, tb_hi, tb_lo, g));
+    ASP_LAUNCH_CHECK("gemm_tn_pair_kernel");
+    return ASP_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_pair(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi, const CUtensorMap& tb_lo,
+                         const GemmArgs& g, int epilogue, cudaStream_t stream) {
+    switch (epilogue) {
+        case EPI_BF16: return launch_gemm_pair<BLOCK_N, EPI_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_GELU_BF16: return launch_gemm_pair<BLOCK_N, EPI_GELU_BF16>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_RESID_F32: return launch_gemm_pair<BLOCK_N, EPI_RESID_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+        case EPI_F32: return launch_gemm_pair<BLOCK_N, EPI_F32>(ta_hi, ta_lo, tb_hi, tb_lo, g, stream);
+    }
+    set_error("gemm: unknown epilogue %d", epilogue);
+    return ASP_ERR_INVALID;
+}
+
+// asp_set_option("gemm_kernel"): 0 one tile per CTA, 1 persistent with 128-wide tiles, 2 / 4 persistent with 256- / 192-wide
+// tiles where N allows, 3 (default) persistent, tile width picked per shape.
+// asp_set_option("gemm_pair"): 0 off, 1 CTA pairs (cta_group::2) with 128-wide pair tiles, 2 with 256-wide ones where N
+// allows.
 // asp_set_option("gemm_cluster"): 1, 2 or 4 CTAs per cluster sharing each W tile by TMA multicast (persistent kernels).
 int g_gemm_kernel = 3;
+constexpr int kCost192 = 520;  // (FFN2 - attention-output time at 192 columns) / (36 K blocks x 2 rounds)
 int g_gemm_cluster = 1;
+int g_gemm_pair = 0;
 int g_pdl = 1;
 
 int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
@@ -606,28 +819,50 @@ int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const voi
     if (epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16) ASP_REQUIRE(out_hi, "gemm: bf16 epilogue needs out_hi");
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     int rc;
-    // Tile width of the persistent kernel.  A 128x256 tile needs 48 KB of operands per 4 MMAs where two 128x128 tiles
-    // need 64 KB, and the operand feed (not the tensor pipe) is what bounds the 128-wide main loop (547 vs 690 clk per K
-    // block of twice the work, tools/gemm_bench.py).  It pays once the wide tiles still fill about one wave; the fp32 +
-    // residual epilogue is twice as long per tile, so those shapes want three waves unless the main loop is the 3-pass
-    // bf16x3 one.
+    // Tile width of the persistent kernel.  Measured main-loop cost per 64-wide K block (tools/gemm_bench.py, slope of
+    // time over K): 547 clk at 128 columns, 520 at 192, 690 at 256 -- the 256-wide loop runs at the tensor pipe's
+    // practical rate (1.7 PFLOP/s, what cuBLAS reaches on this part; CTA pairs add nothing to it), the 128-wide one at
+    // 62 % of that.  Pick the width that minimises rounds x cost + the last tile's exposed epilogue.
     int bn = BN;
-    if (g_gemm_kernel >= 2 && (N % 256) == 0) {
+    if (g_gemm_kernel == 2 && (N % 256) == 0) bn = 256;
+    if (g_gemm_kernel == 4 && (N % 192) == 0) bn = 192;
+    if (g_gemm_kernel == 3) {
         int dev = 0, sms = 148;
         ASP_CUDA(cudaGetDevice(&dev));
         ASP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        const long tiles256 = (long)((M + kBlockM - 1) / kBlockM) * (N / 256);
-        const bool bf16_out = epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16;
-        if (g_gemm_kernel == 2 || (10 * tiles256 >= 9L * sms && (bf16_out || a_lo != nullptr || tiles256 >= 3L * sms))) bn = 256;
+        const long m_tiles = (M + kBlockM - 1) / kBlockM, k_iters = (long)(K / kBlockK) * (a_lo ? 3 : 1);
+        const bool f32_out = epilogue == EPI_RESID_F32 || epilogue == EPI_F32;
+        long best = -1;
+        const int widths[3] = {128, 192, 256}, cost[3] = {547, kCost192, 690};
+        for (int i = 0; i < 3; ++i) {
+            if (N % widths[i]) continue;
+            const long tiles = m_tiles * (N / widths[i]), rounds = (tiles + sms - 1) / sms;
+            const long c = rounds * k_iters * cost[i] + (long)widths[i] * (f32_out ? 24 : 12);
+            if (best < 0 || c < best) {
+                best = c;
+                bn = widths[i];
+            }
+        }
+    }
+    if (g_gemm_pair && g_gemm_kernel >= 1) {
+        const int pbn = (g_gemm_pair == 2 && (N % 256) == 0) ? 256 : 128;
+        if ((rc = make_tmap_bf16(&ta_hi, a_hi, M, K, kBlockM))) return rc;
+        if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, pbn / 2))) return rc;
+        if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;
+        if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, pbn / 2))) return rc;
+        GemmArgs gp{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32};
+        return pbn == 256 ? dispatch_pair<256>(ta_hi, ta_lo, tb_hi, tb_lo, gp, epilogue, stream)
+                          : dispatch_pair<128>(ta_hi, ta_lo, tb_hi, tb_lo, gp, epilogue, stream);
     }
     if ((rc = make_tmap_bf16(&ta_hi, a_hi, M, K, kBlockM))) return rc;
-    const int w_box = g_gemm_kernel >= 1 ? bn / g_gemm_cluster : bn;  // each CTA of a cluster fetches its slice of the W tile
+    const int w_box = (g_gemm_kernel >= 1 && bn != 192) ? bn / g_gemm_cluster : bn;  // each CTA of a cluster fetches its slice of the W tile
     if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, w_box))) return rc;
     if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, w_box))) return rc;
     GemmArgs g{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32};
     if (g_gemm_kernel >= 1) {
-        const int cl = g_gemm_cluster;
+        const int cl = bn == 192 ? 1 : g_gemm_cluster;
+        if (bn == 192) return dispatch_persistent<192, 1>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
         if (bn == 256) {
             if (cl == 4) return dispatch_persistent<256, 4>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
             if (cl == 2) return dispatch_persistent<256, 2>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);

@@ -191,6 +191,55 @@ __device__ __forceinline__ void tmem_ld32_wait(float (&v)[32]) {
                  : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, execute one M=256 MMA ---------------
+// Each CTA holds its 128 rows of A and HALF of the B tile in its own shared memory and its 128 accumulator rows in its
+// own TMEM; the leader (even rank) issues the MMAs for both.  All pair-scoped instructions are collective over the pair.
+// shared::cluster address of the object at this CTA-relative address in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map_addr(const void* p, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(p)), "r"(rank));
+    return remote;
+}
+
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier at the same
+// offset (the leader's MMA thread waits for both halves of a stage on one barrier).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// Arrive on the mbarrier at this offset in BOTH CTAs of the pair once every MMA issued so far has completed.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// Arrive on the mbarrier at this offset in CTA `rank` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_map_addr(bar, rank)) : "memory");
+}
+
 // ---- TMEM as per-thread scratch (32x32b shape: thread t of warp w <-> TMEM lane 32*(w%4)+t, consecutive columns) ------
 // Registers -> TMEM, 4 consecutive columns of this thread's lane.  Complete (for this thread) after tmem_wait_st().
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float4& v) {

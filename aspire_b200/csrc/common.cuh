@@ -69,6 +69,7 @@ extern int g_ot_stagger; // asp_set_option("ot_stagger")
 extern int g_ot_fused_mode;  // asp_set_option("ot_fused_mode")
 extern int g_gemm_kernel;    // asp_set_option("gemm_kernel")
 extern int g_gemm_cluster;   // asp_set_option("gemm_cluster")
+extern int g_gemm_pair;      // asp_set_option("gemm_pair")
 
 // Epsilon schedule passed by value in kernel parameter space (uniform, read through the constant bank).
 struct EpsSched {

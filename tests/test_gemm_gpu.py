@@ -100,7 +100,7 @@ def test_gemm_kernel_variants_agree(epi):
     resid = torch.randn(M, N, device="cuda", generator=g) if epi == EPI_RESID else None
     try:
         base = None
-        for mode, cluster in [(0, 1), (1, 1), (2, 1), (1, 2), (2, 2), (1, 4), (2, 4), (3, 1)]:
+        for mode, cluster in [(0, 1), (1, 1), (2, 1), (4, 1), (1, 2), (2, 2), (1, 4), (2, 4), (3, 1)]:
             _abi.set_option("gemm_kernel", mode)
             _abi.set_option("gemm_cluster", cluster)
             for lo in (False, True):

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--modes", type=int, nargs="+", default=[0, 1, 2, 3])
     ap.add_argument("--shapes", nargs="+", default=None, help="custom shapes as N,K,epilogue (instead of the BERT set)")
     ap.add_argument("--clusters", type=int, nargs="+", default=[1], help="CTAs per cluster sharing W by TMA multicast")
+    ap.add_argument("--pairs", type=int, nargs="+", default=[0], help="CTA-pair kernel: 0 off, 1 128-wide, 2 256-wide")
     ap.add_argument("--reps", type=int, default=8, help="timed repetitions (0: one checked launch only, for ncu)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -49,9 +50,11 @@ def main():
             elif epi == EPI_RESID:
                 ref = ref + resid.double()
             line = f"M={M:5d} {name:8s} N={N:4d} K={K:4d}"
-            for mode, cl in [(m, c) for m in a.modes for c in (a.clusters if m else [1])]:
+            for mode, cl, pair in [(m, c, p) for m in a.modes for c in (a.clusters if m else [1])
+                                   for p in (a.pairs if m else [0])]:
                 _abi.set_option("gemm_kernel", mode)
                 _abi.set_option("gemm_cluster", cl)
+                _abi.set_option("gemm_pair", pair)
 
                 def run():
                     _abi.check(_abi.lib().asp_gemm_bf16_tn(
@@ -65,7 +68,7 @@ def main():
                 got = (out_hi if epi in (EPI_BF16, EPI_GELU) else out_f).double()
                 err = ((got - ref).abs().max() / ref.abs().max()).item()
                 if a.reps == 0:
-                    line += f" | m{mode}c{cl}: err {err:.1e}"
+                    line += f" | m{mode}c{cl}p{pair}: err {err:.1e}"
                     continue
                 ts = []
                 for _ in range(a.reps):
@@ -76,10 +79,11 @@ def main():
                 ts.sort()
                 us = ts[len(ts) // 2]
                 tf = 2.0 * M * N * K * (3 if a.x3 else 1) / us / 1e6
-                line += f" | m{mode}c{cl}: {us:6.1f} us {tf:5.0f} TF err {err:.0e}"
+                line += f" | m{mode}c{cl}p{pair}: {us:6.1f} us {tf:5.0f} TF err {err:.0e}"
             print(line, flush=True)
     _abi.set_option("gemm_kernel", 3)
     _abi.set_option("gemm_cluster", 1)
+    _abi.set_option("gemm_pair", 0)
 
 
 if __name__ == "__main__":
