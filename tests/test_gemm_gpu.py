@@ -86,7 +86,8 @@ def test_gemm_bf16x3_is_fp32_equivalent(M, N, K):
 
 @pytest.mark.parametrize("epi", [EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32])
 def test_gemm_kernel_variants_agree(epi):
-    """Every kernel choice (one tile per CTA, persistent 128- / 256-wide, 1/2/4-CTA clusters sharing W by TMA multicast)
+    """Every kernel choice (one tile per CTA, persistent 128- / 192- / 256-wide, 1/2/4-CTA clusters sharing W by TMA
+    multicast, CTA pairs on tcgen05 cta_group::2)
     runs the same K order into the same fp32 accumulator, so the results must agree to the last bit -- including the
     ragged last row block (M = 1000) and the cluster ranks whose row block lies entirely past M."""
     from aspire_b200 import _abi
@@ -100,9 +101,11 @@ def test_gemm_kernel_variants_agree(epi):
     resid = torch.randn(M, N, device="cuda", generator=g) if epi == EPI_RESID else None
     try:
         base = None
-        for mode, cluster in [(0, 1), (1, 1), (2, 1), (4, 1), (1, 2), (2, 2), (1, 4), (2, 4), (3, 1)]:
+        for mode, cluster, pair in [(0, 1, 0), (1, 1, 0), (2, 1, 0), (4, 1, 0), (1, 2, 0), (2, 2, 0), (1, 4, 0), (2, 4, 0),
+                                    (3, 1, 0), (3, 1, 1), (3, 1, 2)]:
             _abi.set_option("gemm_kernel", mode)
             _abi.set_option("gemm_cluster", cluster)
+            _abi.set_option("gemm_pair", pair)  # 1 / 2: CTA pairs (tcgen05 cta_group::2), 128- / 256-wide pair tiles
             for lo in (False, True):
                 out = _gemm(a_hi, a_lo if lo else None, w_hi, w_lo if lo else None, bias, resid, epi, want_lo=lo)
                 got = [t.clone() for t in out if t is not None]
@@ -113,7 +116,9 @@ def test_gemm_kernel_variants_agree(epi):
                     base[key] = got
                 else:
                     for x, y in zip(base[key], got):
-                        assert torch.equal(x, y), f"mode {mode} cluster {cluster} lo={lo} differs from the one-tile kernel"
+                        assert torch.equal(x, y), (f"mode {mode} cluster {cluster} pair {pair} lo={lo} differs from the "
+                                                   "one-tile kernel")
     finally:
         _abi.set_option("gemm_kernel", 3)
         _abi.set_option("gemm_cluster", 1)
+        _abi.set_option("gemm_pair", 0)
