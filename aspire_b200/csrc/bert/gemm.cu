@@ -4,6 +4,13 @@
 // (examples/ex_aspire_consent.py:72): Q/K/V, attention output, and the two feed-forward projections of each of the
 // 12 layers.  W keeps the PyTorch Linear layout [out_features, in_features], so both operands are K-major.
 //
+// Three kernels share the operand format, the epilogues and the results (bit-identical, tests/test_gemm_gpu.py):
+//   * gemm_tn_persistent_kernel -- the product path: one CTA per SM walks 128 x {128,192,256} tiles with a TMA ring that
+//     runs ahead across tiles, a double-buffered TMEM accumulator and 8 epilogue warps (optionally 2/4-CTA clusters that
+//     share W tiles by TMA multicast);
+//   * gemm_tn_pair_kernel       -- the same pipeline on CTA pairs (tcgen05 cta_group::2, M = 256 over two SMs);
+//   * gemm_tn_kernel            -- one tile per CTA, the round's first version, kept as the measured baseline:
+//
 // One CTA (128 threads) computes a 128 x BLOCK_N output tile:
 //   * warp 0 / lane 0  -- TMA producer: cp.async.bulk.tensor 128x64 (A) and BLOCK_Nx64 (W) bf16 boxes, 128B swizzle,
 //                         into a STAGES-deep shared-memory ring, completion on mbarriers (expect_tx);

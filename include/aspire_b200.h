@@ -44,7 +44,15 @@ const char* asp_last_error(void);
 int asp_sm_count(void);
 /* Kernels launched by this library since load (all threads); used by bench.py's gpu_launches. */
 long long asp_launch_count(void);
-/* Tuning/testing knobs.  "ot_kernel": 0 auto, 1 force warp-per-pair (never fuse), 2 force thread-per-pair. */
+/* Tuning/testing knobs (process-wide; the defaults are the product path).
+ *   "ot_kernel"     0 auto, 1 force warp-per-pair (never fuse), 2 force thread-per-pair
+ *   "ot_fused_mode" 1 Gram/Sinkhorn-warp fused kernel (default), 0 both phases per warp;  "ot_stagger" 1/0
+ *   "gemm_kernel"   encoder GEMM: 3 persistent kernel, tile width picked per shape (default); 1 / 4 / 2 force 128- /
+ *                   192- / 256-wide tiles; 0 one tile per CTA
+ *   "gemm_cluster"  1 (default), 2 or 4 CTAs per cluster sharing W tiles by TMA multicast
+ *   "gemm_pair"     0 (default) off, 1 / 2 CTA pairs (tcgen05 cta_group::2) with 128- / 256-wide pair tiles
+ *   "pdl"           1 (default) encoder kernels use programmatic dependent launch, 0 plain stream order
+ * Every setting computes bit-identical GEMM results (tests/test_gemm_gpu.py). */
 int asp_set_option(const char* key, int value);
 
 /* ---- K1: per-sentence token-span mean pooling -------------------------------------------------
