@@ -75,9 +75,16 @@ def lib():
     for name in declared_symbols():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
         if name not in ("asp_last_error", "asp_launch_count", "asp_ot_score_workspace_bytes", "asp_l2max_allpairs_workspace_bytes",
-                        "asp_bert_workspace_bytes"):
+                        "asp_bert_workspace_bytes", "asp_wordpiece_create", "asp_wordpiece_destroy"):
             fn.restype = ci
     L.asp_launch_count.restype = cll
+    L.asp_wordpiece_create.restype = vp
+    L.asp_wordpiece_create.argtypes = [vp, vp, ci, ci, ci, vp, ci]
+    L.asp_wordpiece_destroy.restype = None
+    L.asp_wordpiece_destroy.argtypes = [vp]
+    L.asp_wordpiece_encode.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
+    L.asp_abstracts_plan.argtypes = [vp, vp, ci, ci, vp, vp]
+    L.asp_abstracts_fill.argtypes = [vp, vp, vp, ci, ci, ci, ci, cll, ci, ci, vp, vp, vp, vp]
     L.asp_ot_score_workspace_bytes.restype = ctypes.c_size_t
     L.asp_l2max_allpairs_workspace_bytes.restype = ctypes.c_size_t
     L.asp_bert_workspace_bytes.restype = ctypes.c_size_t

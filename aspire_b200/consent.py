@@ -143,6 +143,146 @@ def prepare_abstracts_fast(batch_abs, pt_lm_tokenizer):
     return bert_batch, abs_lens, torch.from_numpy(span_arr)
 
 
+class NativeWordPiece:
+    """The library's multi-threaded BERT word-piece tokenizer (``asp_wordpiece_*``) configured from a Hugging Face fast
+    tokenizer.  Construction raises ``ValueError`` when the tokenizer is anything but the plain BERT pipeline the
+    reference loads (BertNormalizer with text cleaning -> BertPreTokenizer -> WordPiece with the ``##`` prefix, special
+    tokens matched verbatim), so callers can fall back to ``prepare_abstracts_fast``."""
+
+    def __init__(self, tokenizer, threads=None):
+        import json
+        import os
+        backend = getattr(tokenizer, "backend_tokenizer", None)
+        if backend is None:
+            raise ValueError("not a fast (tokenizers-backed) tokenizer")
+        cfg = json.loads(backend.to_str())
+        norm, pre, model = cfg.get("normalizer") or {}, cfg.get("pre_tokenizer") or {}, cfg.get("model") or {}
+        if norm.get("type") != "BertNormalizer" or not norm.get("clean_text", False):
+            raise ValueError("normalizer is not BertNormalizer(clean_text=True)")
+        if pre.get("type") != "BertPreTokenizer":
+            raise ValueError("pre-tokenizer is not BertPreTokenizer")
+        if model.get("type") != "WordPiece" or model.get("continuing_subword_prefix") != "##":
+            raise ValueError("model is not WordPiece with the '##' prefix")
+        if cfg.get("truncation") or cfg.get("padding"):
+            raise ValueError("tokenizer has truncation / padding enabled")
+        vocab = dict(model["vocab"])
+        specials = []
+        for tok in cfg.get("added_tokens", []):
+            if tok.get("single_word") or tok.get("lstrip") or tok.get("rstrip") or tok.get("normalized"):
+                raise ValueError(f"added token {tok.get('content')!r} uses matching options the native path lacks")
+            vocab.setdefault(tok["content"], tok["id"])
+            if vocab[tok["content"]] != tok["id"]:
+                raise ValueError(f"added token {tok['content']!r} has two ids")
+            specials.append(tok["id"])
+        by_id = [None] * (max(vocab.values()) + 1)
+        for t, i in vocab.items():
+            by_id[i] = t
+        encoded = [(t or "").encode("utf-8") for t in by_id]
+        offsets = np.zeros(len(encoded) + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in encoded], out=offsets[1:])
+        blob = b"".join(encoded)
+        special_ids = np.asarray(specials, dtype=np.int32)
+        self.max_chars = int(model.get("max_input_chars_per_word", 100))
+        self.threads = int(threads or min(16, os.cpu_count() or 1))
+        self.tokenizer = tokenizer
+        self._lib = _abi.lib()
+        self._handle = self._lib.asp_wordpiece_create(blob, offsets.ctypes.data, len(encoded), int(bool(norm.get("lowercase", True))),
+                                                      int(vocab[model["unk_token"]]), special_ids.ctypes.data, len(special_ids))
+        if not self._handle:
+            raise ValueError("asp_wordpiece_create: " + self._lib.asp_last_error().decode("utf8", "replace"))
+
+    def __del__(self):
+        if getattr(self, "_handle", None):
+            self._lib.asp_wordpiece_destroy(self._handle)
+            self._handle = None
+
+    def encode(self, sentences):
+        """list(str) -> (ids int32 [total], offsets int64 [n+1]); same ids as ``tokenizer(s, add_special_tokens=False)``.
+        Sentences with non-ASCII characters go through the Hugging Face tokenizer (they need the Unicode tables)."""
+        raw = [s.encode("utf-8") for s in sentences]
+        n = len(raw)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum(np.fromiter(map(len, raw), dtype=np.int64, count=n), out=offsets[1:])
+        ids = np.empty(max(int(offsets[-1]), 1), dtype=np.int32)
+        out_offsets = np.zeros(n + 1, dtype=np.int64)
+        fallback = np.zeros(max(n, 1), dtype=np.uint8)
+        _abi.check(self._lib.asp_wordpiece_encode(self._handle, b"".join(raw), offsets.ctypes.data, n, self.max_chars, self.threads,
+                                                  ids.ctypes.data, out_offsets.ctypes.data, fallback.ctypes.data),
+                   "asp_wordpiece_encode")
+        ids = ids[:out_offsets[-1]]
+        todo = np.flatnonzero(fallback[:n])
+        if len(todo):
+            extra = self.tokenizer([sentences[i] for i in todo], add_special_tokens=False, return_attention_mask=False,
+                                   return_token_type_ids=False)["input_ids"]
+            parts, prev = [], 0
+            for i, e in zip(todo, extra):  # the native pass left zero ids for these sentences: splice theirs in
+                parts.append(ids[prev:out_offsets[i]])
+                parts.append(np.asarray(e, dtype=np.int32))
+                prev = out_offsets[i]
+            parts.append(ids[prev:])
+            lens = np.diff(out_offsets)
+            lens[todo] = [len(e) for e in extra]
+            ids = np.concatenate(parts) if parts else ids
+            out_offsets = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(lens, out=out_offsets[1:])
+        return ids, out_offsets
+
+
+def native_wordpiece(tokenizer):
+    """The cached ``NativeWordPiece`` of a tokenizer, or None when the tokenizer is not the plain BERT pipeline."""
+    cached = getattr(tokenizer, "_asp_native_wordpiece", None)
+    if cached is None:
+        try:
+            cached = NativeWordPiece(tokenizer)
+        except (ValueError, KeyError, TypeError):
+            cached = False
+        try:
+            object.__setattr__(tokenizer, "_asp_native_wordpiece", cached)
+        except Exception:  # a tokenizer that refuses new attributes is simply probed again next time
+            pass
+    return cached or None
+
+
+def prepare_abstracts_native(batch_abs, pt_lm_tokenizer):
+    """``prepare_abstracts_fast`` with the word pieces, the 500-piece truncation, the [CLS]..[SEP] wrapping, the padding
+    and the span table all produced by the library's host code (``asp_wordpiece_encode`` / ``asp_abstracts_plan`` /
+    ``asp_abstracts_fill``; examples/ex_aspire_consent.py:107-212).  Same return value, bit for bit; falls back to
+    ``prepare_abstracts_fast`` for tokenizers the native path does not cover.
+
+    :return: (bert_batch, abs_lens: list(int), spans: int32 tensor [B, max(abs_lens), 2], (-1, -1) = no sentence)
+    """
+    wp = native_wordpiece(pt_lm_tokenizer)
+    if wp is None:
+        return prepare_abstracts_fast(batch_abs, pt_lm_tokenizer)
+    flat, doc_sents = [], np.empty(len(batch_abs), dtype=np.int32)
+    for d, ex in enumerate(batch_abs):
+        flat.append(ex['TITLE'] + ' [SEP] ')
+        flat.extend(ex['ABSTRACT'])
+        doc_sents[d] = 1 + len(ex['ABSTRACT'])
+    ids, offsets = wp.encode(flat)
+    L_, n_docs = _abi.lib(), len(batch_abs)
+    seq_lens = np.empty(max(n_docs, 1), dtype=np.int32)
+    abs_lens = np.empty(max(n_docs, 1), dtype=np.int32)
+    _abi.check(L_.asp_abstracts_plan(offsets.ctypes.data, doc_sents.ctypes.data, n_docs, MAX_WORDPIECES, seq_lens.ctypes.data,
+                                     abs_lens.ctypes.data), "asp_abstracts_plan")
+    seq_lens, abs_lens = seq_lens[:n_docs].tolist(), abs_lens[:n_docs].tolist()
+    for n in abs_lens:
+        assert (n > 0)
+    width, max_sents = max(seq_lens), max(abs_lens)
+    tok = torch.empty((n_docs, width), dtype=torch.int64)
+    seg = torch.empty((n_docs, width), dtype=torch.int64)
+    att = torch.empty((n_docs, width), dtype=torch.int64)
+    spans = torch.empty((n_docs, max_sents, 2), dtype=torch.int32)
+    ids = np.ascontiguousarray(ids)
+    _abi.check(L_.asp_abstracts_fill(ids.ctypes.data if len(ids) else None, offsets.ctypes.data, doc_sents.ctypes.data, n_docs,
+                                     MAX_WORDPIECES, int(pt_lm_tokenizer.cls_token_id), int(pt_lm_tokenizer.sep_token_id),
+                                     int(pt_lm_tokenizer.pad_token_id), width, max_sents, tok.data_ptr(), seg.data_ptr(),
+                                     att.data_ptr(), spans.data_ptr()), "asp_abstracts_fill")
+    bert_batch = {'tokid_tt': tok, 'seg_tt': seg, 'attnmask_tt': att, 'seq_lens': seq_lens}
+    return bert_batch, abs_lens, spans
+
+
 def spans_from_token_idxs(sent_tok_idxs, max_sents):
     """list[B][S][tokens] -> int32 [B, max_sents, 2] half-open (start, end); (-1,-1) for missing sentences."""
     B = len(sent_tok_idxs)

@@ -23,7 +23,7 @@ import os
 import numpy as np
 import torch
 
-from .consent import prepare_abstracts
+from .consent import prepare_abstracts_native
 from .similarity import SimilarityModel, caching_score, pack_pool
 
 
@@ -139,7 +139,7 @@ class CachingScoringModel:
         for s in range(0, len(missing), self.encode_batch_size):
             chunk = missing[s:s + self.encode_batch_size]
             docs = [{'TITLE': pid2abstract[p]['title'], 'ABSTRACT': pid2abstract[p]['abstract']} for p in chunk]
-            bert_batch, abs_lens, senttok = prepare_abstracts(batch_abs=docs, pt_lm_tokenizer=self.tokenizer)
+            bert_batch, abs_lens, senttok = prepare_abstracts_native(batch_abs=docs, pt_lm_tokenizer=self.tokenizer)
             reps = caching_encode(self.model, {'bert_batch': bert_batch, 'abs_lens': abs_lens, 'senttok_idxs': senttok})
             assert len(reps) == len(chunk)
             self.pid2model_reps.update(zip(chunk, reps))
@@ -264,22 +264,22 @@ def rank_pool_sent(root_path, reps_path, dataset, data_to_read='sent', score_typ
 
 def encode_stream(model, tokenizer, papers, batch_size=32, workers=2):
     """Encode a list of {'TITLE', 'ABSTRACT'} papers with the host preparation of batch n+1 (tokenisation, span table:
-    ``prepare_abstracts_fast``) running on worker threads while the GPU encodes batch n -- the Rust tokenizers release
-    the GIL, and at 5-10 k documents/s on the device the tokeniser is otherwise the bottleneck of
-    ``AspireModel.encode`` / ``caching_encode`` (utils/models.py:199-209, disent_models.py:344-371).
+    ``prepare_abstracts_native``, the library's multi-threaded word-piece front end, 50-100 k documents/s; the Hugging
+    Face tokenizer for anything it does not cover) running on worker threads while the GPU encodes batch n -- both
+    release the GIL, and at 15 k documents/s on the device the per-sentence Python protocol (0.6 k documents/s) would
+    otherwise bound ``AspireModel.encode`` / ``caching_encode`` (utils/models.py:199-209, disent_models.py:344-371).
 
     ``model``: an AspireConSent.  Yields one fp32 CPU tensor [num_sents, 768] per paper, in input order.
     """
     from concurrent.futures import ThreadPoolExecutor
-    from .consent import prepare_abstracts_fast
     chunks = [papers[s:s + batch_size] for s in range(0, len(papers), batch_size)]
     with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
-        pending = [pool.submit(prepare_abstracts_fast, c, tokenizer) for c in chunks[:workers + 1]]
+        pending = [pool.submit(prepare_abstracts_native, c, tokenizer) for c in chunks[:workers + 1]]
         for k in range(len(chunks)):
             bert_batch, abs_lens, spans = pending.pop(0).result()
             nxt = k + workers + 1
             if nxt < len(chunks):
-                pending.append(pool.submit(prepare_abstracts_fast, chunks[nxt], tokenizer))
+                pending.append(pool.submit(prepare_abstracts_native, chunks[nxt], tokenizer))
             with torch.no_grad():
                 _, reps = model.forward(bert_batch=bert_batch, abs_lens=abs_lens, sent_tok_idxs=spans)
             for i, n in enumerate(abs_lens):

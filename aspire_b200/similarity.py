@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from . import _abi
-from .consent import AspireConSent, prepare_abstracts
+from .consent import AspireConSent, prepare_abstracts, prepare_abstracts_native
 from .distances import (AllPairMaskedWasserstein, bbox_diameter, epsilon_schedule, l2max_scores, ot_scores,
                         rep_len_tup)
 
@@ -311,8 +311,10 @@ class AspireModel(SimilarityModel):
         return -ot_dist
 
     def encode(self, batch_papers: List[Dict]):
-        bert_batch, abs_lens, sent_token_idxs = prepare_abstracts(batch_abs=batch_papers,
-                                                                  pt_lm_tokenizer=self.tokenizer)
+        # same batch as prepare_abstracts (utils/models.py:200), built by the library's host code when the tokenizer is
+        # the plain BERT pipeline; the sentence spans arrive as the (start, end) table the pooling kernel consumes
+        bert_batch, abs_lens, sent_token_idxs = prepare_abstracts_native(batch_abs=batch_papers,
+                                                                         pt_lm_tokenizer=self.tokenizer)
         with torch.no_grad():
             _, batch_reps_sent = self.model.forward(bert_batch=bert_batch, abs_lens=abs_lens,
                                                     sent_tok_idxs=sent_token_idxs)

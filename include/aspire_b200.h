@@ -257,6 +257,37 @@ int asp_topk(const float* scores, int Q, long long N, int k, long long base_id, 
 int asp_topk_merge(const float* in_scores, const long long* in_ids, int Q, int R, int k, float* out_scores,
                    long long* out_ids, asp_stream_t stream);
 
+/* ---- host front end of the encoder: BERT word pieces + sequence assembly (no GPU involved) -------------------
+ * Replaces tokenizer.tokenize + convert_tokens_to_ids per sentence (examples/ex_aspire_consent.py:131-133 =
+ * src/learning/batchers.py:579-581) and the per-document concatenation / 500-piece truncation / [CLS]..[SEP] /
+ * padding / span bookkeeping of examples/ex_aspire_consent.py:120-173, multi-threaded.
+ *
+ * asp_wordpiece_create: vocabulary = n_vocab UTF-8 tokens concatenated in vocab_blob, token id = its index,
+ *   vocab_offsets[n_vocab+1]; "##x" entries are continuation pieces; special_ids name the tokens ([SEP], [MASK] ...)
+ *   that are matched verbatim in the raw text before normalisation.  Returns NULL on error (asp_last_error()).
+ * asp_wordpiece_encode: n_sent sentences concatenated in `text` (offsets[n_sent+1], bytes).  out_ids needs room for
+ *   offsets[n_sent]-offsets[0] entries; on return sentence i owns out_ids[out_offsets[i] .. out_offsets[i+1]).
+ *   Text is cleaned, (optionally) lower-cased, split on whitespace and punctuation and cut into greedy longest-match
+ *   word pieces; words longer than max_chars_per_word become the unknown token.  Sentences holding a byte >= 0x80 are
+ *   NOT tokenised (needs_fallback[i] = 1, zero ids): the caller runs them through the original tokenizer.
+ */
+typedef struct asp_wordpiece asp_wordpiece;
+asp_wordpiece* asp_wordpiece_create(const char* vocab_blob, const int64_t* vocab_offsets, int n_vocab, int lower_case,
+                                    int unk_id, const int32_t* special_ids, int n_special);
+void asp_wordpiece_destroy(asp_wordpiece* wp);
+int asp_wordpiece_encode(const asp_wordpiece* wp, const char* text, const int64_t* offsets, int n_sent,
+                         int max_chars_per_word, int threads, int32_t* out_ids, int64_t* out_offsets,
+                         uint8_t* needs_fallback);
+/* Document d owns doc_sents[d] consecutive sentences (element 0 = the title); sentence k's ids are
+ * ids[sent_offsets[k] .. sent_offsets[k+1]).  plan: seq_lens[d] (with [CLS]/[SEP]) and abs_lens[d] (kept abstract
+ * sentences) under the `budget`-piece truncation rule.  fill: tokid/seg/attn int64 [n_docs,width] (pad_id outside the
+ * sequence, like the reference) and spans int32 [n_docs,max_sents,2] half-open token ranges, (-1,-1) = no sentence. */
+int asp_abstracts_plan(const int64_t* sent_offsets, const int32_t* doc_sents, int n_docs, int budget, int32_t* seq_lens,
+                       int32_t* abs_lens);
+int asp_abstracts_fill(const int32_t* ids, const int64_t* sent_offsets, const int32_t* doc_sents, int n_docs, int budget,
+                       int cls_id, int sep_id, int64_t pad_id, int width, int max_sents, int64_t* tokid, int64_t* seg,
+                       int64_t* attn, int32_t* spans);
+
 #ifdef __cplusplus
 }
 #endif

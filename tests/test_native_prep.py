@@ -1,0 +1,136 @@
+"""Host front end of the encoder (`asp_wordpiece_*`, `asp_abstracts_*`; no GPU involved): the library's BERT word-piece
+tokenizer and sequence assembly against the Hugging Face fast tokenizer + `prepare_abstracts_fast`, which in turn is
+pinned to the reference-shaped `prepare_abstracts` in test_host_api.py.  Integer work: everything must match exactly.
+"""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shims
+
+SYLL = ["al", "ign", "trans", "port", "op", "ti", "mal", "bio", "med", "ic", "graph", "neur", "net", "work", "re", "triev",
+        "sent", "ence", "pa", "per"]
+PUNCT = ".,;:()[]#-!?'\"/\\{}<>=+*&^%$@~`|_"
+
+
+def _tokenizer(tmp_path, lower=True, extra=()):
+    from transformers import BertTokenizerFast
+    rnd = random.Random(11)
+    words = sorted({"".join(rnd.choice(SYLL) for _ in range(rnd.randint(1, 3))) for _ in range(1500)})
+    vocab = (["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words + ["##" + s for s in SYLL] + list(PUNCT) +
+             ["a", "b", "##a", "##b", "1", "2", "##1", "##2", "Trans", "##Port"] + list(extra))
+    vf = tmp_path / ("vocab_%d.txt" % lower)
+    vf.write_text("\n".join(vocab) + "\n")
+    return BertTokenizerFast(vocab_file=str(vf), do_lower_case=lower), words
+
+
+def _random_word(rnd, words):
+    r = rnd.random()
+    if r < 0.55:
+        return rnd.choice(words)
+    if r < 0.65:
+        return rnd.choice(words).upper() if rnd.random() < 0.5 else rnd.choice(words).capitalize()
+    if r < 0.72:
+        return rnd.choice(words) + rnd.choice(PUNCT) + rnd.choice(words)
+    if r < 0.78:
+        return "".join(rnd.choice("ab12xyz") for _ in range(rnd.randint(1, 12)))
+    if r < 0.81:
+        return "x" * rnd.randint(95, 105)  # straddles max_input_chars_per_word = 100
+    if r < 0.85:
+        return rnd.choice(["[SEP]", "[MASK]", "[sep]", "[CLS]x", "a[UNK]b", "[PAD", "[[SEP]]", "[SEP][SEP]"])
+    if r < 0.90:
+        return rnd.choice(["\t", "\n", "\x0b", "\x0c", "\x01", "\x1f", "\x7f", "  ", "\r\n", "\x00"])
+    if r < 0.94:
+        return rnd.choice(["naïve", "résumé", "β-cell", "中文", "Å", "x y", "​", "ﬁn", "İ"])
+    return rnd.choice(SYLL)
+
+
+def _same(a, b):
+    assert a[1] == b[1], "abs_lens differ"
+    assert a[0]["seq_lens"] == b[0]["seq_lens"], "seq_lens differ"
+    for k in ("tokid_tt", "seg_tt", "attnmask_tt"):
+        assert a[0][k].dtype == b[0][k].dtype and torch.equal(a[0][k], b[0][k]), k
+    assert a[2].dtype == b[2].dtype and torch.equal(a[2], b[2]), "span tables differ"
+
+
+@pytest.mark.parametrize("lower", [True, False])
+def test_native_prep_matches_hf_tokenizer_fuzz(tmp_path, lower):
+    from aspire_b200.consent import native_wordpiece, prepare_abstracts_fast, prepare_abstracts_native
+    tok, words = _tokenizer(tmp_path, lower)
+    wp = native_wordpiece(tok)
+    assert wp is not None, "the plain BERT pipeline must be handled natively"
+    rnd = random.Random(5 + lower)
+    asserted = 0
+    for _ in range(120):
+        batch = [{"TITLE": " ".join(_random_word(rnd, words) for _ in range(rnd.randint(0, 14))),
+                  "ABSTRACT": [" ".join(_random_word(rnd, words) for _ in range(rnd.randint(0, 90)))
+                               for _ in range(rnd.randint(1, 30))]} for _ in range(rnd.randint(1, 6))]
+        flat = [s for ex in batch for s in [ex["TITLE"] + " [SEP] "] + ex["ABSTRACT"]]
+        ids, offs = wp.encode(flat)
+        want = tok(flat, add_special_tokens=False)["input_ids"]
+        for i, w in enumerate(want):
+            assert ids[offs[i]:offs[i + 1]].tolist() == w, repr(flat[i])[:200]
+        try:
+            ref = prepare_abstracts_fast(batch, tok)
+        except AssertionError:  # a document whose sentences all vanish: both front ends must refuse it
+            with pytest.raises(AssertionError):
+                prepare_abstracts_native(batch, tok)
+            asserted += 1
+            continue
+        _same(ref, prepare_abstracts_native(batch, tok))
+    assert asserted < 60
+
+
+def test_native_prep_truncation_and_edges(tmp_path):
+    from aspire_b200.consent import MAX_WORDPIECES, prepare_abstracts, prepare_abstracts_native, spans_from_token_idxs
+    tok, words = _tokenizer(tmp_path)
+    w = words[0]
+    cases = [
+        [{"TITLE": "", "ABSTRACT": [w]}],                                                    # empty title
+        [{"TITLE": w, "ABSTRACT": ["", w, ""]}],                                             # empty sentences keep a slot
+        [{"TITLE": w, "ABSTRACT": [" ".join([w] * 300), " ".join([w] * 300), w]}],           # second sentence is cut, third dropped
+        [{"TITLE": w, "ABSTRACT": [" ".join([w] * (MAX_WORDPIECES - 2)), w, w]}],            # budget met exactly, later ones dropped
+        [{"TITLE": " ".join([w] * 10), "ABSTRACT": [w] * 40}, {"TITLE": w, "ABSTRACT": [w]}],  # ragged batch
+        [{"TITLE": w, "ABSTRACT": ["naïve " + w, w + " résumé"]}],                           # Unicode sentences take the fallback
+    ]
+    for batch in cases:
+        bb, al, idxs = prepare_abstracts(batch_abs=batch, pt_lm_tokenizer=tok)
+        nb, nal, spans = prepare_abstracts_native(batch, tok)
+        assert nal == al and nb["seq_lens"] == bb["seq_lens"]
+        for k in ("tokid_tt", "seg_tt", "attnmask_tt"):
+            assert torch.equal(nb[k], bb[k])
+        assert torch.equal(spans, spans_from_token_idxs(idxs, max(al)))
+        assert max(nb["seq_lens"]) <= MAX_WORDPIECES + 2
+    with pytest.raises(AssertionError):  # the title alone fills the budget: no abstract sentence survives
+        prepare_abstracts_native([{"TITLE": " ".join([w] * 600), "ABSTRACT": [w]}], tok)
+
+
+def test_native_prep_falls_back_for_other_tokenizers():
+    from aspire_b200.consent import native_wordpiece, prepare_abstracts_fast, prepare_abstracts_native
+    toy = ref_shims.ToyTokenizer()
+    assert native_wordpiece(toy) is None
+    batch = [{"TITLE": "optimal transport", "ABSTRACT": ["we study alignment .", "graphs of papers"]}]
+    _same(prepare_abstracts_fast(batch, toy), prepare_abstracts_native(batch, toy))
+
+
+def test_native_prep_abi_errors():
+    from aspire_b200 import _abi
+    L = _abi.lib()
+    assert not L.asp_wordpiece_create(None, None, 0, 1, 0, None, 0)
+    assert b"asp_wordpiece_create" in L.asp_last_error()
+    offs = np.array([0, 3, 5], dtype=np.int64)
+    sents = np.array([0], dtype=np.int32)  # a document without even a title element
+    out = np.zeros(4, dtype=np.int32)
+    rc = L.asp_abstracts_plan(offs.ctypes.data, sents.ctypes.data, 1, 500, out.ctypes.data, out[2:].ctypes.data)
+    assert rc != 0 and b"no title" in L.asp_last_error()
+    # fill with a width smaller than the plan asks for must refuse, not overrun
+    sents[0] = 2
+    ids = np.arange(5, dtype=np.int32)
+    tokid = np.zeros((1, 4), dtype=np.int64)
+    spans = np.zeros((1, 1, 2), dtype=np.int32)
+    rc = L.asp_abstracts_fill(ids.ctypes.data, offs.ctypes.data, sents.ctypes.data, 1, 500, 101, 102, ctypes.c_longlong(0), 4, 1,
+                              tokid.ctypes.data, tokid.copy().ctypes.data, tokid.copy().ctypes.data, spans.ctypes.data)
+    assert rc != 0 and b"does not fit" in L.asp_last_error()

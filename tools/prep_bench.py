@@ -1,0 +1,43 @@
+"""Host-side throughput of the three abstract-preparation front ends (documents/s, CPU only): the reference-shaped
+per-sentence protocol, one batched call into the Hugging Face (Rust) tokenizer, and the library's native word-piece +
+sequence assembly.  Synthetic ~250-token abstracts over a synthetic word-piece vocabulary (no vocab files offline)."""
+import os
+import random
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from transformers import BertTokenizerFast  # noqa: E402
+
+from aspire_b200.consent import prepare_abstracts, prepare_abstracts_fast, prepare_abstracts_native  # noqa: E402
+
+
+def main():
+    rnd = random.Random(1)
+    syll = ["al", "ign", "trans", "port", "op", "ti", "mal", "bio", "med", "ic", "graph", "neur", "net", "work", "re",
+            "triev", "sent", "ence", "pa", "per"]
+    words = ["".join(rnd.choice(syll) for _ in range(rnd.randint(1, 3))) for _ in range(3000)]
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + sorted(set(words)) + ["##" + s for s in syll] + [".", ","]
+    vf = os.path.join(tempfile.mkdtemp(), "vocab.txt")
+    with open(vf, "w") as fh:
+        fh.write("\n".join(vocab) + "\n")
+    tok = BertTokenizerFast(vocab_file=vf, do_lower_case=True)
+    docs = [{"TITLE": " ".join(rnd.choice(words) for _ in range(10)),
+             "ABSTRACT": [" ".join(rnd.choice(words) + rnd.choice(["", "", "", "s", "ing"]) for _ in range(rnd.randint(15, 35))) + " ."
+                          for _ in range(rnd.randint(5, 11))]} for _ in range(4096)]
+    print(f"host cores: {os.cpu_count()}")
+    for name, fn, n_docs in (("prepare_abstracts (per sentence)", prepare_abstracts, 512),
+                             ("prepare_abstracts_fast (HF batch)", prepare_abstracts_fast, 2048),
+                             ("prepare_abstracts_native", prepare_abstracts_native, 4096)):
+        for bs in (32, 128, 512):
+            fn(batch_abs=docs[:bs], pt_lm_tokenizer=tok)
+            t0 = time.perf_counter()
+            for i in range(0, n_docs, bs):
+                out = fn(batch_abs=docs[i:i + bs], pt_lm_tokenizer=tok)
+            dt = time.perf_counter() - t0
+            print(f"{name:36s} batch {bs:4d}: {n_docs / dt:9.0f} docs/s   (width {out[0]['tokid_tt'].shape[1]})", flush=True)
+
+
+if __name__ == "__main__":
+    main()
