@@ -185,11 +185,49 @@ class NativeWordPiece:
         self.max_chars = int(model.get("max_input_chars_per_word", 100))
         self.threads = int(threads or min(16, os.cpu_count() or 1))
         self.tokenizer = tokenizer
+        self._unicode = False
         self._lib = _abi.lib()
         self._handle = self._lib.asp_wordpiece_create(blob, offsets.ctypes.data, len(encoded), int(bool(norm.get("lowercase", True))),
                                                       int(vocab[model["unk_token"]]), special_ids.ctypes.data, len(special_ids))
         if not self._handle:
             raise ValueError("asp_wordpiece_create: " + self._lib.asp_last_error().decode("utf8", "replace"))
+
+    def _install_unicode(self):
+        """Per-code-point tables of the Basic Multilingual Plane, taken from the tokenizer's own normaliser and
+        pre-tokenizer: what each character is normalised to, and whether it separates words (space) or stands alone
+        (punctuation).  Context-dependent characters (capital sigma: final-sigma rule of lower-casing), surrogates and
+        anything the normaliser rejects stay with the Hugging Face tokenizer, as do characters beyond the BMP."""
+        self._unicode = None  # tried
+        backend = self.tokenizer.backend_tokenizer
+        norm, pre = backend.normalizer, backend.pre_tokenizer
+        pieces, offsets = [], np.zeros(0x10001, dtype=np.uint32)
+        out_class = np.zeros(0x10000, dtype=np.uint8)
+        fallback = np.zeros(0x10000, dtype=np.uint8)
+        total = 0
+        for cp in range(0x10000):
+            out = b""
+            if 0xD800 <= cp <= 0xDFFF or cp == 0x3A3:
+                fallback[cp] = 1
+            else:
+                ch = chr(cp)
+                try:
+                    out = norm.normalize_str(ch).encode("utf-8")
+                    parts = [t for t, _ in pre.pre_tokenize_str("a" + ch + "a")]
+                    if parts == ["a", "a"]:
+                        out_class[cp] = 1
+                    elif parts == ["a", ch, "a"]:
+                        out_class[cp] = 2
+                    elif parts != ["a" + ch + "a"]:
+                        fallback[cp] = 1
+                except Exception:
+                    fallback[cp], out = 1, b""
+            pieces.append(out)
+            total += len(out)
+            offsets[cp + 1] = total
+        blob = b"".join(pieces)
+        rc = self._lib.asp_wordpiece_set_unicode(self._handle, offsets.ctypes.data, blob, out_class.ctypes.data,
+                                                 fallback.ctypes.data)
+        self._unicode = rc == 0
 
     def __del__(self):
         if getattr(self, "_handle", None):
@@ -198,7 +236,9 @@ class NativeWordPiece:
 
     def encode(self, sentences):
         """list(str) -> (ids int32 [total], offsets int64 [n+1]); same ids as ``tokenizer(s, add_special_tokens=False)``.
-        Sentences with non-ASCII characters go through the Hugging Face tokenizer (they need the Unicode tables)."""
+        Non-ASCII sentences use per-character tables read off the tokenizer itself (installed on first need); what
+        those cannot express (characters beyond the BMP, capital sigma, malformed text) goes through the Hugging Face
+        tokenizer."""
         raw = [s.encode("utf-8") for s in sentences]
         n = len(raw)
         offsets = np.zeros(n + 1, dtype=np.int64)
@@ -210,8 +250,13 @@ class NativeWordPiece:
         _abi.check(self._lib.asp_wordpiece_encode(self._handle, b"".join(raw), offsets.ctypes.data, n, self.max_chars, self.threads,
                                                   ids.ctypes.data, out_offsets.ctypes.data, fallback.ctypes.data),
                    "asp_wordpiece_encode")
-        ids = ids[:out_offsets[-1]]
         todo = np.flatnonzero(fallback[:n])
+        if len(todo) and not self._unicode:
+            # first non-ASCII sentence: give the library the tokenizer's own per-character tables and run it again
+            self._install_unicode()
+            if self._unicode:
+                return self.encode(sentences)
+        ids = ids[:out_offsets[-1]]
         if len(todo):
             extra = self.tokenizer([sentences[i] for i in todo], add_special_tokens=False, return_attention_mask=False,
                                    return_token_type_ids=False)["input_ids"]

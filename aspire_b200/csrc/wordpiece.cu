@@ -10,10 +10,15 @@
 // Scope: the BERT tokenizer the reference loads (BasicTokenizer + WordPiece: clean text, lower-case, split on
 // whitespace and punctuation, greedy longest-match-first word pieces with the "##" continuation prefix, words longer
 // than max_input_chars_per_word -> [UNK]; special tokens such as the literal "[SEP]" the reference appends to the title
-// are matched verbatim before normalisation) on ASCII text.  A sentence holding any byte >= 0x80 is NOT tokenised here:
-// it is reported back (needs_fallback) and the caller runs it through the original tokenizer, because accent
-// stripping, NFC/NFD and the CJK rules need the Unicode tables.  No CUDA in this file; it lives in the same library so
-// the ctypes binding and the error convention are shared.
+// are matched verbatim before normalisation).  ASCII sentences take a single-pass fast path with the rules written
+// out below.  Non-ASCII sentences are normalised and classified through per-code-point tables of the Basic
+// Multilingual Plane that the caller reads off the tokenizer's own normaliser and pre-tokenizer
+// (asp_wordpiece_set_unicode) -- accent stripping, lower-casing, CJK spacing, Unicode spaces / punctuation all come
+// from there, nothing about Unicode is restated here.  What the tables cannot express (characters beyond U+FFFF,
+// characters whose treatment depends on context, malformed UTF-8 -- or any non-ASCII byte when no tables were
+// given) is reported back per sentence (needs_fallback) and the caller runs that sentence through the original
+// tokenizer.  No CUDA in this file; it lives in the same library so the ctypes binding and the error convention are
+// shared.
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -30,6 +35,14 @@ struct asp_wordpiece {
     size_t max_piece = 0;
     int32_t unk_id = 0;
     bool lower_case = true;
+    // Optional per-code-point tables of the Basic Multilingual Plane (asp_wordpiece_set_unicode): what the tokenizer's
+    // normaliser turns each character into (lower-casing, accent stripping, text cleaning, spaces around CJK ...), how
+    // the pre-tokenizer classes each character (0 word, 1 space, 2 punctuation), and which characters must be left to
+    // the original tokenizer because their treatment depends on context.
+    bool unicode = false;
+    std::vector<uint32_t> norm_offsets;  // 65537
+    std::string norm_blob;
+    std::vector<uint8_t> out_class, fallback;  // 65536 each
 };
 
 namespace {
@@ -43,12 +56,13 @@ inline bool is_punct(unsigned char c) {
 }
 
 // Greedy longest-match-first word pieces of one cleaned, lower-cased word (WordpieceTokenizer.tokenize).
-inline void wordpiece(const asp_wordpiece& wp, const char* w, size_t n, size_t max_chars, int32_t*& out) {
-    if (n > max_chars) {
+template <typename Out>
+inline void wordpiece(const asp_wordpiece& wp, const char* w, size_t n, size_t n_chars, size_t max_chars, Out& out) {
+    if (n_chars > max_chars) {
         *out++ = wp.unk_id;
         return;
     }
-    int32_t* const first = out;
+    const auto first = out;
     size_t start = 0;
     while (start < n) {
         const auto& map = start ? wp.continuation : wp.initial;
@@ -73,15 +87,17 @@ inline void wordpiece(const asp_wordpiece& wp, const char* w, size_t n, size_t m
 
 // One sentence -> ids at `out` (capacity >= its byte length: every id consumes at least one byte).  Returns the count,
 // or -1 if the sentence holds a non-ASCII byte.
+int64_t encode_sentence_unicode(const asp_wordpiece& wp, const char* s, size_t n, size_t max_chars, int32_t* out_base);
+
 int64_t encode_sentence(const asp_wordpiece& wp, const char* s, size_t n, size_t max_chars, int32_t* out) {
     for (size_t i = 0; i < n; ++i)
-        if ((unsigned char)s[i] >= 0x80) return -1;
+        if ((unsigned char)s[i] >= 0x80) return wp.unicode ? encode_sentence_unicode(wp, s, n, max_chars, out) : -1;
     int32_t* const base = out;
     std::string word;
     word.reserve(64);
     auto flush = [&]() {
         if (!word.empty()) {
-            wordpiece(wp, word.data(), word.size(), max_chars, out);
+            wordpiece(wp, word.data(), word.size(), word.size(), max_chars, out);
             word.clear();
         }
     };
@@ -109,13 +125,113 @@ int64_t encode_sentence(const asp_wordpiece& wp, const char* s, size_t n, size_t
         } else if (is_punct(c)) {
             flush();
             const char p = (char)c;
-            wordpiece(wp, &p, 1, max_chars, out);
+            wordpiece(wp, &p, 1, 1, max_chars, out);
         } else {
             word.push_back(wp.lower_case && c >= 'A' && c <= 'Z' ? (char)(c + 32) : (char)c);
         }
     }
     flush();
     return out - base;
+}
+
+// Decodes one UTF-8 sequence at s[i..n); returns its length (0 = malformed) and the code point.
+inline int utf8_decode(const char* s, size_t i, size_t n, uint32_t& cp) {
+    const unsigned char c = (unsigned char)s[i];
+    if (c < 0x80) {
+        cp = c;
+        return 1;
+    }
+    const int len = (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 0;
+    if (!len || i + len > n) return 0;
+    cp = c & (0xFF >> (len + 1));
+    for (int k = 1; k < len; ++k) {
+        const unsigned char d = (unsigned char)s[i + k];
+        if ((d & 0xC0) != 0x80) return 0;
+        cp = (cp << 6) | (d & 0x3F);
+    }
+    if ((len == 2 && cp < 0x80) || (len == 3 && cp < 0x800) || (len == 4 && cp < 0x10000)) return 0;  // overlong
+    return len;
+}
+
+struct IdSink {  // bounded writer: a sentence may never emit more ids than it has bytes (the caller's capacity)
+    int32_t* p;
+    int32_t* end;
+    bool overflow = false;
+    IdSink& operator++(int) { return *this; }
+    struct Ref {
+        IdSink& s;
+        void operator=(int32_t v) {
+            if (s.p < s.end)
+                *s.p++ = v;
+            else
+                s.overflow = true;
+        }
+    };
+    Ref operator*() { return Ref{*this}; }
+};
+inline bool operator==(const IdSink& a, const IdSink& b) { return a.p == b.p; }
+
+// Pre-tokenise + word-piece one NORMALISED segment (split on the table's spaces and punctuation).
+inline void segment_to_ids(const asp_wordpiece& wp, const std::string& buf, size_t max_chars, IdSink& out, std::string& word) {
+    size_t chars = 0;
+    auto flush = [&]() {
+        if (!word.empty()) {
+            const IdSink first = out;
+            wordpiece(wp, word.data(), word.size(), chars, max_chars, out);
+            (void)first;
+            word.clear();
+            chars = 0;
+        }
+    };
+    for (size_t i = 0; i < buf.size();) {
+        uint32_t cp = 0;
+        int len = utf8_decode(buf.data(), i, buf.size(), cp);
+        if (!len) len = 1, cp = 0xFFFD;  // cannot happen: the blob holds the normaliser's own (valid) output
+        const uint8_t cls = cp < 0x10000 ? wp.out_class[cp] : 0;
+        if (cls == 1) {
+            flush();
+        } else if (cls == 2) {
+            flush();
+            wordpiece(wp, buf.data() + i, (size_t)len, 1, max_chars, out);
+        } else {
+            word.append(buf, i, (size_t)len);
+            ++chars;
+        }
+        i += (size_t)len;
+    }
+    flush();
+}
+
+// Sentence with non-ASCII characters, through the per-code-point tables.  -1: leave it to the original tokenizer.
+int64_t encode_sentence_unicode(const asp_wordpiece& wp, const char* s, size_t n, size_t max_chars, int32_t* out_base) {
+    IdSink out{out_base, out_base + n};
+    std::string buf, word;
+    buf.reserve(n + 16);
+    size_t i = 0;
+    while (i < n) {
+        const unsigned char c = (unsigned char)s[i];
+        if (!wp.specials.empty() && c == (unsigned char)wp.specials.front().first[0]) {
+            const std::pair<std::string, int32_t>* hit = nullptr;
+            for (const auto& sp : wp.specials)
+                if (sp.first.size() <= n - i && memcmp(s + i, sp.first.data(), sp.first.size()) == 0 &&
+                    (!hit || sp.first.size() > hit->first.size()))
+                    hit = &sp;
+            if (hit) {
+                segment_to_ids(wp, buf, max_chars, out, word);
+                buf.clear();
+                *out = hit->second;
+                i += hit->first.size();
+                continue;
+            }
+        }
+        uint32_t cp = 0;
+        const int len = utf8_decode(s, i, n, cp);
+        if (!len || cp >= 0x10000 || wp.fallback[cp]) return -1;
+        buf.append(wp.norm_blob, wp.norm_offsets[cp], wp.norm_offsets[cp + 1] - wp.norm_offsets[cp]);
+        i += (size_t)len;
+    }
+    segment_to_ids(wp, buf, max_chars, out, word);
+    return out.overflow ? -1 : out.p - out_base;
 }
 
 }  // namespace
@@ -163,6 +279,19 @@ extern "C" asp_wordpiece* asp_wordpiece_create(const char* vocab_blob, const int
 }
 
 extern "C" void asp_wordpiece_destroy(asp_wordpiece* wp) { delete wp; }
+
+extern "C" int asp_wordpiece_set_unicode(asp_wordpiece* wp, const uint32_t* norm_offsets, const char* norm_blob,
+                                         const uint8_t* out_class, const uint8_t* fallback) {
+    ASP_REQUIRE(wp && norm_offsets && norm_blob && out_class && fallback, "asp_wordpiece_set_unicode: NULL argument");
+    for (int cp = 0; cp < 0x10000; ++cp)
+        ASP_REQUIRE(norm_offsets[cp] <= norm_offsets[cp + 1], "asp_wordpiece_set_unicode: offsets must not decrease (at U+%04X)", cp);
+    wp->norm_offsets.assign(norm_offsets, norm_offsets + 0x10001);
+    wp->norm_blob.assign(norm_blob, norm_offsets[0x10000]);
+    wp->out_class.assign(out_class, out_class + 0x10000);
+    wp->fallback.assign(fallback, fallback + 0x10000);
+    wp->unicode = true;
+    return ASP_OK;
+}
 
 extern "C" int asp_wordpiece_encode(const asp_wordpiece* wp, const char* text, const int64_t* offsets, int n_sent,
                                     int max_chars_per_word, int threads, int32_t* out_ids, int64_t* out_offsets,

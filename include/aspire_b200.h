@@ -268,13 +268,21 @@ int asp_topk_merge(const float* in_scores, const long long* in_ids, int Q, int R
  * asp_wordpiece_encode: n_sent sentences concatenated in `text` (offsets[n_sent+1], bytes).  out_ids needs room for
  *   offsets[n_sent]-offsets[0] entries; on return sentence i owns out_ids[out_offsets[i] .. out_offsets[i+1]).
  *   Text is cleaned, (optionally) lower-cased, split on whitespace and punctuation and cut into greedy longest-match
- *   word pieces; words longer than max_chars_per_word become the unknown token.  Sentences holding a byte >= 0x80 are
- *   NOT tokenised (needs_fallback[i] = 1, zero ids): the caller runs them through the original tokenizer.
+ *   word pieces; words longer than max_chars_per_word become the unknown token.  Without asp_wordpiece_set_unicode,
+ *   sentences holding a byte >= 0x80 are NOT tokenised (needs_fallback[i] = 1, zero ids): the caller runs them
+ *   through the original tokenizer.
  */
 typedef struct asp_wordpiece asp_wordpiece;
 asp_wordpiece* asp_wordpiece_create(const char* vocab_blob, const int64_t* vocab_offsets, int n_vocab, int lower_case,
                                     int unk_id, const int32_t* special_ids, int n_special);
 void asp_wordpiece_destroy(asp_wordpiece* wp);
+/* Optional: per-code-point tables of the Basic Multilingual Plane so that non-ASCII sentences are tokenised here too.
+ *   norm_offsets[65537] / norm_blob: UTF-8 text each character is normalised to (may be empty, or longer than one
+ *   character); out_class[65536]: 0 word character, 1 separates words, 2 punctuation (a word of its own), applied to
+ *   the normalised text; fallback[65536]: 1 = a sentence holding this character is reported in needs_fallback.
+ *   Characters beyond U+FFFF and malformed UTF-8 always are. */
+int asp_wordpiece_set_unicode(asp_wordpiece* wp, const uint32_t* norm_offsets, const char* norm_blob,
+                              const uint8_t* out_class, const uint8_t* fallback);
 int asp_wordpiece_encode(const asp_wordpiece* wp, const char* text, const int64_t* offsets, int n_sent,
                          int max_chars_per_word, int threads, int32_t* out_ids, int64_t* out_offsets,
                          uint8_t* needs_fallback);

@@ -134,3 +134,52 @@ def test_native_prep_abi_errors():
     rc = L.asp_abstracts_fill(ids.ctypes.data, offs.ctypes.data, sents.ctypes.data, 1, 500, 101, 102, ctypes.c_longlong(0), 4, 1,
                               tokid.ctypes.data, tokid.copy().ctypes.data, tokid.copy().ctypes.data, spans.ctypes.data)
     assert rc != 0 and b"does not fit" in L.asp_last_error()
+
+
+@pytest.mark.parametrize("lower", [True, False])
+def test_native_wordpiece_unicode_tables_fuzz(tmp_path, lower):
+    """Non-ASCII text: the per-code-point tables are read off the tokenizer's own normaliser / pre-tokenizer, so accent
+    stripping, lower-casing, CJK spacing, Unicode spaces and punctuation, zero-width and control characters must all
+    come out as the Hugging Face tokenizer produces them; capital sigma (context-dependent lower-casing), characters
+    beyond the BMP and whatever else the tables decline are answered by the Hugging Face tokenizer itself."""
+    from aspire_b200.consent import native_wordpiece
+    extra = ["β", "##β", "naive", "resume", "α", "δ", "中", "文", "±", "°", "–", "—", "“", "”", "’", "é", "É", "##é", "µ", "μ",
+             "ß", "ı", "i", "##i", "ж", "Ж", "##ж", "×", "→", "σ", "ς", "##ς", "##σ", "ο", "φ", "##ο", "##φ"]
+    tok, words = _tokenizer(tmp_path, lower, extra=extra)
+    wp = native_wordpiece(tok)
+    assert wp is not None
+    rnd = random.Random(31 + lower)
+    pools = [list(range(0x20, 0x7f)), list(range(0xa0, 0x180)), list(range(0x370, 0x400)), list(range(0x400, 0x460)),
+             list(range(0x2000, 0x2070)), list(range(0x4e00, 0x4e40)), list(range(0x300, 0x330)), list(range(0x1e00, 0x1f00)),
+             [0x3a3, 0x3c3, 0x3c2, 0x130, 0x131, 0xfb01, 0x1f600, 0x200b, 0xad, 0xfffd, 0xa0, 0x3000, 0x85, 0x2028, 0xac00,
+              0xd55c, 0x10348]]
+    sentences = []
+    for _ in range(1500):
+        parts = []
+        for _ in range(rnd.randint(0, 40)):
+            r = rnd.random()
+            if r < 0.5:
+                parts.append(rnd.choice(words))
+            elif r < 0.6:
+                parts.append(" ")
+            elif r < 0.65:
+                parts.append(rnd.choice(["[SEP]", "[MASK]", "naïve", "résumé", "RÉSUMÉ", "β-cell", "中文", "Ж", "ΣΟΦΟΣ", "σοφος"]))
+            else:
+                parts.append("".join(chr(rnd.choice(rnd.choice(pools))) for _ in range(rnd.randint(1, 4))))
+            if rnd.random() < 0.7:
+                parts.append(" ")
+        sentences.append("".join(parts))
+    ids, offs = wp.encode(sentences)  # one batch: native sentences and fallback sentences interleaved
+    assert wp._unicode is True
+    want = tok(sentences, add_special_tokens=False)["input_ids"]
+    for i, w in enumerate(want):
+        assert ids[offs[i]:offs[i + 1]].tolist() == w, repr(sentences[i])[:200]
+    # the tables really are in use: a sentence of BMP characters is answered natively, one with an emoji is not
+    L = wp._lib
+    for text, expect in (("naïve β-cell “x” 中文", 0), ("smile \U0001F600", 1), ("ΣΟΦΟΣ", 1)):
+        raw = text.encode("utf-8")
+        o = np.array([0, len(raw)], dtype=np.int64)
+        out, oo, fb = np.zeros(len(raw), dtype=np.int32), np.zeros(2, dtype=np.int64), np.zeros(1, dtype=np.uint8)
+        assert L.asp_wordpiece_encode(wp._handle, raw, o.ctypes.data, 1, 100, 1, out.ctypes.data, oo.ctypes.data,
+                                      fb.ctypes.data) == 0
+        assert int(fb[0]) == expect, text
