@@ -227,7 +227,7 @@ class NativeWordPiece:
         blob = b"".join(pieces)
         rc = self._lib.asp_wordpiece_set_unicode(self._handle, offsets.ctypes.data, blob, out_class.ctypes.data,
                                                  fallback.ctypes.data)
-        self._unicode = rc == 0
+        self._unicode = True if rc == 0 else None
 
     def __del__(self):
         if getattr(self, "_handle", None):
@@ -251,7 +251,7 @@ class NativeWordPiece:
                                                   ids.ctypes.data, out_offsets.ctypes.data, fallback.ctypes.data),
                    "asp_wordpiece_encode")
         todo = np.flatnonzero(fallback[:n])
-        if len(todo) and not self._unicode:
+        if len(todo) and self._unicode is False:  # None = tried and unavailable
             # first non-ASCII sentence: give the library the tokenizer's own per-character tables and run it again
             self._install_unicode()
             if self._unicode:
