@@ -218,7 +218,8 @@ def test_prepare_abstracts_fast_equals_per_sentence_protocol(tmp_path):
     and against the ToyTokenizer fallback path."""
     import random
     from transformers import BertTokenizerFast
-    from aspire_b200.consent import prepare_abstracts, prepare_abstracts_fast, spans_from_token_idxs
+    from aspire_b200.consent import prepare_abstracts_per_sentence as prepare_abstracts  # the reference's protocol
+    from aspire_b200.consent import prepare_abstracts_fast, spans_from_token_idxs
     words = ["optimal", "transport", "sentence", "paper", "graph", "neural", "network", "the", "of", "a", "we", "study",
              "align", "##ment", "##s", "##ing", "bio", "##medical", "retrieval", ".", ","]
     vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + words

@@ -1,6 +1,6 @@
 """Host front end of the encoder (`asp_wordpiece_*`, `asp_abstracts_*`; no GPU involved): the library's BERT word-piece
 tokenizer and sequence assembly against the Hugging Face fast tokenizer + `prepare_abstracts_fast`, which in turn is
-pinned to the reference-shaped `prepare_abstracts` in test_host_api.py.  Integer work: everything must match exactly.
+pinned to the reference-shaped per-sentence protocol in test_host_api.py.  Integer work: everything must match exactly.
 """
 import ctypes
 import random
@@ -86,6 +86,7 @@ def test_native_prep_matches_hf_tokenizer_fuzz(tmp_path, lower):
 
 def test_native_prep_truncation_and_edges(tmp_path):
     from aspire_b200.consent import MAX_WORDPIECES, prepare_abstracts, prepare_abstracts_native, spans_from_token_idxs
+    from aspire_b200.consent import prepare_abstracts_per_sentence
     tok, words = _tokenizer(tmp_path)
     w = words[0]
     cases = [
@@ -97,7 +98,11 @@ def test_native_prep_truncation_and_edges(tmp_path):
         [{"TITLE": w, "ABSTRACT": ["naïve " + w, w + " résumé"]}],                           # Unicode sentences take the fallback
     ]
     for batch in cases:
-        bb, al, idxs = prepare_abstracts(batch_abs=batch, pt_lm_tokenizer=tok)
+        bb, al, idxs = prepare_abstracts_per_sentence(batch_abs=batch, pt_lm_tokenizer=tok)  # the reference's protocol
+        db, dal, didxs = prepare_abstracts(batch_abs=batch, pt_lm_tokenizer=tok)             # the drop-in name (native)
+        assert dal == al and didxs == idxs and db["seq_lens"] == bb["seq_lens"]
+        for k in ("tokid_tt", "seg_tt", "attnmask_tt"):
+            assert db[k].dtype == bb[k].dtype and torch.equal(db[k], bb[k])
         nb, nal, spans = prepare_abstracts_native(batch, tok)
         assert nal == al and nb["seq_lens"] == bb["seq_lens"]
         for k in ("tokid_tt", "seg_tt", "attnmask_tt"):

@@ -1,6 +1,6 @@
-"""Host-side throughput of the three abstract-preparation front ends (documents/s, CPU only): the reference-shaped
-per-sentence protocol, one batched call into the Hugging Face (Rust) tokenizer, and the library's native word-piece +
-sequence assembly.  Synthetic ~250-token abstracts over a synthetic word-piece vocabulary (no vocab files offline)."""
+"""Host-side throughput of the abstract-preparation front ends (documents/s, CPU only): the reference's per-sentence
+protocol, one batched call into the Hugging Face (Rust) tokenizer, the library's native word-piece + sequence assembly,
+and the drop-in ``prepare_abstracts`` (native batch + the reference's index lists).  Synthetic ~250-token abstracts over a synthetic word-piece vocabulary (no vocab files offline)."""
 import os
 import random
 import sys
@@ -10,7 +10,8 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from transformers import BertTokenizerFast  # noqa: E402
 
-from aspire_b200.consent import prepare_abstracts, prepare_abstracts_fast, prepare_abstracts_native  # noqa: E402
+from aspire_b200.consent import (prepare_abstracts, prepare_abstracts_fast, prepare_abstracts_native,  # noqa: E402
+                                  prepare_abstracts_per_sentence)
 
 
 def main():
@@ -27,9 +28,10 @@ def main():
              "ABSTRACT": [" ".join(rnd.choice(words) + rnd.choice(["", "", "", "s", "ing"]) for _ in range(rnd.randint(15, 35))) + " ."
                           for _ in range(rnd.randint(5, 11))]} for _ in range(4096)]
     print(f"host cores: {os.cpu_count()}")
-    for name, fn, n_docs in (("prepare_abstracts (per sentence)", prepare_abstracts, 512),
+    for name, fn, n_docs in (("per-sentence protocol (reference)", prepare_abstracts_per_sentence, 512),
                              ("prepare_abstracts_fast (HF batch)", prepare_abstracts_fast, 2048),
-                             ("prepare_abstracts_native", prepare_abstracts_native, 4096)):
+                             ("prepare_abstracts_native", prepare_abstracts_native, 4096),
+                             ("prepare_abstracts (drop-in name)", prepare_abstracts, 4096)):
         for bs in (32, 128, 512):
             fn(batch_abs=docs[:bs], pt_lm_tokenizer=tok)
             t0 = time.perf_counter()
