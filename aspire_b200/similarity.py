@@ -396,14 +396,36 @@ class AspireContextNER(AspireModel):
 
     def _get_ner_token_idxs(self, input_data, sent_token_idxs):
         """Token positions of every entity: the entity's word pieces are searched in its sentence's word pieces; an
-        entity that is not found, or that falls (partly) behind the 500-piece truncation, gets [] (:661-682)."""
+        entity that is not found, or that falls (partly) behind the 500-piece truncation, gets [] (:661-682).
+
+        The reference tokenises every sentence and every entity with its own ``tokenizer.tokenize`` call; here all of
+        them go through ONE call of the library's word-piece front end when the tokenizer is the plain BERT pipeline
+        (ids instead of token strings: the vocabulary is a bijection, and unknown words are the same [UNK] either way)."""
+        from .consent import native_wordpiece
+        wp = native_wordpiece(self.tokenizer)
+        pieces_of = None
+        if wp is not None:
+            texts = []
+            for sample, sample_sent_idxs in zip(input_data, sent_token_idxs):
+                for ners, sentence, _ in zip(sample['ENTITIES'], sample['ABSTRACT'], sample_sent_idxs):
+                    texts.append(sentence)
+                    texts.extend(ners)
+            ids, offs = wp.encode(texts)
+            ids, offs, cursor = ids.tolist(), offs.tolist(), [0]
+
+            def pieces_of(_text):  # texts are consumed in the order they were collected
+                k = cursor[0]
+                cursor[0] += 1
+                return ids[offs[k]:offs[k + 1]]
+        else:
+            pieces_of = self.tokenizer.tokenize
         all_idxs = []
         for sample, sample_sent_idxs in zip(input_data, sent_token_idxs):
             sample_idxs = []
             for ners, sentence, token_idxs in zip(sample['ENTITIES'], sample['ABSTRACT'], sample_sent_idxs):
-                tokens = self.tokenizer.tokenize(sentence)
+                tokens = pieces_of(sentence)
                 for ner in ners:
-                    rng = self.find_sublist_range(tokens, self.tokenizer.tokenize(ner))
+                    rng = self.find_sublist_range(tokens, pieces_of(ner))
                     if rng and rng[-1] < len(token_idxs):
                         sample_idxs.append([token_idxs[k] for k in rng])
                     else:

@@ -188,3 +188,35 @@ def test_native_wordpiece_unicode_tables_fuzz(tmp_path, lower):
         assert L.asp_wordpiece_encode(wp._handle, raw, o.ctypes.data, 1, 100, 1, out.ctypes.data, oo.ctypes.data,
                                       fb.ctypes.data) == 0
         assert int(fb[0]) == expect, text
+
+
+def test_context_ner_entity_positions_batched_equals_per_call(tmp_path):
+    """AspireContextNER._get_ner_token_idxs (utils/models.py:661-682): all sentences and entities through one call of
+    the native tokenizer against one ``tokenizer.tokenize`` call each, on the same fast tokenizer."""
+    from aspire_b200.consent import prepare_abstracts_per_sentence
+    from aspire_b200.similarity import AspireContextNER
+    tok, words = _tokenizer(tmp_path)
+    tok_slow, _ = _tokenizer(tmp_path)
+    object.__setattr__(tok_slow, "_asp_native_wordpiece", False)  # pin the per-call path
+    rnd = random.Random(77)
+    batch = []
+    for _ in range(12):
+        abstract, entities = [], []
+        for _ in range(rnd.randint(1, 40)):
+            sent = [_random_word(rnd, words) for _ in range(rnd.randint(1, 40))]
+            ents = []
+            for _ in range(rnd.randint(0, 4)):
+                if rnd.random() < 0.7 and len(sent) > 1:
+                    a = rnd.randrange(len(sent))
+                    ents.append(" ".join(sent[a:a + rnd.randint(1, 3)]))
+                else:
+                    ents.append(" ".join(rnd.choice(words) for _ in range(rnd.randint(1, 3))))  # usually absent
+            abstract.append(" ".join(sent))
+            entities.append(ents)
+        batch.append({"TITLE": " ".join(rnd.choice(words) for _ in range(8)), "ABSTRACT": abstract, "ENTITIES": entities})
+    _, _, sent_idxs = prepare_abstracts_per_sentence(batch_abs=batch, pt_lm_tokenizer=tok_slow)
+    fast, slow = object.__new__(AspireContextNER), object.__new__(AspireContextNER)
+    fast.tokenizer, slow.tokenizer = tok, tok_slow
+    got, want = fast._get_ner_token_idxs(batch, sent_idxs), slow._get_ner_token_idxs(batch, sent_idxs)
+    assert got == want
+    assert sum(len(x) > 0 for doc in want for x in doc) > 20 and sum(len(x) == 0 for doc in want for x in doc) > 5
