@@ -301,6 +301,8 @@ extern "C" int asp_wordpiece_encode(const asp_wordpiece* wp, const char* text, c
     ASP_REQUIRE(max_chars_per_word >= 1, "asp_wordpiece_encode: max_chars_per_word must be >= 1");
     out_offsets[0] = 0;
     if (n_sent == 0) return ASP_OK;
+    for (int i = 0; i < n_sent; ++i)
+        ASP_REQUIRE(offsets[i] <= offsets[i + 1], "asp_wordpiece_encode: offsets must not decrease (sentence %d)", i);
     // pass 1 (parallel): sentence i writes its ids at its own byte offset -- always enough room -- and its count
     std::vector<int64_t> counts((size_t)n_sent);
     const int64_t base = offsets[0];
@@ -357,6 +359,9 @@ extern "C" int asp_abstracts_plan(const int64_t* sent_offsets, const int32_t* do
     int64_t first = 0;
     for (int d = 0; d < n_docs; ++d) {
         ASP_REQUIRE(doc_sents[d] >= 1, "asp_abstracts_plan: document %d has no title element", d);
+        for (int k = 0; k < doc_sents[d]; ++k)
+            ASP_REQUIRE(sent_offsets[first + k] <= sent_offsets[first + k + 1],
+                        "asp_abstracts_plan: sentence offsets must not decrease (document %d, sentence %d)", d, k);
         int total = 0, spans = 0;
         walk_doc(sent_offsets, first, doc_sents[d], budget, [&](int k, int, int take) {
             total += take;
@@ -376,6 +381,10 @@ extern "C" int asp_abstracts_fill(const int32_t* ids, const int64_t* sent_offset
                 "asp_abstracts_fill: bad argument");
     int64_t first = 0;
     for (int d = 0; d < n_docs; ++d) {
+        ASP_REQUIRE(doc_sents[d] >= 1, "asp_abstracts_fill: document %d has no title element", d);
+        for (int k = 0; k < doc_sents[d]; ++k)
+            ASP_REQUIRE(sent_offsets[first + k] <= sent_offsets[first + k + 1],
+                        "asp_abstracts_fill: sentence offsets must not decrease (document %d, sentence %d)", d, k);
         int64_t* row = tokid + (size_t)d * width;
         int32_t* sp = spans + (size_t)d * max_sents * 2;
         for (int s = 0; s < 2 * max_sents; ++s) sp[s] = -1;
