@@ -84,6 +84,7 @@ def lib():
     L.asp_wordpiece_destroy.argtypes = [vp]
     L.asp_wordpiece_set_unicode.argtypes = [vp, vp, vp, vp, vp]
     L.asp_wordpiece_encode.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, vp]
+    L.asp_pack_pool.argtypes = [vp, vp, ci, ci, ci, vp, ci]
     L.asp_abstracts_plan.argtypes = [vp, vp, ci, ci, vp, vp]
     L.asp_abstracts_fill.argtypes = [vp, vp, vp, ci, ci, ci, ci, cll, ci, ci, vp, vp, vp, vp]
     L.asp_ot_score_workspace_bytes.restype = ctypes.c_size_t

@@ -296,6 +296,11 @@ int asp_abstracts_fill(const int32_t* ids, const int64_t* sent_offsets, const in
                        int cls_id, int sep_id, int64_t pad_id, int width, int max_sents, int64_t* tokid, int64_t* seg,
                        int64_t* attn, int32_t* spans);
 
+/* ---- host side of a pool: pad n per-paper encodings into one staging buffer (no GPU involved) ---------------
+ * Replaces the per-candidate padding loop of caching_score (src/learning/facetid_models/disent_models.py:274-290).
+ * srcs[j]: lens[j] rows of D floats, contiguous, host memory; dst: [n, smax, D] floats, rows lens[j]..smax zeroed. */
+int asp_pack_pool(const float* const* srcs, const int32_t* lens, int n, int smax, int D, float* dst, int threads);
+
 #ifdef __cplusplus
 }
 #endif

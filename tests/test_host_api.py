@@ -241,3 +241,36 @@ def test_prepare_abstracts_fast_equals_per_sentence_protocol(tmp_path):
             for k in ("tokid_tt", "seg_tt", "attnmask_tt"):
                 assert torch.equal(fb[k], bb[k])
             assert torch.equal(spans, spans_from_token_idxs(idxs, max(al)))
+
+
+def test_pack_pool_native_gather_matches_padding_loop():
+    """pack_pool (asp_pack_pool behind it) against the per-candidate padding loop it replaces
+    (disent_models.py:274-290): numpy fp32 / fp64 / non-contiguous inputs and torch tensors, ragged lengths, an explicit
+    max_sents, an empty encoding; bad shapes are refused."""
+    from aspire_b200.similarity import pack_pool
+    rng = np.random.default_rng(3)
+    encs = []
+    for j in range(257):
+        s = int(rng.integers(0 if j == 5 else 1, 11))
+        a = rng.standard_normal((s, 768))
+        kind = j % 4
+        if kind == 0:
+            encs.append(a.astype(np.float32))
+        elif kind == 1:
+            encs.append(a)                                                   # float64, as np.load of a reps file gives
+        elif kind == 2:
+            encs.append(torch.from_numpy(a.astype(np.float32)))
+        else:
+            encs.append(np.asfortranarray(a.astype(np.float32)))             # not C-contiguous
+    for max_sents in (None, 12):
+        got, lens = pack_pool(encs, "cpu", max_sents=max_sents)
+        smax = max_sents or max(int(e.shape[0]) for e in encs)
+        want = torch.zeros((len(encs), smax, 768), dtype=torch.float32)
+        for j, e in enumerate(encs):
+            want[j, :e.shape[0]] = torch.as_tensor(np.asarray(e), dtype=torch.float32)
+        assert got.shape == want.shape and torch.equal(got, want)
+        assert lens.dtype == torch.int32 and lens.tolist() == [int(e.shape[0]) for e in encs]
+    with pytest.raises(Exception):
+        pack_pool(encs, "cpu", max_sents=4)                                  # an encoding longer than max_sents
+    with pytest.raises(ValueError):
+        pack_pool([np.zeros((3, 768), np.float32), np.zeros((2, 700), np.float32)], "cpu")
