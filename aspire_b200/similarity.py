@@ -113,6 +113,15 @@ class SimilarityModel(metaclass=ABCMeta):
             self.cache.close()
 
 
+def _pad_tensors(encs, device, smax, D):
+    """[S_j, D] tensors -> zero-padded fp32 [N, smax, D] on ``device`` with torch ops only (encodings already on the GPU)."""
+    moved = [e.detach().to(device=device, dtype=torch.float32) for e in encs]
+    padded = torch.nn.utils.rnn.pad_sequence(moved, batch_first=True)
+    out = torch.zeros((len(encs), smax, D), dtype=torch.float32, device=device)
+    out[:, :padded.shape[1]] = padded
+    return out
+
+
 def pack_pool(cand_encs, device, max_sents=None):
     """list of [S_j, D] encodings (torch / numpy) -> (fp32 [N, Smax, D] zero padded on ``device``, int32 lens [N]).
 
@@ -125,11 +134,7 @@ def pack_pool(cand_encs, device, max_sents=None):
     D = int(cand_encs[0].shape[1])
     lens_t = torch.tensor(lens, dtype=torch.int32)
     if all(isinstance(e, Tensor) and e.is_cuda for e in cand_encs):
-        dev_encs = [e.detach().to(device=device, dtype=torch.float32) for e in cand_encs]
-        out = torch.zeros((n, smax, D), dtype=torch.float32, device=device)
-        padded = torch.nn.utils.rnn.pad_sequence(dev_encs, batch_first=True)
-        out[:, :padded.shape[1]] = padded
-        return out, lens_t.to(device, non_blocking=True)
+        return _pad_tensors(cand_encs, device, smax, D), lens_t.to(device, non_blocking=True)
     keep, ptrs = [], np.empty(n, dtype=np.uintp)  # `keep` holds the converted copies alive until the gather is done
     for j, e in enumerate(cand_encs):
         if isinstance(e, Tensor):

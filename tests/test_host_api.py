@@ -270,6 +270,10 @@ def test_pack_pool_native_gather_matches_padding_loop():
             want[j, :e.shape[0]] = torch.as_tensor(np.asarray(e), dtype=torch.float32)
         assert got.shape == want.shape and torch.equal(got, want)
         assert lens.dtype == torch.int32 and lens.tolist() == [int(e.shape[0]) for e in encs]
+        # the branch taken for GPU-resident encodings (torch ops only) must produce the same buffer
+        from aspire_b200.similarity import _pad_tensors
+        as_tensors = [torch.as_tensor(np.asarray(e), dtype=torch.float32) for e in encs]
+        assert torch.equal(_pad_tensors(as_tensors, "cpu", smax, 768), want)
     with pytest.raises(Exception):
         pack_pool(encs, "cpu", max_sents=4)                                  # an encoding longer than max_sents
     with pytest.raises(ValueError):
