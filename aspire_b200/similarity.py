@@ -127,7 +127,7 @@ def pack_pool(cand_encs, device, max_sents=None):
 
     Encodings that already live on the GPU are padded there; host encodings are gathered into one (pinned) staging
     buffer by ``asp_pack_pool`` -- a few memcpy threads instead of the per-candidate Python loop of ``caching_score``
-    (disent_models.py:274-290), which at 1 000 candidates costs 50-70 ms in front of a 0.05 ms kernel."""
+    (disent_models.py:274-290), which at 1 000 candidates costs 13-17 ms (3-4 ms here) in front of a 0.05 ms kernel."""
     n = len(cand_encs)
     lens = [int(e.shape[0]) for e in cand_encs]
     smax = max_sents or max(lens)
