@@ -10,6 +10,8 @@ Mirrors the release API of the reference, keyword for keyword:
 The pooling step (K1) runs in the CUDA library (``asp_span_mean_pool``): sentence spans are contiguous token
 ranges, so the kernel takes ``(start, end)`` pairs instead of the reference's dense [B,L,768] float64 masks.
 """
+import threading
+
 import numpy as np
 import torch
 from torch import nn
@@ -205,6 +207,7 @@ class NativeWordPiece:
         self.threads = int(threads or min(16, os.cpu_count() or 1))
         self.tokenizer = tokenizer
         self._unicode = False
+        self._install_lock = threading.Lock()
         self._lib = _abi.lib()
         self._handle = self._lib.asp_wordpiece_create(blob, offsets.ctypes.data, len(encoded), int(bool(norm.get("lowercase", True))),
                                                       int(vocab[model["unk_token"]]), special_ids.ctypes.data, len(special_ids))
@@ -272,7 +275,9 @@ class NativeWordPiece:
         todo = np.flatnonzero(fallback[:n])
         if len(todo) and self._unicode is False:  # None = tried and unavailable
             # first non-ASCII sentence: give the library the tokenizer's own per-character tables and run it again
-            self._install_unicode()
+            with self._install_lock:
+                if self._unicode is False:
+                    self._install_unicode()
             if self._unicode:
                 return self.encode(sentences)
         ids = ids[:out_offsets[-1]]

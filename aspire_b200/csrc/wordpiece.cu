@@ -20,6 +20,7 @@
 // tokenizer.  No CUDA in this file; it lives in the same library so the ctypes binding and the error convention are
 // shared.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <string>
 #include <string_view>
@@ -39,7 +40,7 @@ struct asp_wordpiece {
     // normaliser turns each character into (lower-casing, accent stripping, text cleaning, spaces around CJK ...), how
     // the pre-tokenizer classes each character (0 word, 1 space, 2 punctuation), and which characters must be left to
     // the original tokenizer because their treatment depends on context.
-    bool unicode = false;
+    std::atomic<bool> unicode{false};  // published with release order once the tables below are complete
     std::vector<uint32_t> norm_offsets;  // 65537
     std::string norm_blob;
     std::vector<uint8_t> out_class, fallback;  // 65536 each
@@ -91,7 +92,7 @@ int64_t encode_sentence_unicode(const asp_wordpiece& wp, const char* s, size_t n
 
 int64_t encode_sentence(const asp_wordpiece& wp, const char* s, size_t n, size_t max_chars, int32_t* out) {
     for (size_t i = 0; i < n; ++i)
-        if ((unsigned char)s[i] >= 0x80) return wp.unicode ? encode_sentence_unicode(wp, s, n, max_chars, out) : -1;
+        if ((unsigned char)s[i] >= 0x80) return wp.unicode.load(std::memory_order_acquire) ? encode_sentence_unicode(wp, s, n, max_chars, out) : -1;
     int32_t* const base = out;
     std::string word;
     word.reserve(64);
@@ -283,13 +284,15 @@ extern "C" void asp_wordpiece_destroy(asp_wordpiece* wp) { delete wp; }
 extern "C" int asp_wordpiece_set_unicode(asp_wordpiece* wp, const uint32_t* norm_offsets, const char* norm_blob,
                                          const uint8_t* out_class, const uint8_t* fallback) {
     ASP_REQUIRE(wp && norm_offsets && norm_blob && out_class && fallback, "asp_wordpiece_set_unicode: NULL argument");
+    // the tables are a function of the tokenizer: installed once, never replaced (other threads may be reading them)
+    if (wp->unicode.load(std::memory_order_acquire)) return ASP_OK;
     for (int cp = 0; cp < 0x10000; ++cp)
         ASP_REQUIRE(norm_offsets[cp] <= norm_offsets[cp + 1], "asp_wordpiece_set_unicode: offsets must not decrease (at U+%04X)", cp);
     wp->norm_offsets.assign(norm_offsets, norm_offsets + 0x10001);
     wp->norm_blob.assign(norm_blob, norm_offsets[0x10000]);
     wp->out_class.assign(out_class, out_class + 0x10000);
     wp->fallback.assign(fallback, fallback + 0x10000);
-    wp->unicode = true;
+    wp->unicode.store(true, std::memory_order_release);
     return ASP_OK;
 }
 

@@ -220,3 +220,20 @@ def test_context_ner_entity_positions_batched_equals_per_call(tmp_path):
     got, want = fast._get_ner_token_idxs(batch, sent_idxs), slow._get_ner_token_idxs(batch, sent_idxs)
     assert got == want
     assert sum(len(x) > 0 for doc in want for x in doc) > 20 and sum(len(x) == 0 for doc in want for x in doc) > 5
+
+
+def test_native_prep_is_reentrant(tmp_path):
+    """encode_stream prepares batches on worker threads: concurrent calls on ONE tokenizer (one shared native handle,
+    Unicode tables installed lazily by whichever thread meets the first non-ASCII sentence) must each return what a
+    serial call returns."""
+    from concurrent.futures import ThreadPoolExecutor
+    from aspire_b200.consent import prepare_abstracts_fast, prepare_abstracts_native
+    tok, words = _tokenizer(tmp_path)
+    rnd = random.Random(123)
+    batches = [[{"TITLE": " ".join(_random_word(rnd, words) for _ in range(rnd.randint(1, 10))),
+                 "ABSTRACT": [" ".join([rnd.choice(words)] + [_random_word(rnd, words) for _ in range(rnd.randint(0, 60))])
+                              for _ in range(rnd.randint(1, 20))]} for _ in range(rnd.randint(1, 8))] for _ in range(48)]
+    with ThreadPoolExecutor(max_workers=6) as pool:
+        got = list(pool.map(lambda b: prepare_abstracts_native(b, tok), batches))
+    for b, g in zip(batches, got):
+        _same(prepare_abstracts_fast(b, tok), g)
