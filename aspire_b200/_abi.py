@@ -57,6 +57,7 @@ def lib():
     L.asp_pair_cost.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp]
     L.asp_l2max.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
     L.asp_pair_heads.argtypes = [vp, vp, ci, vp, ci, ci, ci, cf, vp, vp, vp, vp]
+    L.asp_mix_cls_scores.argtypes = [vp, vp, ci, vp, ci, ci, cf, cf, vp]
     L.asp_ot_sinkhorn.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, vp,
                                   ctypes.POINTER(AspOtOutputs), vp]
     L.asp_ot_score.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, ctypes.POINTER(AspOtOutputs), vp,

@@ -91,6 +91,17 @@ int pair_cost_launch(const float* q, const int32_t* q_lens, int q_group, const f
 int launch_sinkhorn(const float* cost, const int32_t* q_lens, int q_group, const int32_t* c_lens, int B, int Sq, int Sc,
                     const EpsSched& sched, float temp, const OtOut& out, cudaStream_t stream);
 int make_sched(const float* eps_host, int n_eps, EpsSched* s);
+// long / ragged documents (<= 32 x 32 sentences): cost tile + Sinkhorn (or the tsAspire max) in one kernel (ot_varlen.cu)
+extern int g_ot_varlen;  // asp_set_option("ot_varlen")
+extern int g_vl_flags;   // asp_set_option("vl_flags")
+bool ot_varlen_supported(int Sq, int Sc, int D);
+int ot_varlen_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
+                     const int32_t* c_index, int B, int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int l2max_varlen_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens, int B,
+                        int Sq, int Sc, int D, float* best, int32_t* flat_idx, float* pair_sims, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
+size_t ot_varlen_workspace_bytes(int B);  // scratch for the shape sort (0: batch too small to bother)
 OtOut to_out(const asp_ot_outputs* o);
 
 // ---- device math ------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 // Epilogue: each thread owns one query-sentence row of the accumulator: d^2 = |q|^2 + |c|^2 - 2 q.c, running
 // (min d^2, first j) per candidate document -> shared memory -> min over the query document's rows (first i on ties,
 // i.e. the flat index i*S+j of the first maximum, pair_distances.py:176) -> score = -sqrt(max(d^2, 1e-8)).
+#include <algorithm>
 #include "common.cuh"
 #include "bert/tc05.cuh"
 
@@ -187,7 +188,6 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
                 if (++j == S) {  // candidate document finished
                     ep_d2[r * 17 + (cdoc & 15)] = best;
                     ep_j[r * 17 + (cdoc & 15)] = best_j;
-                    // more than 16 documents per tile (S < 10) are flushed in rounds of 16 below
                     best = INFINITY;
                     best_j = 0;
                     j = 0;
@@ -249,7 +249,7 @@ extern "C" int asp_l2max_allpairs(const float* q, const int32_t* q_lens, int NQ,
                                   size_t workspace_bytes, asp_stream_t stream_) {
     using namespace asp;
     ASP_REQUIRE(q && c && q_lens && c_lens && scores, "asp_l2max_allpairs: NULL pointer");
-    ASP_REQUIRE(NQ >= 0 && NC >= 0 && S >= 10 && S <= 64, "asp_l2max_allpairs: sentences per document must be in [10, 64] (got %d)", S);
+    ASP_REQUIRE(NQ >= 0 && NC >= 0 && S >= 1 && S <= 64, "asp_l2max_allpairs: sentences per document must be in [1, 64] (got %d)", S);
     ASP_REQUIRE(D >= 64 && (D % 64) == 0, "asp_l2max_allpairs: D must be a multiple of 64 (got %d)", D);
     ASP_REQUIRE(aligned16(q) && aligned16(c), "asp_l2max_allpairs: q/c must be 16-byte aligned");
     ASP_REQUIRE(workspace && workspace_bytes >= asp_l2max_allpairs_workspace_bytes(NQ, NC, S, D),
@@ -269,7 +269,9 @@ extern "C" int asp_l2max_allpairs(const float* q, const int32_t* q_lens, int NQ,
     ASP_LAUNCH_CHECK("split_rows_kernel");
     split_rows_kernel<<<(unsigned)((crows + 3) / 4), 128, 0, stream>>>(c, (long long)crows, D, c_hi, c_lo, cn);
     ASP_LAUNCH_CHECK("split_rows_kernel");
-    const int docs_m = kApBlockM / S, docs_n = kApBlockN / S;
+    // whole documents per tile; the epilogue keeps at most 16 candidate documents per tile (short documents, S < 10 --
+    // CSFCube abstracts average 7 sentences -- simply leave the tile's last columns unused)
+    const int docs_m = kApBlockM / S, docs_n = std::min(kApBlockN / S, 16);
     CUtensorMap tq_hi, tq_lo, tc_hi, tc_lo;
     int rc;
     if ((rc = make_tmap_bf16_k32(&tq_hi, q_hi, qrows, D, docs_m * S))) return rc;

@@ -712,6 +712,7 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
 
 extern "C" size_t asp_ot_score_workspace_bytes(int B, int Sq, int Sc, int D) {
     if (asp::ot_fused_supported(Sq, Sc, D) && asp::g_ot_kernel != 1) return 0;
+    if (asp::ot_varlen_supported(Sq, Sc, D) && asp::g_ot_kernel == 0) return asp::ot_varlen_workspace_bytes(B);
     return (size_t)B * Sq * Sc * sizeof(float);
 }
 
@@ -736,6 +737,9 @@ extern "C" int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, 
     if (asp::ot_fused_supported(Sq, Sc, D) && asp::g_ot_kernel != 1)
         return asp::ot_fused_launch(q, q_lens, q_group, c, c_lens, nullptr, B, Sq, Sc, D, sched, temp, o,
                                     (cudaStream_t)stream);
+    if (asp::ot_varlen_supported(Sq, Sc, D) && asp::g_ot_kernel == 0)
+        return asp::ot_varlen_launch(q, q_lens, q_group, c, c_lens, nullptr, B, Sq, Sc, D, sched, temp, o, workspace,
+                                     workspace_bytes, (cudaStream_t)stream);
     const size_t need = (size_t)B * Sq * Sc * sizeof(float);
     ASP_REQUIRE(workspace && workspace_bytes >= need, "asp_ot_score: workspace of %zu bytes needed for %dx%d sentences",
                 need, Sq, Sc);
@@ -774,13 +778,17 @@ extern "C" int asp_ot_score_indexed(const float* q, const int32_t* q_lens, int q
     if (rc) return rc;
     ASP_REQUIRE(out && c_index, "asp_ot_score_indexed: out / c_index is NULL");
     ASP_REQUIRE(q_group >= 1 && temp > 0.f, "asp_ot_score_indexed: q_group >= 1 and temp > 0 required");
-    if (!asp::ot_fused_supported(Sq, Sc, D)) {
+    const bool fused = asp::ot_fused_supported(Sq, Sc, D);
+    if (!fused && !asp::ot_varlen_supported(Sq, Sc, D)) {
         asp::set_error("asp_ot_score_indexed: %dx%d sentences, D=%d is not a fused shape", Sq, Sc, D);
         return ASP_ERR_UNSUPPORTED;
     }
     asp::EpsSched sched;
     rc = asp::make_sched(eps_host, n_eps, &sched);
     if (rc) return rc;
+    if (!fused)
+        return asp::ot_varlen_launch(q, q_lens, q_group, c, c_lens, c_index, B, Sq, Sc, D, sched, temp, asp::to_out(out),
+                                     nullptr, 0, (cudaStream_t)stream);
     return asp::ot_fused_launch(q, q_lens, q_group, c, c_lens, c_index, B, Sq, Sc, D, sched, temp, asp::to_out(out),
                                 (cudaStream_t)stream);
 }

@@ -236,6 +236,9 @@ extern "C" int asp_l2max(const float* q, const int32_t* q_lens, int q_broadcast,
     if (rc) return rc;
     ASP_REQUIRE(best, "asp_l2max: best is NULL");
     if (B == 0) return ASP_OK;
+    if ((Sq > 10 || Sc > 10) && asp::ot_varlen_supported(Sq, Sc, D))  // long documents: rows staged once, no re-reads
+        return asp::l2max_varlen_launch(q, q_lens, q_broadcast ? B : 1, c, c_lens, B, Sq, Sc, D, best, flat_idx, pair_sims,
+                                        nullptr, 0, (cudaStream_t)stream);
     return asp::launch_pair_cost<asp::MODE_L2MAX>(q, q_lens, q_broadcast ? B : 1, c, c_lens, B, Sq, Sc, D, pair_sims, best,
                                                   flat_idx, (cudaStream_t)stream);
 }

@@ -70,7 +70,38 @@ pair_heads_kernel(const float* __restrict__ cost, const int32_t* __restrict__ q_
     }
 }
 
+// caching_score's score mixing (disent_models.py:298-307): scores[b] = sent_prop * scores[b] +
+// abs_prop * (-|| q_cls - c_cls[b] + 1e-6 ||_2), the second term being -functional.pairwise_distance(p=2) of the CLS
+// vectors (eps = 1e-6 added to the difference, as torch does).  One warp per candidate.
+__global__ void __launch_bounds__(128)
+mix_cls_kernel(float* __restrict__ scores, const float* __restrict__ q_cls, int q_group, const float* __restrict__ c_cls,
+               int B, int D, float sent_prop, float abs_prop) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float* qv = q_cls + (size_t)(b / q_group) * D;
+    const float* cv = c_cls + (size_t)b * D;
+    float acc = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float d = qv[k] - cv[k] + 1e-6f;
+        acc = fmaf(d, d, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) scores[b] = sent_prop * scores[b] + abs_prop * (-sqrtf(acc));
+}
+
 }  // namespace asp
+
+extern "C" int asp_mix_cls_scores(float* scores, const float* q_cls, int q_group, const float* c_cls, int B, int D,
+                                  float sent_prop, float abs_prop, asp_stream_t stream) {
+    ASP_REQUIRE(scores && q_cls && c_cls, "asp_mix_cls_scores: NULL pointer");
+    ASP_REQUIRE(B >= 0 && D >= 1 && q_group >= 1, "asp_mix_cls_scores: bad shape B=%d D=%d q_group=%d", B, D, q_group);
+    if (B == 0) return ASP_OK;
+    asp::mix_cls_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(scores, q_cls, q_group, c_cls, B, D, sent_prop,
+                                                                      abs_prop);
+    ASP_LAUNCH_CHECK("mix_cls_kernel");
+    return ASP_OK;
+}
 
 extern "C" int asp_pair_heads(const float* cost, const int32_t* q_lens, int q_group, const int32_t* c_lens, int B, int Sq,
                               int Sc, float temp, float* top2, float* att, float* att_probs, asp_stream_t stream) {

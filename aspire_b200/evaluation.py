@@ -88,7 +88,7 @@ def score(model: SimilarityModel, dataset, facet, scores_filename, mode='batched
         query_encoding = model.get_encoding(pids=[query_pid], dataset=dataset)[query_pid]
         if facet is not None:
             query_encoding = model.get_faceted_encoding(query_encoding, facet, dataset.get(query_pid))
-        candidate_pids = query_pool['cands']
+        candidate_pids = list(dict.fromkeys(query_pool['cands']))  # a pid listed twice is ranked once (dict, evaluate.py:71-76)
         candidate_encodings = model.get_encoding(pids=candidate_pids, dataset=dataset)
         if mode == 'batched' and hasattr(model, 'score_pool'):
             sims = model.score_pool(query_encoding, [candidate_encodings[c] for c in candidate_pids]).tolist()
@@ -132,7 +132,20 @@ class CachingScoringModel:
         self.pid2model_reps = {}
 
     def save_cache(self, out_fname):
-        np.savez(out_fname, **{f"{p}::{k}": v for p, d in self.pid2model_reps.items() for k, v in d.items()})
+        """pp_gen_nearest.py:125-129: the whole ``pid2model_reps`` dict as one gzip-compressed joblib pickle."""
+        import joblib
+        joblib.dump(self.pid2model_reps, out_fname, compress=('gzip', 3))
+
+    def load_cache(self, fname):
+        """Read a ``pid2model_reps`` pickle written by ``save_cache`` here or by the reference
+        ({pid: {'doc_cls_reps': np [D], 'sent_reps': np [S, D]}}, disent_models.py:365-371); documents already in the
+        cache keep their entries.  Returns the number of documents read."""
+        import joblib
+        reps = joblib.load(fname)
+        for pid, d in reps.items():
+            assert 'sent_reps' in d and np.asarray(d['sent_reps']).ndim == 2, f"{fname}: entry {pid} is not a cached encoding"
+            self.pid2model_reps.setdefault(pid, d)
+        return len(reps)
 
     def _encode_missing(self, pids, pid2abstract):
         missing = [p for p in pids if p not in self.pid2model_reps]
@@ -240,7 +253,7 @@ def rank_pool_sent(root_path, reps_path, dataset, data_to_read='sent', score_typ
     dev = torch.device("cuda", torch.cuda.current_device())
     ranked = collections.OrderedDict()
     for qpid, pool in qpid2pool.items():
-        cand_pids = pool['cands']
+        cand_pids = list(dict.fromkeys(pool['cands']))  # cand_sims is a dict in the reference (:947-969)
         q_rows = [docsent2idx[f'{qpid}-{i}'] for i in range(n_sents[qpid])]
         q = torch.from_numpy(all_reps[q_rows])[None].to(dev).contiguous()
         q_lens = torch.tensor([len(q_rows)], dtype=torch.int32, device=dev)
@@ -256,6 +269,64 @@ def rank_pool_sent(root_path, reps_path, dataset, data_to_read='sent', score_typ
     if write:
         name = rep_type or os.path.basename(os.path.normpath(reps_path))
         out_fname = os.path.join(reps_path, f'test-pid2pool-{dataset}{split}-{name}-ranked.json')
+        with codecs.open(out_fname, 'w', 'utf-8') as fp:
+            json.dump(ranked, fp)
+        logging.info(f'Wrote: {out_fname}')
+    return ranked
+
+
+def rank_pool_sent_treccovid(root_path, reps_path, dataset, data_to_read='sent', score_type='l2max', rep_type=None,
+                             write=True, cand_chunk=16384):
+    """Deep, overlapping pools (TREC-COVID: every query against most of the corpus): ``rank_pool_sent_treccovid`` of
+    src/pre_process/pp_gen_nearest.py:729-860.  The reference computes ONE all-query-sentences x all-corpus-sentences
+    ``-cdist`` (:788-795) and slices it per pool (:816); here every query document is scored against every document
+    that occurs in any pool by the tensor-core all-pairs kernel (``asp_l2max_allpairs``, chunks of ``cand_chunk``
+    documents), and a pool's scores are a gather from that [queries, documents] matrix.
+
+    Same files, same output format and tie order as ``rank_pool_sent``; as in the reference a candidate listed twice
+    in a pool is ranked once (its ``cand_sims`` is a dict, :823-848).  ``score_type``: 'l2max' / 'l2lse' (the max over
+    sentence pairs; other aggregations go through ``rank_pool_sent``).
+    """
+    from .distances import l2max_allpairs
+    if score_type not in {'l2max', 'l2lse'}:
+        raise ValueError(f'Unknown score type: {score_type}')
+    with codecs.open(os.path.join(root_path, f'test-pid2anns-{dataset}.json'), 'r', 'utf-8') as fp:
+        qpid2pool = json.load(fp)
+    with codecs.open(os.path.join(reps_path, f'pid2idx-{dataset}-sent.json'), 'r', 'utf-8') as fp:
+        docsent2idx = json.load(fp)
+    all_reps = np.nan_to_num(np.load(os.path.join(reps_path, f'{dataset}-{data_to_read}.npy')).astype(np.float32))
+    n_sents = {}
+    with codecs.open(os.path.join(root_path, f'abstracts-{dataset}.jsonl'), 'r', 'utf-8') as fh:
+        for line in fh:
+            if line.strip():
+                rec = json.loads(line)
+                n_sents[rec['paper_id']] = len(rec['abstract'])
+    query_pids = list(qpid2pool)
+    pools = {q: list(dict.fromkeys(qpid2pool[q]['cands'])) for q in query_pids}
+    docs = list(dict.fromkeys(c for q in query_pids for c in pools[q]))  # union of the pools, first-seen order
+    col_of = {c: i for i, c in enumerate(docs)}
+    S = max([n_sents[p] for p in query_pids + docs] + [1])
+    D = all_reps.shape[1]
+    if S > 64 or D % 64 != 0:  # outside the all-pairs kernel's tiles: one launch per pool instead
+        return rank_pool_sent(root_path, reps_path, dataset, data_to_read, 'l2max', '', rep_type, write)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def pack(pids):
+        return pack_pool([all_reps[[docsent2idx[f'{p}-{i}'] for i in range(n_sents[p])]] for p in pids], dev, max_sents=S)
+    q, q_lens = pack(query_pids)
+    sims = torch.empty((len(query_pids), len(docs)), dtype=torch.float32, device=dev)
+    for s0 in range(0, len(docs), cand_chunk):
+        c, c_lens = pack(docs[s0:s0 + cand_chunk])
+        sims[:, s0:s0 + c.shape[0]] = l2max_allpairs(q, q_lens, c, c_lens, want_idx=False)[0]
+    sims = sims.cpu().numpy()
+    ranked = collections.OrderedDict()
+    for qi, qpid in enumerate(query_pids):
+        cand_pids = pools[qpid]
+        row = sims[qi, [col_of[c] for c in cand_pids]]
+        ranked[qpid] = [(cpid, -1 * s) for cpid, s in rank_candidates(cand_pids, row)]
+    if write:
+        name = rep_type or os.path.basename(os.path.normpath(reps_path))
+        out_fname = os.path.join(reps_path, f'test-pid2pool-{dataset}-{name}-ranked.json')
         with codecs.open(out_fname, 'w', 'utf-8') as fp:
             json.dump(ranked, fp)
         logging.info(f'Wrote: {out_fname}')

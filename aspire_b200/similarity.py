@@ -24,26 +24,87 @@ from .distances import (AllPairMaskedWasserstein, bbox_diameter, epsilon_schedul
                         rep_len_tup)
 
 
-class EncodingsCache(dict):
-    """{paper_id: encoding} with the three h5py.File members the reference touches (utils/models.py:76-95,112-114).
+_HDF5_MAGIC = b"\x89HDF\r\n\x1a\n"
 
-    h5py is not a dependency here; the cache persists as one ``.npz`` when a filename is given.
+
+def _h5py_or_none():
+    try:
+        import h5py  # the reference's cache format (utils/models.py:76-81); optional here
+        return h5py
+    except ImportError:
+        return None
+
+
+class EncodingsCache:
+    """{paper_id: fp32 encoding [S, D]} -- the encodings cache of src/evaluation/utils/models.py:68-124.
+
+    The reference's cache is an ``h5py.File(cache_filename, 'a')`` with one dataset per paper id (:76-95, read back at
+    :112-114).  When h5py is importable this class opens exactly that file (same open modes, same fallback to 'w' on
+    a corrupt file), so caches written by the reference are read and vice versa.  Without h5py the cache persists as
+    one ``.npz`` beside the requested name (``encodings.h5`` -> ``encodings.h5.npz``; the SAME path is used to load
+    and to save), written only when something changed; an existing HDF5 file that cannot be read without h5py raises
+    instead of being silently re-encoded.  Members: the ones the callers touch -- ``in``, ``get``, ``[]``, ``keys``,
+    ``create_dataset(name=, data=)``, ``close``.
     """
 
     def __init__(self, filename=None):
-        super().__init__()
         self.filename = filename
-        if filename and os.path.exists(filename):
-            with np.load(filename, allow_pickle=False) as z:
-                for k in z.files:
-                    self[k] = z[k]
+        self._mem, self._h5, self._dirty, self.path = {}, None, False, None
+        if not filename:
+            return
+        h5py = _h5py_or_none()
+        if h5py is not None and not filename.endswith(".npz"):
+            try:
+                self._h5 = h5py.File(filename, 'a')
+            except Exception:
+                logging.info(f"Error: could not open encodings cache {filename}.\nOverwriting the cache.")
+                self._h5 = h5py.File(filename, 'w')
+            return
+        self.path = filename if filename.endswith(".npz") else filename + ".npz"
+        if self.path != filename and os.path.exists(filename):
+            with open(filename, "rb") as fh:
+                if fh.read(8) == _HDF5_MAGIC:
+                    raise _abi.AspireB200Error(f"{filename} is an HDF5 encodings cache; install h5py to read it")
+        if os.path.exists(self.path):
+            with np.load(self.path, allow_pickle=False) as z:
+                names = [str(k) for k in z["__keys__"]] if "__keys__" in z.files else None
+                if names is None:  # archives of the first layout: one entry per paper id
+                    self._mem = {k: z[k] for k in z.files}
+                else:
+                    self._mem = {name: z[f"a{i}"] for i, name in enumerate(names)}
+
+    def __contains__(self, pid):
+        return pid in (self._h5 if self._h5 is not None else self._mem)
+
+    def __len__(self):
+        return len(self._h5 if self._h5 is not None else self._mem)
+
+    def keys(self):
+        return (self._h5 if self._h5 is not None else self._mem).keys()
+
+    def get(self, pid, default=None):
+        store = self._h5 if self._h5 is not None else self._mem
+        return store[pid] if pid in store else default
+
+    def __getitem__(self, pid):
+        return (self._h5 if self._h5 is not None else self._mem)[pid]
 
     def create_dataset(self, name, data):
-        self[name] = data.detach().cpu().numpy() if isinstance(data, Tensor) else np.asarray(data)
+        arr = data.detach().cpu().numpy() if isinstance(data, Tensor) else np.asarray(data)
+        if self._h5 is not None:
+            self._h5.create_dataset(name=name, data=arr)
+        else:
+            self._mem[name] = arr
+            self._dirty = True
 
     def close(self):
-        if self.filename:
-            np.savez(self.filename if self.filename.endswith(".npz") else self.filename + ".npz", **self)
+        if self._h5 is not None:
+            self._h5.close()
+            self._h5 = None
+        elif self.path and self._dirty:
+            names = list(self._mem)  # paper ids are data, not keyword names: stored as an array beside a0, a1, ...
+            np.savez(self.path, __keys__=np.asarray(names, dtype=str), **{f"a{i}": self._mem[n] for i, n in enumerate(names)})
+            self._dirty = False
 
 
 def batchify(dataset: Dict, batch_size: int):
@@ -506,35 +567,83 @@ def get_model(model_name, trained_model_path=None) -> SimilarityModel:
     raise NotImplementedError(f"No Implementation for model {model_name}")
 
 
+def _mix_scores(scores, query_encode_ret_dict, cand_encode_ret_dicts, sent_loss_prop, abs_loss_prop, dev):
+    """disent_models.py:298-307: sent_loss_prop * sentence score (+ abs_loss_prop * -||cls_q - cls_c||) -> np [B]."""
+    if sent_loss_prop == 1.0 and not abs_loss_prop > 0.0:
+        return scores.cpu().numpy()
+    B = scores.shape[0]
+    if abs_loss_prop > 0.0:
+        qc = torch.as_tensor(np.asarray(query_encode_ret_dict['doc_cls_reps']), dtype=torch.float32).to(dev).view(1, -1).contiguous()
+        cc = torch.as_tensor(np.stack([np.asarray(d['doc_cls_reps']) for d in cand_encode_ret_dicts]),
+                             dtype=torch.float32).to(dev).contiguous()
+    else:  # only the scaling: the CLS term is multiplied by exactly 0 (any finite vectors do)
+        qc = torch.zeros((1, 4), dtype=torch.float32, device=dev)
+        cc = torch.zeros((B, 4), dtype=torch.float32, device=dev)
+    scores = scores.contiguous()
+    _abi.check(_abi.lib().asp_mix_cls_scores(_abi.ptr(scores), _abi.ptr(qc), max(B, 1), _abi.ptr(cc), B, int(cc.shape[1]),
+                                             float(sent_loss_prop), float(max(abs_loss_prop, 0.0)), _abi.stream_of(dev)),
+               "asp_mix_cls_scores")
+    return scores.cpu().numpy()
+
+
 def caching_score(query_encode_ret_dict, cand_encode_ret_dicts, score_agg_type='l2wasserstein',
-                  model_hparams=None):
+                  model_hparams=None, sent_loss_prop=None, abs_loss_prop=None):
     """Batched 1 x B scorer with the calling convention of WordSentAlignBiEnc.caching_score
-    (src/learning/facetid_models/disent_models.py:256-342; sent_loss_prop=1, abs_loss_prop=0).
+    (src/learning/facetid_models/disent_models.py:256-342).
 
     :param query_encode_ret_dict: {'sent_reps': np [Sq,D], 'doc_cls_reps': np [D]}
     :param cand_encode_ret_dicts: list of such dicts
+    :param score_agg_type: 'l2wasserstein' | 'l2max' | 'l2lse' (scored as l2max, :294-295) | 'l2top2' | 'l2attention'
+    :param sent_loss_prop, abs_loss_prop: the mixing weights of :298-307 -- batch_scores = sent_loss_prop * sentence
+        score + abs_loss_prop * (-||cls_q - cls_c||_2) when abs_loss_prop > 0.  Default: ``model_hparams``'
+        'sent_loss_prop' (or 'sentsup_loss_prop' if larger, :300-303) and 'abs_loss_prop', else 1 and 0 (the values
+        WordSentAlignBiEnc hard-codes, :253-254).
     :return: {'batch_scores': np [B], 'pair_scores': list of un-padded per-pair outputs}
         l2wasserstein -> pair_scores[i] = [alpha[:ql], beta[:cl], -C[:ql,:cl], plan[:ql,:cl], plan*-C[:ql,:cl]]
-        l2max         -> pair_scores[i] = -dist[:ql,:cl]
+        l2max, l2top2 -> pair_scores[i] = -dist[:ql,:cl]
+        l2attention   -> pair_scores[i] = [-dist[:ql,:cl], softmax[:ql,:cl], softmax*-dist[:ql,:cl]]
     """
     hp = dict(model_hparams or {})
+    if sent_loss_prop is None:
+        sent_loss_prop = max(float(hp.get('sent_loss_prop', 1.0)), float(hp['sentsup_loss_prop'])) \
+            if 'sentsup_loss_prop' in hp else float(hp.get('sent_loss_prop', 1.0))
+    if abs_loss_prop is None:
+        abs_loss_prop = float(hp.get('abs_loss_prop', 0.0))
     dev = torch.device("cuda", torch.cuda.current_device())
     c, c_lens = pack_pool([d['sent_reps'] for d in cand_encode_ret_dicts], dev)
     q = torch.as_tensor(np.asarray(query_encode_ret_dict['sent_reps']), dtype=torch.float32).to(dev)[None].contiguous()
     qn = q.shape[1]
     q_lens = torch.tensor([qn], dtype=torch.int32, device=dev)
     lens = c_lens.cpu().tolist()
-    if score_agg_type == 'l2max':
+
+    def mixed(t):
+        return _mix_scores(t, query_encode_ret_dict, cand_encode_ret_dicts, sent_loss_prop, abs_loss_prop, dev)
+    if score_agg_type in ('l2max', 'l2lse'):
         best, _idx, sims = l2max_scores(q, q_lens, c, c_lens, broadcast_query=True, want_pair_sims=True)
         sims = sims.cpu().numpy()
-        return {'batch_scores': best.cpu().numpy(), 'pair_scores': [sims[i, :qn, :n] for i, n in enumerate(lens)]}
+        return {'batch_scores': mixed(best), 'pair_scores': [sims[i, :qn, :n] for i, n in enumerate(lens)]}
+    if score_agg_type in ('l2top2', 'l2attention'):
+        from .distances import pair_heads
+        B = c.shape[0]
+        qrep, qlrep = q.expand(B, -1, -1).contiguous(), q_lens.expand(B).contiguous()
+        if score_agg_type == 'l2top2':
+            if qn * c.shape[1] < 2:
+                raise RuntimeError("selected index k out of range")  # torch.topk(k=2) over one entry (pair_distances.py:336)
+            res = pair_heads(qrep, qlrep, c, c_lens, want=("top2",))
+            neg = (-res["dist"]).cpu().numpy()
+            return {'batch_scores': mixed(res["top2"]), 'pair_scores': [neg[i, :qn, :n] for i, n in enumerate(lens)]}
+        res = pair_heads(qrep, qlrep, c, c_lens, temp=hp.get('cdatt_sm_temp', 1.0), want=("att", "att_probs"), raw_pads=True)
+        neg, probs = (-res["dist"]).cpu().numpy(), res["att_probs"].cpu().numpy()
+        return {'batch_scores': mixed(res["att"]),
+                'pair_scores': [[neg[i, :qn, :n], probs[i, :qn, :n], probs[i, :qn, :n] * neg[i, :qn, :n]]
+                                for i, n in enumerate(lens)]}
     if score_agg_type != 'l2wasserstein':
         raise ValueError(f'Unknown aggregation: {score_agg_type}')
     diameter = hp.get('geoml_diameter') or bbox_diameter(q, c)
     eps = epsilon_schedule(diameter, hp.get('geoml_blur', 0.05), hp.get('geoml_scaling', 0.9))
     res = ot_scores(q, q_lens, c, c_lens, eps, temp=hp.get('sent_sm_temp', 1.0), broadcast_query=True,
                     want=("primal", "alpha", "beta", "neg_cost", "plan", "weighted"))
-    host = {k: v.cpu().numpy() for k, v in res.items()}
+    host = {k: v.cpu().numpy() for k, v in res.items() if k != "primal"}
     pairs = [[host["alpha"][i, :qn], host["beta"][i, :n], host["neg_cost"][i, :qn, :n], host["plan"][i, :qn, :n],
               host["weighted"][i, :qn, :n]] for i, n in enumerate(lens)]
-    return {'batch_scores': host["primal"], 'pair_scores': pairs}
+    return {'batch_scores': mixed(res["primal"]), 'pair_scores': pairs}

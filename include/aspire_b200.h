@@ -139,7 +139,7 @@ int asp_l2max(const float* q, const int32_t* q_lens, int q_broadcast, const floa
  * then a per-candidate column-slice np.max; all-queries x all-corpus variant :788-816) and
  * allpair_masked_dist_l2max (pair_distances.py:138-186) applied to all NQ x NC pairs: one tcgen05 contraction
  * [NQ*S, D] x [D, NC*S] with fp32-equivalent (bf16x3) products and a segmented max epilogue.
- * q [NQ,S,D], c [NC,S,D] zero padded fp32, lens int32; S in [10,64], D % 64 == 0.
+ * q [NQ,S,D], c [NC,S,D] zero padded fp32, lens int32; S in [1,64], D % 64 == 0 (at most 16 candidate documents share a tile, so S < 10 uses part of it).
  * scores [NQ,NC] = max_{i<ql,j<cl} -||q_i-c_j|| (-1e9 if a side is empty); flat_idx [NQ,NC] (optional) = i*S+j
  * of the first maximum.  workspace: asp_l2max_allpairs_workspace_bytes() of device scratch (bf16 hi/lo copies).
  */
@@ -208,6 +208,15 @@ int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, const float
  */
 int asp_pair_heads(const float* cost, const int32_t* q_lens, int q_group, const int32_t* c_lens, int B, int Sq, int Sc,
                    float temp, float* top2, float* att, float* att_probs, asp_stream_t stream);
+
+/*
+ * Score mixing of WordSentAlignBiEnc.caching_score (src/learning/facetid_models/disent_models.py:298-307), in place:
+ *   scores[b] = sent_prop * scores[b] + abs_prop * ( -|| q_cls[b / q_group] - c_cls[b] + 1e-6 ||_2 )
+ * (the second term is -torch.nn.functional.pairwise_distance(query_cls, cand_cls, p=2)).  scores [B] are the sentence-level
+ * scores of asp_ot_score / asp_l2max / asp_pair_heads; q_cls [ceil(B/q_group), D], c_cls [B, D] the documents' CLS vectors.
+ */
+int asp_mix_cls_scores(float* scores, const float* q_cls, int q_group, const float* c_cls, int B, int D,
+                       float sent_prop, float abs_prop, asp_stream_t stream);
 
 /*
  * Q x C all-pairs mode of asp_ot_score (dual values only): scores[i*NC + j] = OT_eps(query i, candidate j) for every

@@ -131,6 +131,24 @@ def test_rank_pool_sent_from_npy_reps_vs_float64_numpy_path(tmp_path):
                 assert abs(-neg_sim - want[cpid]) <= 3e-5 * max(1.0, abs(want[cpid])), (score_type, qpid, cpid)
             vals = [v for _, v in ranked]
             assert vals == sorted(vals)
+    # the all-queries x all-documents caller (pp_gen_nearest.py:729-860) on the tensor-core all-pairs kernel: documents
+    # of 1..8 sentences (S < 10), a candidate listed twice is ranked once, same scores and order as the per-pool path
+    from aspire_b200.evaluation import rank_pool_sent_treccovid
+    pool["501"]["cands"].append("505")
+    pool["501"]["relevance_adju"].append(0)
+    with open(os.path.join(root, f"test-pid2anns-{ds}.json"), "w") as fh:
+        json.dump(pool, fh)
+    per_pool = rank_pool_sent(root, reps, ds, score_type="l2max", write=False)
+    deep = rank_pool_sent_treccovid(root, reps, ds, score_type="l2max", cand_chunk=16)
+    with open(os.path.join(reps, f"test-pid2pool-{ds}-myreps-ranked.json")) as fh:
+        assert [c for c, _ in json.load(fh)["501"]] == [c for c, _ in deep["501"]]
+    for qpid in pool:
+        assert len(deep[qpid]) == len(set(pool[qpid]["cands"])) == len(per_pool[qpid])
+        a, b = dict(per_pool[qpid]), dict(deep[qpid])
+        assert max(abs(a[c] - b[c]) for c in a) <= 3e-5
+        gap = np.diff([v for _, v in per_pool[qpid]]).min()
+        if gap > 1e-4:
+            assert [c for c, _ in per_pool[qpid]] == [c for c, _ in deep[qpid]]
 
 
 def test_resident_corpus_indexed_pools_match_packed_pools():

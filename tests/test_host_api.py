@@ -130,6 +130,57 @@ def test_faceted_encoding_and_cache(tmp_path):
     assert torch.equal(again["p3"], encs["p3"])
 
 
+def test_encodings_cache_h5_style_name_roundtrip_and_formats(tmp_path, monkeypatch):
+    """The reference names its cache ``encodings.h5`` (utils/utils.py:53-60).  Without h5py the cache must come back
+    from the SAME resolved path it was saved to, survive paper ids that are not identifiers, write only when dirty, and
+    refuse (not silently re-encode) a real HDF5 file; with h5py importable it must open the reference's own format."""
+    import sys
+    import types
+    import numpy as np
+    from aspire_b200 import _abi
+    from aspire_b200.similarity import EncodingsCache
+    monkeypatch.setitem(sys.modules, "h5py", None)  # "import h5py" raises ImportError
+    fn = str(tmp_path / "encodings.h5")
+    c = EncodingsCache(fn)
+    c.create_dataset(name="file", data=torch.ones(2, 3))       # np.savez's own keyword
+    c.create_dataset(name="10.1/abc-def", data=np.arange(6.).reshape(3, 2))
+    c.close()
+    assert os.path.exists(fn + ".npz") and not os.path.exists(fn)
+    c2 = EncodingsCache(fn)
+    assert set(c2.keys()) == {"file", "10.1/abc-def"} and "file" in c2 and len(c2) == 2
+    assert np.array_equal(np.array(c2.get("10.1/abc-def")), np.arange(6.).reshape(3, 2))
+    stamp = os.path.getmtime(fn + ".npz")
+    c2.close()                                                 # nothing changed: not rewritten
+    assert os.path.getmtime(fn + ".npz") == stamp
+    with open(str(tmp_path / "real.h5"), "wb") as fh:
+        fh.write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(_abi.AspireB200Error):
+        EncodingsCache(str(tmp_path / "real.h5"))
+    # with h5py importable: h5py.File(filename, 'a'), 'w' when that fails, one dataset per paper id
+    calls = []
+
+    class FakeFile(dict):
+        def __init__(self, name, mode):
+            calls.append((name, mode))
+            if mode == 'a' and name.endswith("corrupt.h5"):
+                raise OSError("bad superblock")
+            super().__init__()
+
+        def create_dataset(self, name, data):
+            self[name] = np.asarray(data)
+
+        def close(self):
+            calls.append("closed")
+    monkeypatch.setitem(sys.modules, "h5py", types.SimpleNamespace(File=FakeFile))
+    c3 = EncodingsCache(str(tmp_path / "enc.h5"))
+    c3.create_dataset(name="p1", data=torch.zeros(1, 2))
+    assert "p1" in c3 and np.array(c3.get("p1")).shape == (1, 2)
+    c3.close()
+    EncodingsCache(str(tmp_path / "corrupt.h5"))
+    assert calls == [(str(tmp_path / "enc.h5"), 'a'), "closed", (str(tmp_path / "corrupt.h5"), 'a'),
+                     (str(tmp_path / "corrupt.h5"), 'w')]
+
+
 def test_shard_bounds_cover_pool():
     from aspire_b200.ranking import shard_bounds
     for n, w in [(1000000, 8), (1003, 8), (5, 8), (100000, 3)]:

@@ -100,6 +100,31 @@ def test_caching_score_vs_golden():
         caching_score(qd, cds, "nope")
 
 
+def test_caching_score_mixing_vs_reference_golden():
+    """disent_models.py:298-307: sent_loss_prop / sentsup_loss_prop scaling and the abs_loss_prop CLS-distance term,
+    for all four aggregation heads, against tests/golden/caching_score_mix.npz (written by oracle/make_golden_mix.py
+    from the UNMODIFIED reference method)."""
+    from aspire_b200.similarity import caching_score
+    z = np.load(os.path.join(GOLDEN, "caching_score_mix.npz"))
+    lens = z["c_lens"].tolist()
+    offs = np.cumsum([0] + lens)
+    qd = {"sent_reps": z["q"], "doc_cls_reps": z["q_cls"]}
+    cds = [{"sent_reps": z["c_cat"][offs[i]:offs[i + 1]], "doc_cls_reps": z["c_cls"][i]} for i in range(len(lens))]
+    for agg in ("l2wasserstein", "l2max", "l2top2", "l2attention"):
+        for tag in "abc":
+            sp, ssp, ap = z["mix_" + tag].tolist()
+            hp = {"sent_loss_prop": sp, "abs_loss_prop": ap}
+            if ssp >= 0:
+                hp["sentsup_loss_prop"] = ssp
+            got = caching_score(qd, cds, agg, model_hparams=hp)["batch_scores"]
+            ref = z[f"{agg}_{tag}"]
+            tol = 3e-4 if agg == "l2wasserstein" else 2e-5
+            assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1)) <= tol, (agg, tag)
+    # explicit arguments win over the hparams
+    got = caching_score(qd, cds, "l2max", model_hparams={"abs_loss_prop": 9.0}, sent_loss_prop=0.6, abs_loss_prop=0.4)
+    np.testing.assert_allclose(got["batch_scores"], z["l2max_a"], rtol=1e-5, atol=2e-5)
+
+
 def test_ranking_parity_map():
     """SURVEY 8d ranking-parity set (scaled): rank by kernel vs oracle; MAP within 1e-3 (here: equal rankings
     up to near-ties), through topk on the device."""

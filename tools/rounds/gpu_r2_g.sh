@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, call G: slice loop inside the shape variants (8 or 4 steps per trip), producers parked on consumed-barriers
+set -x
+mkdir -p gpurun_out
+timeout 240 python -m pytest tests/test_varlen_gpu.py -m gpu -q --timeout 300 > gpurun_out/r2g_pytest.txt 2>&1; echo "pytest exit $?" >> gpurun_out/r2g_pytest.txt
+grep -E "FAIL|passed|failed|exit|Error|assert" gpurun_out/r2g_pytest.txt | cut -c1-250 | tail -12
+timeout 300 python tools/side_bench.py varlen > gpurun_out/r2g_side_varlen.txt 2>&1; cat gpurun_out/r2g_side_varlen.txt
+ASP_OPTIONS=vl_flags=1 timeout 300 python tools/side_bench.py varlen > gpurun_out/r2g_side_varlen_full.txt 2>&1; cat gpurun_out/r2g_side_varlen_full.txt
+ASP_VARLEN_B=20000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ot_varlen -s 3 -c 1 -o gpurun_out/r2g_varlen python tools/side_bench.py varlen > gpurun_out/r2g_ncu_log.txt 2>&1; tail -3 gpurun_out/r2g_ncu_log.txt

@@ -29,6 +29,9 @@ def timeit(fn, iters=5, warm=2):
 
 def main():
     only = set(sys.argv[1:])
+    for kv in os.environ.get('ASP_OPTIONS', '').split(','):
+        if '=' in kv:
+            _abi.set_option(kv.split('=')[0], int(kv.split('=')[1]))
     dev = torch.device("cuda")
     g = torch.Generator(device="cuda").manual_seed(2345)
     if not only or "allpairs" in only:
@@ -51,7 +54,7 @@ def main():
         del q, c
     if not only or "varlen" in only:
         # config 5: paired documents with 2..30 sentences, 50-step schedule
-        B, S, D = 20000, 30, 768
+        B, S, D = int(os.environ.get('ASP_VARLEN_B', 100000)), 30, 768
         q = 0.3 * torch.randn(B, S, D, device=dev, generator=g)
         c = 0.3 * torch.randn(B, S, D, device=dev, generator=g)
         ql = torch.randint(2, 31, (B,), device=dev, generator=g).int()
