@@ -10,7 +10,8 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaspire_b200.so")
+# ASPIRE_B200_LIB: developer override (A/B builds of the same ABI under tools/); the product path is the in-tree library
+LIB_PATH = os.environ.get("ASPIRE_B200_LIB") or os.path.join(_HERE, "libaspire_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aspire_b200.h")
 
 _lib = None
@@ -56,6 +57,8 @@ def lib():
     L.asp_span_mean_pool.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp]
     L.asp_pair_cost.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp]
     L.asp_l2max.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
+    L.asp_l2max_ws.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    L.asp_l2max_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.asp_pair_heads.argtypes = [vp, vp, ci, vp, ci, ci, ci, cf, vp, vp, vp, vp]
     L.asp_mix_cls_scores.argtypes = [vp, vp, ci, vp, ci, ci, cf, cf, vp]
     L.asp_ot_sinkhorn.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, vp,
@@ -90,6 +93,7 @@ def lib():
     L.asp_abstracts_fill.argtypes = [vp, vp, vp, ci, ci, ci, ci, cll, ci, ci, vp, vp, vp, vp]
     L.asp_ot_score_workspace_bytes.restype = ctypes.c_size_t
     L.asp_l2max_allpairs_workspace_bytes.restype = ctypes.c_size_t
+    L.asp_l2max_workspace_bytes.restype = ctypes.c_size_t
     L.asp_bert_workspace_bytes.restype = ctypes.c_size_t
     _lib = L
     return L

@@ -31,10 +31,16 @@
 #include <type_traits>
 #include "ot_pair.cuh"
 
+#ifndef ASP_VL_U_SMALL
+#define ASP_VL_U_SMALL 8
+#define ASP_VL_U_BIG 4
+#endif
+
 namespace asp {
 
-constexpr int kVlPitch = 36;                       // floats per staged row piece: 32 data + 4 pad (bank spread)
-constexpr int kVlUnitFloats = 8 * kVlPitch;        // ring allocation unit: 8 row pieces
+constexpr int kVlPitch = 32;                       // floats per staged row piece: 128 bytes, 128-byte aligned; its eight 16-byte
+                                                   // chunks are stored XOR-swizzled by (row & 7) -- what TMA's 128B swizzle does
+constexpr int kVlUnitFloats = 8 * kVlPitch;        // ring allocation unit: 8 row pieces = 1 KB
 constexpr int kVlTileLd = 36;
 constexpr int kVlTileFloats = 32 * kVlTileLd;      // cost tile / exponential scratch
 constexpr int kVlMaxS = 32;
@@ -87,39 +93,60 @@ __device__ __forceinline__ uint32_t vl_smem_u32(const void* p) { return (uint32_
 // One slice (32 floats of every row of the pair) of the Gram tile.  Slot rows [0, ql) = query rows, [ql, ql+cl) =
 // candidate rows.  Rows a lane touches beyond the valid ones hold stale bytes: they only ever reach accumulators of
 // entries that the epilogue masks.
+__device__ __forceinline__ float4 vl_lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 vl_lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// Slot layout: row r of the slice (query rows first, then candidate rows) is the 128 bytes at slot + 128 r; its 16-byte
+// chunk k sits at chunk position k ^ (r & 7).  A piece therefore lands in ONE 128-byte-aligned line of shared memory (the
+// four sectors of a cp.async'ed global line merge into one wavefront; with padded 144-byte rows every LDGSTS took 11
+// wavefronts instead of 4), while the Gram loads -- 8 rows r = li + 8a at the same k, or 4 rows ql + lj + 4b -- still hit
+// distinct bank groups.  Since r & 7 does not depend on a, and flips only bit 2 with the parity of b, a lane needs three
+// swizzled base addresses per slice and one XOR with the compile-time (k << 4) per step.
 template <int NA, int NB>
-__device__ __forceinline__ void vl_slice(const float* slot, int ql, int li, int lj, int r0, int chunk, float2 (&acc)[4][8],
+__device__ __forceinline__ void vl_slice(uint32_t slot, int ql, int li, int lj, int r0, int chunk, float2 (&acc)[4][8],
                                          float2 (&nq)[8], float2 (&nc)[8]) {
-    constexpr int P4 = kVlPitch / 4;  // float4 per row piece
     {
-        const float4* own = reinterpret_cast<const float4*>(slot) + r0 * P4 + chunk;
+        // squared norms from the pieces the producer lane of the same index copied: rows r0 + 4m (and ql + r0 + 4m)
+        const uint32_t qe = slot + r0 * 128 + ((chunk ^ r0) << 4), qo = qe ^ 64;
 #pragma unroll
         for (int m = 0; m < 2 * NA; ++m) {
-            const float4 v = own[m * 4 * P4];
+            const float4 v = vl_lds128((m & 1 ? qo : qe) + m * 512);
             nq[m] = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), nq[m]);
             nq[m] = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), nq[m]);
         }
-        const float4* ownc = own + ql * P4;
+        const int rc = ql + r0;
+        const uint32_t ce = slot + rc * 128 + ((chunk ^ (rc & 7)) << 4), co = ce ^ 64;
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
-            const float4 v = ownc[m * 4 * P4];
+            const float4 v = vl_lds128((m & 1 ? co : ce) + m * 512);
             nc[m] = __ffma2_rn(make_float2(v.x, v.y), make_float2(v.x, v.y), nc[m]);
             nc[m] = __ffma2_rn(make_float2(v.z, v.w), make_float2(v.z, v.w), nc[m]);
         }
     }
-    const float4* sq = reinterpret_cast<const float4*>(slot) + li * P4;
-    const float4* sc = reinterpret_cast<const float4*>(slot) + (ql + lj) * P4;
+    const uint32_t pq = (slot + li * 128) ^ (li << 4);
+    const int rcl = ql + lj;
+    const uint32_t pc0 = (slot + rcl * 128) ^ ((rcl & 7) << 4), pc1 = pc0 ^ 64;
     // Unroll policy: a taken branch costs this warp (the only Gram warp of its scheduler) an instruction-fetch bubble
     // that nothing hides, so small tiles run the eight 4-float steps of a slice as straight-line code and large tiles in
     // two trips (with one or two steps per trip, 60 % of the Gram warps' samples were "no instruction").
-    constexpr int U = (NA * NB <= 12) ? 8 : 4;
+    constexpr int U = (NA * NB <= 12) ? ASP_VL_U_SMALL : ASP_VL_U_BIG;
 #pragma unroll U
     for (int kq = 0; kq < 8; ++kq) {
+        const uint32_t aq = pq ^ (kq << 4), ac0 = pc0 ^ (kq << 4), ac1 = pc1 ^ (kq << 4);
         float4 qv[NA], cv[NB];
 #pragma unroll
-        for (int a = 0; a < NA; ++a) qv[a] = sq[a * 8 * P4 + kq];
+        for (int a = 0; a < NA; ++a) qv[a] = vl_lds128(aq + a * 1024);
 #pragma unroll
-        for (int b = 0; b < NB; ++b) cv[b] = sc[b * 4 * P4 + kq];
+        for (int b = 0; b < NB; ++b) cv[b] = vl_lds128((b & 1 ? ac1 : ac0) + b * 512);
 #pragma unroll
         for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -130,60 +157,81 @@ __device__ __forceinline__ void vl_slice(const float* slot, int ql, int li, int 
     }
 }
 
-// One Sinkhorn step in the shared-exponential form, row owner's half: E_ij for the first 4*NB columns (NB = ceil(cl/4)).
-// ONE copy of the code, entered at the bucket's first chunk (fallthrough), so every pair shape runs the same
-// instructions.  The v_j of all 32 columns are fetched up front (always in bounds) so that the chunks carry no load.
-__device__ __forceinline__ float vl_row_exps(int NB, const float2 (&Cr)[16], float u, float t, const float* vs, float* erow) {
-    const float2 uu = dup2(u), nt2 = dup2(-t);
-    float2 R = f2(0.f, 0.f);
-    float4 v4[8];
-#pragma unroll
-    for (int jc = 0; jc < 8; ++jc) v4[jc] = *reinterpret_cast<const float4*>(vs + 4 * jc);
-#define ASP_VL_CHUNK(jc)                                                                              \
-    {                                                                                                 \
-        const float2 x0 = __ffma2_rn(Cr[2 * (jc)], nt2, __fadd2_rn(uu, f2(v4[jc].x, v4[jc].y)));      \
-        const float2 x1 = __ffma2_rn(Cr[2 * (jc) + 1], nt2, __fadd2_rn(uu, f2(v4[jc].z, v4[jc].w)));  \
-        const float4 e = make_float4(ex2(x0.x), ex2(x0.y), ex2(x1.x), ex2(x1.y));                     \
-        R = __fadd2_rn(R, f2(e.x, e.y));                                                              \
-        R = __fadd2_rn(R, f2(e.z, e.w));                                                              \
-        *reinterpret_cast<float4*>(erow + 4 * (jc)) = e;                                              \
+// Max-stabilised recomputation of both half-steps of one Sinkhorn step from the old potentials (the rare path of
+// vl_sinkhorn_steps, when a plain sum left the fp32 range).  Works on the cost tile in shared memory (which the step
+// loop never modifies) with rolled loops: one copy, out of line.
+static __device__ __noinline__ void vl_stabilised_step(const float* tile, const float* us, const float* vs, int ql, int cl,
+                                                       float t, float epsl, int lane, float& ft, float& gt) {
+    const float nt = -t;
+    float m = -INFINITY, sm = 0.f;
+    if (lane < ql) {
+        const float* row = tile + lane * kVlTileLd;
+        for (int j = 0; j < cl; ++j) m = fmaxf(m, fmaf(row[j], nt, vs[j]));
+        for (int j = 0; j < cl; ++j) sm += ex2(fmaf(row[j], nt, vs[j]) - m);
     }
-    switch (NB) {
-        case 8: ASP_VL_CHUNK(7)
-        case 7: ASP_VL_CHUNK(6)
-        case 6: ASP_VL_CHUNK(5)
-        case 5: ASP_VL_CHUNK(4)
-        case 4: ASP_VL_CHUNK(3)
-        case 3: ASP_VL_CHUNK(2)
-        case 2: ASP_VL_CHUNK(1)
-        default: ASP_VL_CHUNK(0)
+    ft = -epsl * (m + lg2(sm));
+    m = -INFINITY;
+    sm = 0.f;
+    if (lane < cl) {
+        const float* col = tile + lane;
+        for (int i = 0; i < ql; ++i) m = fmaxf(m, fmaf(col[i * kVlTileLd], nt, us[i]));
+        for (int i = 0; i < ql; ++i) sm += ex2(fmaf(col[i * kVlTileLd], nt, us[i]) - m);
     }
-#undef ASP_VL_CHUNK
-    return R.x + R.y;
+    gt = -epsl * (m + lg2(sm));
 }
 
-// column owner's half: sum of column `lane` over the first 8*NA rows (rows in [ql, 8*NA) hold exact zeros)
-__device__ __forceinline__ float vl_col_sum(int NA, const float* col) {
-    float S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f;
-#define ASP_VL_ROWS(a)                                  \
-    {                                                   \
-        S0 += col[(8 * (a) + 0) * kVlTileLd];           \
-        S1 += col[(8 * (a) + 1) * kVlTileLd];           \
-        S2 += col[(8 * (a) + 2) * kVlTileLd];           \
-        S3 += col[(8 * (a) + 3) * kVlTileLd];           \
-        S0 += col[(8 * (a) + 4) * kVlTileLd];           \
-        S1 += col[(8 * (a) + 5) * kVlTileLd];           \
-        S2 += col[(8 * (a) + 6) * kVlTileLd];           \
-        S3 += col[(8 * (a) + 7) * kVlTileLd];           \
+// The eps-scaling loop of one pair, lane i owning row i AND column i.  Both sums of a step are computed from REGISTERS:
+//   R_i = sum_j 2^(u_i + v_j - C_ij t) from the lane's row of C,   S_j = sum_i 2^(u_i + v_j - C_ij t) from its column,
+// with u = la + f t and v = lb + g t of all lanes published through a double-buffered 2 x 32-float block of shared memory
+// (ONE __syncwarp per step).  The first version computed every exponential once and transposed the 32 x 32 tile of
+// exponentials through shared memory for the column sums: half the MUFU work, but two more barriers per step, 50 % more
+// instructions, a serial chain row pass -> store -> barrier -> column pass, and 54 instead of ~21 shared-memory
+// wavefronts per step on a kernel whose busiest unit is the shared-memory pipe.  Templated on the Gram bucket (8*NA rows,
+// 4*NB columns) so that a step is straight-line code; padded rows/columns carry log-weight -1e5 and add exact zeros.
+// A sum that leaves the fp32 range redoes the step in the max-stabilised form (rare).
+template <int NA, int NB>
+__device__ __forceinline__ void vl_sinkhorn_steps(const float2 (&Cr)[16], const float2 (&Cc)[16], float la, float lb, bool row_ok,
+                                                  bool col_ok, int ql, int cl, const float2* step_s, int n_eps, float* uv, const float* tile,
+                                                  int lane, float& f_out, float& g_out) {
+    float f = 0.f, g = 0.f;
+#pragma unroll 1
+    for (int k = -1; k <= n_eps; ++k) {
+        const float2 st = step_s[min(max(k, 0), n_eps - 1)];
+        const float t = st.x, epsl = st.y;  // log2e / eps, eps * ln2
+        const bool plain = (k < 0) | (k == n_eps);
+        const float u = fmaf(f, t, la), v = fmaf(g, t, lb);  // f = g = 0 at k = -1
+        float* us = uv + ((k & 1) ? 64 : 0);
+        float* vs = us + 32;
+        us[lane] = u;
+        vs[lane] = v;
+        __syncwarp();
+        const float2 uu = dup2(u), vv = dup2(v), nt2 = dup2(-t);
+        float2 R = f2(0.f, 0.f), S = f2(0.f, 0.f);
+#pragma unroll
+        for (int jc = 0; jc < NB; ++jc) {
+            const float4 v4 = *reinterpret_cast<const float4*>(vs + 4 * jc);
+            const float2 x0 = __ffma2_rn(Cr[2 * jc], nt2, __fadd2_rn(uu, f2(v4.x, v4.y)));
+            const float2 x1 = __ffma2_rn(Cr[2 * jc + 1], nt2, __fadd2_rn(uu, f2(v4.z, v4.w)));
+            R = __fadd2_rn(R, f2(ex2(x0.x), ex2(x0.y)));
+            R = __fadd2_rn(R, f2(ex2(x1.x), ex2(x1.y)));
+        }
+#pragma unroll
+        for (int ic = 0; ic < 2 * NA; ++ic) {
+            const float4 u4 = *reinterpret_cast<const float4*>(us + 4 * ic);
+            const float2 x0 = __ffma2_rn(Cc[2 * ic], nt2, __fadd2_rn(vv, f2(u4.x, u4.y)));
+            const float2 x1 = __ffma2_rn(Cc[2 * ic + 1], nt2, __fadd2_rn(vv, f2(u4.z, u4.w)));
+            S = __fadd2_rn(S, f2(ex2(x0.x), ex2(x0.y)));
+            S = __fadd2_rn(S, f2(ex2(x1.x), ex2(x1.y)));
+        }
+        const float lr = lg2(R.x + R.y), ls = lg2(S.x + S.y);
+        float ft = f - epsl * (lr - la), gt = g - epsl * (ls - lb);
+        const bool ok = (!row_ok || fabsf(lr) < 1e30f) && (!col_ok || fabsf(ls) < 1e30f);
+        if (!__all_sync(0xffffffffu, ok)) vl_stabilised_step(tile, us, vs, ql, cl, t, epsl, lane, ft, gt);
+        f = row_ok ? (plain ? ft : 0.5f * (f + ft)) : 0.f;
+        g = col_ok ? (plain ? gt : 0.5f * (g + gt)) : 0.f;
     }
-    switch (NA) {
-        case 4: ASP_VL_ROWS(3)
-        case 3: ASP_VL_ROWS(2)
-        case 2: ASP_VL_ROWS(1)
-        default: ASP_VL_ROWS(0)
-    }
-#undef ASP_VL_ROWS
-    return (S0 + S1) + (S2 + S3);
+    f_out = f;
+    g_out = g;
 }
 
 // ---- the kernel: producer warp / Gram warps / Sinkhorn warps -------------------------------------------------------------
@@ -198,12 +246,13 @@ __device__ __forceinline__ float vl_col_sum(int NA, const float* col) {
 //               stream their slices into the Gram warp's byte ring with cp.async; completion is signalled per slice on
 //               an mbarrier (cp.async.mbarrier.arrive.noinc), ring space comes back through two shared counters.
 constexpr int kWsGram = 4, kWsSink = 8, kWsWarps = 16;
-constexpr int kWsRingUnits = 24;                               // per Gram warp: 27 648 B
+constexpr int kWsRingUnits = 28;                               // per Gram warp: 28 KB
 constexpr int kWsRingFloats = kWsRingUnits * kVlUnitFloats;
 constexpr int kWsSeq = 16;                                     // slice barriers per Gram warp (slices in flight < 16)
 constexpr int kWsQueue = 8;                                    // pair descriptors per Gram warp
-constexpr int kWsSmemFloats = kWsGram * kWsRingFloats + kWsSink * 2 * kVlTileFloats + kWsSink * 64 + kWsGram * 64;
-constexpr int kWsGramRegs = 232, kWsSinkRegs = 96, kWsProdRegs = 80;  // 4*232 + 8*96 + 4*80 = 2016 <= 2048
+constexpr int kWsSmemFloats = kWsGram * kWsRingFloats + kWsSink * 2 * kVlTileFloats + kWsSink * 128 + kWsGram * 64 +
+                              256;  // + slack to align the rings to 1 KB
+constexpr int kWsGramRegs = 224, kWsSinkRegs = 120, kWsProdRegs = 48;  // 4*224 + 8*120 + 4*48 = 2048
 
 struct WsShared {
     uint64_t slice_full[kWsGram][kWsSeq], slice_empty[kWsGram][kWsSeq];
@@ -243,7 +292,8 @@ __device__ __forceinline__ void ws_setmaxnreg_dec() { asm volatile("setmaxnreg.d
 
 __global__ void __launch_bounds__(kWsWarps * 32, 1)
 ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) float smem_raw[];
+    float* smem = smem_raw + (((1024u - (vl_smem_u32(smem_raw) & 1023u)) & 1023u) >> 2);  // rings start on a 1 KB boundary
     __shared__ float2 step_s[ASP_MAX_EPS];  // per schedule entry: log2e / eps, eps * ln2
     __shared__ WsShared sh;
     for (int k = threadIdx.x; k < sched.n; k += blockDim.x) step_s[k] = make_float2(kLog2e / sched.eps[k], sched.eps[k] * kLn2);
@@ -265,8 +315,8 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tiles = smem + (size_t)kWsGram * kWsRingFloats;                       // [kWsSink][2][kVlTileFloats]
-    float* sink_misc = tiles + (size_t)kWsSink * 2 * kVlTileFloats;              // [kWsSink][64]: v | beta
-    float* gram_misc = sink_misc + (size_t)kWsSink * 64;                         // [kWsGram][64]: row norms
+    float* sink_misc = tiles + (size_t)kWsSink * 2 * kVlTileFloats;              // [kWsSink][2][u | v]
+    float* gram_misc = sink_misc + (size_t)kWsSink * 128;                        // [kWsGram][64]: row norms
     const int D = a.D, nsl = D >> 5;
 
     if (warp >= kWsGram + kWsSink) {
@@ -275,7 +325,7 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
         const int g = warp - (kWsGram + kWsSink);
         const int r0 = lane >> 3, chunk = lane & 7;  // this lane copies rows r0 + 4m, 16-byte chunk `chunk` of the piece
         const unsigned rstride = 16u * (unsigned)D;  // bytes between the rows r and r + 4
-        const uint32_t ring_u32 = vl_smem_u32(smem + (size_t)g * kWsRingFloats) + (uint32_t)(r0 * kVlPitch + chunk * 4) * 4u;
+        const uint32_t ring_u32 = vl_smem_u32(smem + (size_t)g * kWsRingFloats);
         int nx_b = 0, nx_ql = 0, nx_cl = 0, nx_ci = 0;  // the pair claimed one ahead (valid in lane 0 until broadcast)
         auto claim = [&]() {
             if (lane == 0) {
@@ -335,23 +385,28 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
                     if (vpos + waste + pu - cv <= kWsRingUnits && issued - cc < kWsSeq - 1) break;
                     ws_mbar_wait(&sh.slice_empty[g][cc & (kWsSeq - 1)], (cc >> 4) & 1);
                 }
-                const uint32_t dst = ring_u32 + (uint32_t)(o * kVlUnitFloats) * 4u;
-                const uint32_t dstc = dst + (uint32_t)pql * kVlPitch * 4;
+                // row r0 + 4m of each side; chunk position = chunk ^ (row & 7), which alternates with the parity of m
+                const uint32_t slot = ring_u32 + (uint32_t)o * 1024u;
+                const uint32_t dqe = slot + r0 * 128 + ((chunk ^ r0) << 4), dqo = dqe ^ 64;
+                const int rcp = pql + r0;
+                const uint32_t dce = slot + rcp * 128 + ((chunk ^ (rcp & 7)) << 4), dco = dce ^ 64;
                 // every group but the last is complete for every lane: no per-lane predicate
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     if (m >= mq - 1) break;
-                    vl_cp_async16(dst + m * (4 * kVlPitch * 4), reinterpret_cast<const float*>(qsrc + (size_t)(m * rstride)));
+                    vl_cp_async16((m & 1 ? dqo : dqe) + m * 512, reinterpret_cast<const float*>(qsrc + (size_t)(m * rstride)));
                 }
                 if (mq > 0 && last_q)
-                    vl_cp_async16(dst + (mq - 1) * (4 * kVlPitch * 4), reinterpret_cast<const float*>(qsrc + (size_t)((mq - 1) * rstride)));
+                    vl_cp_async16(((mq - 1) & 1 ? dqo : dqe) + (mq - 1) * 512,
+                                  reinterpret_cast<const float*>(qsrc + (size_t)((mq - 1) * rstride)));
 #pragma unroll
                 for (int m = 0; m < 8; ++m) {
                     if (m >= mc - 1) break;
-                    vl_cp_async16(dstc + m * (4 * kVlPitch * 4), reinterpret_cast<const float*>(csrc + (size_t)(m * rstride)));
+                    vl_cp_async16((m & 1 ? dco : dce) + m * 512, reinterpret_cast<const float*>(csrc + (size_t)(m * rstride)));
                 }
                 if (mc > 0 && last_c)
-                    vl_cp_async16(dstc + (mc - 1) * (4 * kVlPitch * 4), reinterpret_cast<const float*>(csrc + (size_t)((mc - 1) * rstride)));
+                    vl_cp_async16(((mc - 1) & 1 ? dco : dce) + (mc - 1) * 512,
+                                  reinterpret_cast<const float*>(csrc + (size_t)((mc - 1) * rstride)));
                 ws_cp_async_arrive(&sh.slice_full[g][issued & (kWsSeq - 1)]);
                 ++issued;
                 qsrc += 128;
@@ -368,7 +423,7 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
         // ============================== Gram warp =============================================================
         ws_setmaxnreg_inc<kWsGramRegs>();
         const int g = warp;
-        const float* ring = smem + (size_t)g * kWsRingFloats;
+        const uint32_t ring_s = vl_smem_u32(smem + (size_t)g * kWsRingFloats);
         float* nrm = gram_misc + g * 64;
         const int li = lane & 7, lj = lane >> 3;     // lane grid: 8 query-row groups x 4 candidate-row groups
         const int r0 = lane >> 3, chunk = lane & 7;  // norm duty: the pieces the producer lane of the same index copied
@@ -403,7 +458,7 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
                         waste = kWsRingUnits - o;
                         o = 0;
                     }
-                    if constexpr (NAc > 0) vl_slice<NAc, NBc>(ring + o * kVlUnitFloats, ql, li, lj, r0, chunk, acc, nq, nc);
+                    if constexpr (NAc > 0) vl_slice<NAc, NBc>(ring_s + (uint32_t)o * 1024u, ql, li, lj, r0, chunk, acc, nq, nc);
                     __syncwarp();  // every lane is done with the slot
                     off = o + units;
                     vpos += waste + units;
@@ -528,8 +583,9 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
     ws_setmaxnreg_dec<kWsSinkRegs>();
     if (a.mode != 0) return;
     const int sw = warp - kWsGram;
-    float* vs = sink_misc + sw * 64;   // [32] v_j of the step (then g for the plan)
-    float* bs = vs + 32;               // [32] beta for the plan
+    float* uv = sink_misc + sw * 128;  // [2][u 32 | v 32]: the potentials of a step, double buffered
+    float* vs = uv;                    // (afterwards: g and beta for the plan)
+    float* bs = uv + 32;
 #pragma unroll 1
     for (int t = 0;; ++t) {
         const int buf = t & 1;
@@ -567,52 +623,35 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
             la = (alpha > 0.f) ? log2f(alpha) : kLogZeroWeight * kLog2e;
             lb = (beta > 0.f) ? log2f(beta) : kLogZeroWeight * kLog2e;
         }
-        __syncwarp();  // column minima read the tile; from here on its buffer holds the step's exponentials
+        // this lane's COLUMN of the tile as well (rows beyond the bucket / the document: 0, like the padded row entries)
+        float2 Cc[16];
+#pragma unroll
+        for (int ic = 0; ic < 16; ++ic) {
+            float c0 = 0.f, c1 = 0.f;
+            if (2 * ic < 8 * NA && col_ok) {
+                if (2 * ic < ql) c0 = tile[(2 * ic) * kVlTileLd + lane];
+                if (2 * ic + 1 < ql) c1 = tile[(2 * ic + 1) * kVlTileLd + lane];
+            }
+            Cc[ic] = f2(c0, c1);
+        }
         float f = 0.f, g = 0.f;
         float* erow = tile + lane * kVlTileLd;
         if (ql > 0 && cl > 0) {
-#pragma unroll 1
-            for (int k = -1; k <= sched.n; ++k) {
-                const float2 st = step_s[min(max(k, 0), sched.n - 1)];
-                const float tt = st.x, epsl = st.y;  // log2e / eps, eps * ln2
-                const bool plain = (k < 0) | (k == sched.n);
-                const float u = fmaf(f, tt, la), v_own = fmaf(g, tt, lb);  // f = g = 0 at k = -1
-                vs[lane] = v_own;
-                __syncwarp();
-                const float R = vl_row_exps(NB, Cr, u, tt, vs, erow);
-                __syncwarp();
-                const float S = vl_col_sum(NA, tile + lane);
-                const float lr = lg2(R), ls = lg2(S);
-                float ft = f - epsl * (lr - la), gt = g - epsl * (ls - lb);
-                const bool ok = (!row_ok || fabsf(lr) < 1e30f) && (!col_ok || fabsf(ls) < 1e30f);
-                if (!__all_sync(0xffffffffu, ok)) {
-                    // max-stabilised recomputation of both half-steps from the old potentials (rare)
-                    const float nt = -tt;
-                    float m = -INFINITY, s = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < cl) m = fmaxf(m, fmaf((j & 1) ? Cr[j >> 1].y : Cr[j >> 1].x, nt, vs[j]));
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < cl) s += ex2(fmaf((j & 1) ? Cr[j >> 1].y : Cr[j >> 1].x, nt, vs[j]) - m);
-                    ft = -epsl * (m + lg2(s));
-                    __syncwarp();  // column sums above are done with the scratch
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < cl) erow[j] = fmaf((j & 1) ? Cr[j >> 1].y : Cr[j >> 1].x, nt, u);
-                    __syncwarp();
-                    float mc = -INFINITY, sc = 0.f;
-                    if (col_ok) {
-                        for (int i = 0; i < ql; ++i) mc = fmaxf(mc, tile[i * kVlTileLd + lane]);
-                        for (int i = 0; i < ql; ++i) sc += ex2(tile[i * kVlTileLd + lane] - mc);
-                    }
-                    gt = -epsl * (mc + lg2(sc));
-                }
-                f = row_ok ? (plain ? ft : 0.5f * (f + ft)) : 0.f;
-                g = col_ok ? (plain ? gt : 0.5f * (g + gt)) : 0.f;
-                __syncwarp();  // scratch and vs are free for the next step
+            switch ((NA - 1) * 8 + (NB - 1)) {
+#define ASP_VL_CASE(na, nb)                                                                                               \
+    case (na - 1) * 8 + (nb - 1):                                                                                         \
+        vl_sinkhorn_steps<na, nb>(Cr, Cc, la, lb, row_ok, col_ok, ql, cl, step_s, sched.n, uv, tile, lane, f, g);         \
+        break;
+#define ASP_VL_ROW(na)                                                                                        \
+    ASP_VL_CASE(na, 1) ASP_VL_CASE(na, 2) ASP_VL_CASE(na, 3) ASP_VL_CASE(na, 4) ASP_VL_CASE(na, 5) ASP_VL_CASE(na, 6) \
+    ASP_VL_CASE(na, 7) ASP_VL_CASE(na, 8)
+                ASP_VL_ROW(1) ASP_VL_ROW(2) ASP_VL_ROW(3) ASP_VL_ROW(4)
+#undef ASP_VL_ROW
+#undef ASP_VL_CASE
+                default: break;
             }
         }
+        __syncwarp();
 
         const float dual = warp_sum(alpha * f + beta * g);
         if (out.dual && lane == 0) out.dual[b] = dual;

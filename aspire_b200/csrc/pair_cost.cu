@@ -229,16 +229,26 @@ extern "C" int asp_pair_cost(const float* q, const int32_t* q_lens, int q_broadc
                                                  nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int asp_l2max(const float* q, const int32_t* q_lens, int q_broadcast, const float* c,
-                         const int32_t* c_lens, int B, int Sq, int Sc, int D, float* best, int32_t* flat_idx,
-                         float* pair_sims, asp_stream_t stream) {
+extern "C" size_t asp_l2max_workspace_bytes(int B, int Sq, int Sc, int D) {
+    return ((Sq > 10 || Sc > 10) && asp::ot_varlen_supported(Sq, Sc, D)) ? asp::ot_varlen_workspace_bytes(B) : 0;
+}
+
+extern "C" int asp_l2max_ws(const float* q, const int32_t* q_lens, int q_broadcast, const float* c, const int32_t* c_lens,
+                            int B, int Sq, int Sc, int D, float* best, int32_t* flat_idx, float* pair_sims, void* workspace,
+                            size_t workspace_bytes, asp_stream_t stream) {
     int rc = asp::check_pair_args(q, q_lens, c, c_lens, B, Sq, Sc, D);
     if (rc) return rc;
     ASP_REQUIRE(best, "asp_l2max: best is NULL");
     if (B == 0) return ASP_OK;
     if ((Sq > 10 || Sc > 10) && asp::ot_varlen_supported(Sq, Sc, D))  // long documents: rows staged once, no re-reads
         return asp::l2max_varlen_launch(q, q_lens, q_broadcast ? B : 1, c, c_lens, B, Sq, Sc, D, best, flat_idx, pair_sims,
-                                        nullptr, 0, (cudaStream_t)stream);
+                                        workspace, workspace_bytes, (cudaStream_t)stream);
     return asp::launch_pair_cost<asp::MODE_L2MAX>(q, q_lens, q_broadcast ? B : 1, c, c_lens, B, Sq, Sc, D, pair_sims, best,
                                                   flat_idx, (cudaStream_t)stream);
+}
+
+extern "C" int asp_l2max(const float* q, const int32_t* q_lens, int q_broadcast, const float* c,
+                         const int32_t* c_lens, int B, int Sq, int Sc, int D, float* best, int32_t* flat_idx,
+                         float* pair_sims, asp_stream_t stream) {
+    return asp_l2max_ws(q, q_lens, q_broadcast, c, c_lens, B, Sq, Sc, D, best, flat_idx, pair_sims, nullptr, 0, stream);
 }

@@ -154,9 +154,11 @@ def l2max_scores(q, q_lens, c, c_lens, broadcast_query=False, want_pair_sims=Fal
     idx = torch.empty(B, dtype=torch.int32, device=dev)
     sims = torch.empty((B, Sq, Sc), dtype=torch.float32, device=dev) if want_pair_sims else None
     L = _abi.lib()
-    _abi.check(L.asp_l2max(_abi.ptr(q), _abi.ptr(q_lens), int(broadcast_query), _abi.ptr(c), _abi.ptr(c_lens),
-                           B, Sq, Sc, D, _abi.ptr(best), _abi.ptr(idx), _abi.ptr(sims), _abi.stream_of(dev)),
-               "asp_l2max")
+    need = int(L.asp_l2max_workspace_bytes(B, Sq, Sc, D))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
+    _abi.check(L.asp_l2max_ws(_abi.ptr(q), _abi.ptr(q_lens), int(broadcast_query), _abi.ptr(c), _abi.ptr(c_lens),
+                              B, Sq, Sc, D, _abi.ptr(best), _abi.ptr(idx), _abi.ptr(sims), _abi.ptr(ws), need,
+                              _abi.stream_of(dev)), "asp_l2max")
     return best, idx, sims
 
 
