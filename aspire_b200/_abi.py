@@ -76,6 +76,9 @@ def lib():
     L.asp_bbox_diameter.argtypes = [vp, cll, vp, cll, ci, vp, vp, vp]
     L.asp_topk.argtypes = [vp, ci, cll, ci, cll, vp, vp, vp]
     L.asp_topk_merge.argtypes = [vp, vp, ci, ci, ci, vp, vp, vp]
+    L.asp_topk_workspace_bytes.argtypes = [ci, cll, ci]
+    L.asp_topk_ws.argtypes = [vp, ci, cll, ci, cll, ci, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    L.asp_topk_merge_packed.argtypes = [vp, ci, ci, ci, vp, vp, vp]
     for name in declared_symbols():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
         if name not in ("asp_last_error", "asp_launch_count", "asp_ot_score_workspace_bytes", "asp_l2max_allpairs_workspace_bytes",
@@ -94,6 +97,7 @@ def lib():
     L.asp_ot_score_workspace_bytes.restype = ctypes.c_size_t
     L.asp_l2max_allpairs_workspace_bytes.restype = ctypes.c_size_t
     L.asp_l2max_workspace_bytes.restype = ctypes.c_size_t
+    L.asp_topk_workspace_bytes.restype = ctypes.c_size_t
     L.asp_bert_workspace_bytes.restype = ctypes.c_size_t
     _lib = L
     return L

@@ -410,8 +410,8 @@ class AspireConSent(nn.Module):
         return doc_cls_reps, sent_reps
 
     # "bf16x3": fp32-equivalent split-bf16 tensor-core math (default, parity with the reference's fp32 forward);
-    # "bf16": plain bf16 operands (fastest); "hf": run the HF module on the GPU instead of the sm_100a kernels
-    # (library path, kept only as an A/B aid for debugging).
+    # "bf16": plain bf16 operands (fastest).  Both run the sm_100a kernels; there is no library backend in this class
+    # (the Hugging Face forward used as a comparison lives in tools/encoder_bench.py and the tests).
     encoder_precision = "bf16x3"
 
     def _device(self):
@@ -439,12 +439,8 @@ class AspireConSent(nn.Module):
 
     def encode_hidden(self, tokid_tt, seg_tt, attnmask_tt, seq_lens=None):
         """BERT forward -> last_hidden_state fp32 [B,L,768] on the GPU (K0)."""
-        if self.encoder_precision == "hf":
-            dev = self._device()
-            if next(self.bert_encoder.parameters()).device != dev:
-                self.bert_encoder.to(dev)
-            out = self.bert_encoder(tokid_tt, token_type_ids=seg_tt, attention_mask=attnmask_tt)
-            return out.last_hidden_state.float()
+        if self.encoder_precision not in ("bf16x3", "bf16"):
+            raise ValueError(f"encoder_precision must be 'bf16x3' or 'bf16' (got {self.encoder_precision!r})")
         if seq_lens is None:
             seq_lens = attnmask_tt.sum(dim=1)
         return self.native_encoder().forward(tokid_tt, seq_lens, type_ids=seg_tt, precision=self.encoder_precision)

@@ -58,20 +58,12 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_ot_kernel = value;
         return ASP_OK;
     }
-    if (strcmp(key, "ot_fused_mode") == 0) {  // developer switch: 1 Gram/Sinkhorn-warp kernel (v7), 0 both phases per warp
-        asp::g_ot_fused_mode = value != 0;
-        return ASP_OK;
-    }
     if (strcmp(key, "ot_varlen") == 0) {  // developer switch: 1 one-kernel path for 11..32-sentence documents, 0 cost + Sinkhorn kernels
         asp::g_ot_varlen = value != 0;
         return ASP_OK;
     }
     if (strcmp(key, "vl_flags") == 0) {  // developer switches of ot_varlen.cu
         asp::g_vl_flags = value;
-        return ASP_OK;
-    }
-    if (strcmp(key, "ot_stagger") == 0) {  // developer switch: phase stagger of the fused kernel on (1) / off (0)
-        asp::g_ot_stagger = value != 0;
         return ASP_OK;
     }
     if (strcmp(key, "gemm_kernel") == 0) {  // developer switch: see bert/gemm.cu

@@ -65,8 +65,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int sm_count();
 extern int g_ot_kernel;  // asp_set_option("ot_kernel")
-extern int g_ot_stagger; // asp_set_option("ot_stagger")
-extern int g_ot_fused_mode;  // asp_set_option("ot_fused_mode")
 extern int g_gemm_kernel;    // asp_set_option("gemm_kernel")
 extern int g_gemm_cluster;   // asp_set_option("gemm_cluster")
 extern int g_gemm_pair;      // asp_set_option("gemm_pair")

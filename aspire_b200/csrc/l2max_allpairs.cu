@@ -219,8 +219,11 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
         if (any) {
             // |q|^2 + |c|^2 - 2 q.c loses its digits when q ~ c (near-duplicate sentences): re-evaluate such a
             // minimum as sum (q-c)^2 in fp32 from the original rows (rare; exact where the ranking is decided)
+            // (torch.cdist / scipy cdist, which the reference uses for tsAspire, give exactly 0 for identical rows)
             const size_t qrow = (size_t)gq * S + bi / S, crow = (size_t)gc * S + bi % S;
+            bool refined = false;
             if (bd < 0.01f * (__ldg(g.qn + qrow) + __ldg(g.cn + crow))) {
+                refined = true;
                 const float4* qr = reinterpret_cast<const float4*>(g.q + qrow * g.D);
                 const float4* cr = reinterpret_cast<const float4*>(g.c + crow * g.D);
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -231,8 +234,9 @@ l2max_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_co
                 }
                 bd = (s0 + s1) + (s2 + s3);
             }
+            bd = refined ? bd : fmaxf(bd, 1e-8f);
         }
-        g.scores[(size_t)gq * g.NC + gc] = any ? -sqrtf(fmaxf(bd, 1e-8f)) : kPadNeg;
+        g.scores[(size_t)gq * g.NC + gc] = any ? -sqrtf(bd) : kPadNeg;
         if (g.flat_idx) g.flat_idx[(size_t)gq * g.NC + gc] = any ? bi : 0;
     }
 }

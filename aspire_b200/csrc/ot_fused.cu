@@ -8,11 +8,11 @@
 // for documents of at most kFT sentences (the reference's abstracts: 10-sentence synthetic config, CSFCube ~7).
 //
 // Every candidate row is read from HBM exactly once (30 KB per pair), only 4-8 bytes per pair are written, and the
-// query never comes from memory in the inner loop.  Two kernels share the phase-1 code below:
+// query never comes from memory in the inner loop.
 //
-//   ot_fused_v7_kernel (default) -- 12 warps per SM, specialised by pipe and sized with setmaxnreg:
+//   ot_fused_v7_kernel -- 12 warps per SM, specialised by pipe and sized with setmaxnreg:
 //     * 8 Gram warps (two per scheduler, 200 registers), phase 1 on the FMA pipe: half-tiles of <= 16 pairs from a
-//       global atomic counter; per pair the two HALF-WARPS take 5 query rows each and their 16 lanes split the
+//       launch-owned atomic counter; per pair the two HALF-WARPS take 5 query rows each and their 16 lanes split the
 //       embedding dimension.  Candidate rows are staged by cp.async through a per-warp shared-memory ring (4 slices =
 //       10 KB in flight per warp, 80 KB per SM; the stream runs across pair boundaries) and read back with one
 //       128-bit LDS per row.  The QUERY rows live in TENSOR MEMORY: each lane parks its 240 floats of the current
@@ -23,9 +23,8 @@
 //       tile streamed from shared memory every step (ot_pair.cuh: solve_pair_thread_stream), one ex2 per (i,j) and
 //       step; full 10x10 tiles run a mask-free specialisation.
 //     * hand-over: per scheduler a ring of four half-tiles, ticketed slots, full/empty mbarriers, parked waits.
-//   ot_fused_kernel (asp_set_option("ot_fused_mode", 0)) -- the previous design: 8 warps per SM, every warp runs
-//     phase 1 on a 32-pair tile and then phase 2 with the cost tile in registers (solve_pair_thread); warps w and w+4
-//     share a scheduler and are phase-staggered so that one is on the FMA pipe while the other is on the MUFU pipe.
+// (The round-1 predecessor -- 8 warps per SM, every warp running both phases, phase-staggered -- is gone: the A/B that
+// kept it alive is recorded in profiles/r01_al_sustained_ab.txt.)
 #include <algorithm>
 #include "bert/tc05.cuh"
 #include "gram.cuh"
@@ -35,22 +34,18 @@ namespace asp {
 
 constexpr int kFT = 10;        // max sentences per document on the fused path
 constexpr int kHR = kFT / 2;   // query rows per half-warp
-constexpr int kFusedWarps = 8; // warps per CTA; ONE CTA per SM, so warps w and w+4 share a scheduler (SM sub-partition)
-constexpr int kCostLd = 101;   // floats per pair in the shared cost tile
+constexpr int kCostLd = 101;   // floats per pair in a padded cost tile (default of phase1's LD)
 constexpr int kRedVals = 64;   // 50 dot products + 5 candidate norms, padded for the 16-lane transpose-reduce
 constexpr int kRing = 5;                   // candidate slices in the per-warp cp.async ring (kRing-1 in flight)
 constexpr int kSliceFloats = kFT * 64;     // one slice: 64 floats of each of the kFT rows
 constexpr int kSliceBytes = kSliceFloats * 4;
-constexpr int kWarpSmem = 32 * kCostLd + 2 * kRedVals + 16 + kRing * kSliceFloats;  // cost tile, reduced values per
-                                                                                   // half, query norms, the ring
-constexpr int kCounterSlots = 256;
+constexpr int kCounterSlots = 1024;
 constexpr int kQCols = 20;        // TMEM columns per query slice and lane: kHR rows x 4 floats
 constexpr int kTmemCols = 512;    // the whole tensor memory of the SM: 256 columns per warp of a lane quadrant;
                                   // D/64 * kQCols <= 256  =>  D <= 768
 constexpr int kMaxFusedD = 768;
 
-__device__ unsigned int g_tile_counter[kCounterSlots];
-__device__ unsigned int g_done_counter[kCounterSlots];
+__device__ unsigned int g_tile_counter[kCounterSlots];  // launch-owned: a launch's slot is zeroed on its own stream
 
 struct FusedArgs {
     const float* q;
@@ -59,8 +54,8 @@ struct FusedArgs {
     const int32_t* c_lens;
     const int32_t* c_index;  // optional: pair b scores candidate document c_index[b] of a resident corpus (c, c_lens are
                              // then indexed by document id); NULL = candidate b
-    int q_group, B, Sq, Sc, D, slot;
-    int stagger;     // 1: warp w+4 starts after warp w's first phase 1 (asp_set_option "ot_stagger")
+    int q_group, B, Sq, Sc, D;
+    unsigned int* counter;  // tile counter of this launch
     int tile_pairs;  // pairs per warp tile (<= 32; chosen by the launcher so that the tiles fill whole waves of warps)
     float inv_temp;
 };
@@ -334,120 +329,6 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
     __syncwarp();
 }
 
-// Phase 2 lives in its own (non-inlined) functions so that it gets a register allocation of its own: the solver wants
-// ~200 registers for the 10x10 tile and the potentials, and must not share them with phase 1's live state.
-__device__ __noinline__ void fused_phase2(const float* row, int ql, int cl, int b, int Sq, int Sc, const float* eps_s,
-                                          int n_eps, float inv_temp, const OtOut* out) {
-    solve_pair_thread<kFT, kFT, false>([&](int i, int j) { return row[i * kFT + j]; }, ql, cl, b, Sq, Sc, eps_s, n_eps,
-                                       inv_temp, *out);
-}
-// every pair of the tile is a full kFT x kFT problem: no length masks anywhere in the step
-__device__ __noinline__ void fused_phase2_full(const float* row, int b, const float* eps_s, int n_eps, float inv_temp,
-                                               const OtOut* out) {
-    solve_pair_thread<kFT, kFT, true>([&](int i, int j) { return row[i * kFT + j]; }, kFT, kFT, b, kFT, kFT, eps_s, n_eps,
-                                      inv_temp, *out);
-}
-
-template <int DT>  // embedding size known at compile time (0 = runtime a.D); D % 128 == 0, D <= kMaxFusedD
-__global__ void __launch_bounds__(kFusedWarps * 32, 1)
-ot_fused_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
-    extern __shared__ float smem[];
-    __shared__ float eps_s[ASP_MAX_EPS];
-    __shared__ OtOut out_s;
-    __shared__ int lut_s[128];
-    __shared__ uint32_t tmem_slot;
-    __shared__ volatile int stagger_s[4];  // set by warp w (< 4) when its first phase 1 is over (or it has no work)
-    if (threadIdx.x < 4) stagger_s[threadIdx.x] = 0;
-    for (int k = threadIdx.x; k < sched.n; k += blockDim.x) eps_s[k] = sched.eps[k];
-    if (threadIdx.x == 0) out_s = out;
-    {
-        const int e = threadIdx.x;  // entry e of the 10x10 tile (row-major); 128 table slots
-        int pk = -1;
-        if (e < kFT * kFT) {
-            // query row i lives in half hh = i / kHR; that half holds candidate row j at position (j - kHR*hh) mod kFT,
-            // and |c_j|^2 was accumulated by half j / kHR at position j % kHR
-            const int i = e / kFT, j = e - i * kFT, hh = i / kHR, ii = i - hh * kHR;
-            const int jpos = (j + kFT - kHR * hh) % kFT;
-            const int dot = hh * kRedVals + ii * kFT + jpos, nrm = (j / kHR) * kRedVals + kHR * kFT + (j % kHR);
-            pk = dot | (nrm << 8) | (j << 16) | (i << 24);
-        }
-        if (e < 128) lut_s[e] = pk;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, kTmemCols);
-    tc::tc_fence_before_sync();
-    __syncthreads();
-    tc::tc_fence_after_sync();
-    // this warp's private tensor memory: the 32 lanes of quadrant warp % 4 (the only ones it can address), columns
-    // [256 * (warp / 4), +256)
-    const uint32_t tq = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
-    float* Cs = smem + (size_t)warp * kWarpSmem;  // cost tile of this warp's 32 pairs
-    float* red = Cs + 32 * kCostLd;               // [2][kRedVals] reduced Gram values of the pair being finished
-    float* qn_s = red + 2 * kRedVals;             // [16] squared norms of the current query's rows
-    float* ring = qn_s + 16;                      // [kRing][kSliceFloats] candidate slices (16-byte aligned)
-    const int ntiles = (a.B + a.tile_pairs - 1) / a.tile_pairs;
-
-    // Phase stagger.  Phase 1 saturates the FMA pipe and phase 2 the MUFU pipe, but two warps of one scheduler that
-    // start together stay in lockstep (equal tiles), queue for the same pipe and leave the other idle.  So warp w+4
-    // starts only when warp w has finished its first phase 1: from then on one of them streams/multiplies while the
-    // other iterates, and both pipes stay busy.
-    bool first = true;
-    if (a.stagger && warp >= 4) {
-        while (stagger_s[warp - 4] == 0) __nanosleep(2000);
-    }
-
-    for (;;) {
-        int tile = 0;
-        if (lane == 0) tile = (int)atomicAdd(&g_tile_counter[a.slot], 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
-        const int base = tile * a.tile_pairs;
-        const int npairs = min(a.tile_pairs, a.B - base);
-        // lane p keeps the lengths of pair base+p
-        int my_ql = 0, my_cl = 0, my_ci = 0;
-        if (lane < npairs) {
-            my_ci = a.c_index ? a.c_index[base + lane] : base + lane;
-            my_ql = min(max(a.q_lens[(base + lane) / a.q_group], 0), a.Sq);
-            my_cl = min(max(a.c_lens[my_ci], 0), a.Sc);
-        }
-        // uniform fast path: every pair of the tile has all kFT x kFT sentences (no predicates, no zero fill)
-        const bool full_tile = __all_sync(0xffffffffu, lane >= npairs || (my_ql == kFT && my_cl == kFT)) &&
-                               a.Sq == kFT && a.Sc == kFT;
-        if (full_tile)
-            phase1<DT, true>(a, base, npairs, my_ql, my_cl, my_ci, lane, Cs, red, qn_s, ring, tq, lut_s);
-        else
-            phase1<DT, false>(a, base, npairs, my_ql, my_cl, my_ci, lane, Cs, red, qn_s, ring, tq, lut_s);
-        __syncwarp();
-        if (first && warp < 4) {
-            if (lane == 0) stagger_s[warp] = 1;
-            first = false;
-        }
-
-        // ---------------- phase 2: one pair per thread ---------------------------------------------------------
-        if (lane < npairs) {
-            if (full_tile)
-                fused_phase2_full(Cs + lane * kCostLd, base + lane, eps_s, sched.n, a.inv_temp, &out_s);
-            else
-                fused_phase2(Cs + lane * kCostLd, my_ql, my_cl, base + lane, a.Sq, a.Sc, eps_s, sched.n, a.inv_temp,
-                             &out_s);
-        }
-        __syncwarp();
-    }
-    if (first && warp < 4 && lane == 0) stagger_s[warp] = 1;  // no tile at all: release the partner
-    // the last warp to leave re-arms the counters for the next launch that uses this slot
-    if (lane == 0) {
-        const unsigned int total_warps = gridDim.x * kFusedWarps;
-        if (atomicAdd(&g_done_counter[a.slot], 1u) == total_warps - 1) {
-            g_tile_counter[a.slot] = 0u;
-            g_done_counter[a.slot] = 0u;
-            __threadfence();
-        }
-    }
-    tc::tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_slot, kTmemCols);
-}
-
 // ---- v7: Gram warps + Sinkhorn warps ---------------------------------------------------------------------------------------
 // 12 warps per SM, all within 168 registers.  Warps 0-7 ("Gram" warps, two per scheduler) run phase 1 back to back on
 // half-tiles of 16 pairs and between them keep the scheduler's FMA pipe busy (one warp alone cannot: it issues at
@@ -537,7 +418,7 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
             int tile = 0;
             unsigned int ticket = 0;
             if (lane == 0) {
-                tile = (int)atomicAdd(&g_tile_counter[a.slot], 1u);
+                tile = (int)atomicAdd(a.counter, 1u);
                 ticket = atomicAdd(&ticket_s[w], 1u);
             }
             tile = __shfl_sync(0xffffffffu, tile, 0);
@@ -572,14 +453,6 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
                 meta_s[w][sl][1] = npairs;
                 meta_s[w][sl][2] = full_tile ? 1 : 0;
                 tc::mbar_arrive(&full_bar[w][sl]);  // release: tile + descriptor visible to the waiter
-            }
-        }
-        if (lane == 0) {  // the last Gram warp to leave re-arms the counters for the next launch using this slot
-            const unsigned int total = gridDim.x * kV7Gram;
-            if (atomicAdd(&g_done_counter[a.slot], 1u) == total - 1) {
-                g_tile_counter[a.slot] = 0u;
-                g_done_counter[a.slot] = 0u;
-                __threadfence();
             }
         }
     } else {
@@ -647,9 +520,6 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     if (warp == 0) tc::tmem_dealloc(tmem_slot, kTmemCols);
 }
 
-int g_ot_stagger = 1;
-int g_ot_fused_mode = 1;  // 1: Gram/Sinkhorn warp kernel (v7), 0: every warp runs both phases (asp_set_option "ot_fused_mode")
-
 bool ot_fused_supported(int Sq, int Sc, int D) {
     return Sq <= kFT && Sc <= kFT && D >= 128 && (D % 128) == 0 && D <= kMaxFusedD;
 }
@@ -658,53 +528,43 @@ int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const fl
                     const int32_t* c_index, int B, int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out,
                     cudaStream_t stream) {
     static std::atomic<unsigned int> next_slot{0};
-    const bool v7 = g_ot_fused_mode == 1;
-    const int smem_v6 = kFusedWarps * kWarpSmem * (int)sizeof(float), smem_v7 = kV7Smem * (int)sizeof(float);
-    const int smem = v7 ? smem_v7 : smem_v6;
+    const int smem = kV7Smem * (int)sizeof(float);
     static thread_local int attr_dev = -1;
+    static thread_local unsigned int* counters = nullptr;
     int dev = 0;
     ASP_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v6));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v6));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
-        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_v7));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ASP_CUDA(cudaFuncSetAttribute(ot_fused_v7_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        ASP_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&counters), g_tile_counter));
         attr_dev = dev;
     }
-    // Tile size: 32 pairs per warp once the batch can feed every resident warp; smaller batches are spread over more
-    // warps (down to one pair per warp) so that a single-query call (1 x 1k candidates) still uses the whole GPU.
-    // Tile size: the batch is cut into the smallest number of whole waves of resident warps (waves = ceil(B / (32 *
-    // warps))) and every tile gets ceil(B / (waves * warps)) <= 32 pairs, so no warp runs one tile more than the
-    // others; small batches spread down to one pair per warp so that a single 1 x 1k call still uses the whole GPU.
+    // Tile size: the batch is cut into the smallest number of whole waves of Gram warps (waves = ceil(B / (16 * warps)))
+    // and every tile gets ceil(B / (waves * warps)) <= 16 pairs, so no warp runs one tile more than the others; small
+    // batches spread down to one pair per warp so that a single 1 x 1k call still uses the whole GPU.
     const int max_ctas = sm_count();
-    const int per_cta = v7 ? kV7Gram : kFusedWarps;  // warps per CTA that take tiles
-    const int max_tile = v7 ? kV7Half : 32;
-    const int nwarps = max_ctas * per_cta;
-    const int waves = (B + max_tile * nwarps - 1) / (max_tile * nwarps);
-    const int tile_pairs = std::min(max_tile, std::max(1, (B + waves * nwarps - 1) / (waves * nwarps)));
-    FusedArgs a{q, q_lens, c, c_lens, c_index, q_group, B, Sq, Sc, D, (int)(next_slot.fetch_add(1) % kCounterSlots), g_ot_stagger,
-                tile_pairs,
-                1.0f / temp};
+    const int nwarps = max_ctas * kV7Gram;
+    const int waves = (B + kV7Half * nwarps - 1) / (kV7Half * nwarps);
+    const int tile_pairs = std::min(kV7Half, std::max(1, (B + waves * nwarps - 1) / (waves * nwarps)));
+    // launch-owned tile counter, zeroed on this launch's stream: an aborted earlier launch cannot leave it armed, and
+    // launches in flight on different streams never share one (1024 slots, round robin)
+    unsigned int* counter = counters + (next_slot.fetch_add(1) % kCounterSlots);
+    ASP_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    FusedArgs a{q, q_lens, c, c_lens, c_index, q_group, B, Sq, Sc, D, counter, tile_pairs, 1.0f / temp};
     const int ntiles = (B + tile_pairs - 1) / tile_pairs;
-    const int ctas = std::min(max_ctas, (ntiles + per_cta - 1) / per_cta);
-    if (v7) {
-        const bool rows = tile_pairs == 1;  // at most one pair per Gram warp: the low-latency instantiation
-        if (D == 768 && rows)
-            ot_fused_v7_kernel<768, true><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
-        else if (D == 768)
-            ot_fused_v7_kernel<768, false><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
-        else if (rows)
-            ot_fused_v7_kernel<0, true><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
-        else
-            ot_fused_v7_kernel<0, false><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
-    } else if (D == 768) {
-        ot_fused_kernel<768><<<ctas, kFusedWarps * 32, smem, stream>>>(a, sched, out);
-    } else {
-        ot_fused_kernel<0><<<ctas, kFusedWarps * 32, smem, stream>>>(a, sched, out);
-    }
-    ASP_LAUNCH_CHECK("ot_fused_kernel");
+    const int ctas = std::min(max_ctas, (ntiles + kV7Gram - 1) / kV7Gram);
+    const bool rows = tile_pairs == 1;  // at most one pair per Gram warp: the low-latency instantiation
+    if (D == 768 && rows)
+        ot_fused_v7_kernel<768, true><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+    else if (D == 768)
+        ot_fused_v7_kernel<768, false><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+    else if (rows)
+        ot_fused_v7_kernel<0, true><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+    else
+        ot_fused_v7_kernel<0, false><<<ctas, kV7Warps * 32, smem, stream>>>(a, sched, out);
+    ASP_LAUNCH_CHECK("ot_fused_v7_kernel");
     return ASP_OK;
 }
 

@@ -14,17 +14,33 @@ import torch
 from . import _abi
 
 
-def topk(scores, k, base_id=0):
-    """scores fp32 CUDA [Q,N] (higher = better) -> (top scores [Q,k], ids int64 [Q,k] = base_id + column)."""
+def topk(scores, k, base_id=0, negate=False, want_packed=False):
+    """scores fp32 CUDA [Q,N] (higher = better) -> (top scores [Q,k], ids int64 [Q,k] = base_id + column).
+
+    ``negate``: rank by -scores and return the negated values (OT distances: smaller = better) -- no separate
+    negation pass.  ``want_packed``: additionally return the list as sortable 64-bit keys [Q,k] (int64 storage of the
+    library's uint64: score bits << 32 | ~id), the one tensor ``gather_topk`` exchanges.  k <= 128 runs the single-pass
+    kernels (the matrix is read from HBM once); larger k the radix-select kernel."""
     _abi.require_cuda(scores)
     assert scores.dim() == 2 and scores.dtype == torch.float32
     scores = scores.contiguous()
     Q, N = scores.shape
+    L = _abi.lib()
     out_s = torch.empty((Q, k), dtype=torch.float32, device=scores.device)
     out_i = torch.empty((Q, k), dtype=torch.int64, device=scores.device)
-    _abi.check(_abi.lib().asp_topk(_abi.ptr(scores), Q, N, k, int(base_id), _abi.ptr(out_s), _abi.ptr(out_i),
-                                   _abi.stream_of(scores.device)), "asp_topk")
-    return out_s, out_i
+    need = int(L.asp_topk_workspace_bytes(Q, N, k))
+    if need == 0:
+        if want_packed:
+            raise _abi.AspireB200Error("topk: packed keys need k <= 128")
+        src = -scores if negate else scores
+        _abi.check(L.asp_topk(_abi.ptr(src), Q, N, k, int(base_id), _abi.ptr(out_s), _abi.ptr(out_i),
+                              _abi.stream_of(scores.device)), "asp_topk")
+        return out_s, out_i
+    ws = torch.empty(need, dtype=torch.uint8, device=scores.device)
+    packed = torch.empty((Q, k), dtype=torch.int64, device=scores.device) if want_packed else None
+    _abi.check(L.asp_topk_ws(_abi.ptr(scores), Q, N, k, int(base_id), int(bool(negate)), _abi.ptr(out_s), _abi.ptr(out_i),
+                             _abi.ptr(packed), _abi.ptr(ws), need, _abi.stream_of(scores.device)), "asp_topk_ws")
+    return (out_s, out_i, packed) if want_packed else (out_s, out_i)
 
 
 def topk_merge(scores, ids, k):
@@ -40,6 +56,48 @@ def topk_merge(scores, ids, k):
     return out_s, out_i
 
 
+def topk_merge_packed(gathered, k):
+    """gathered int64 [R,Q,k] packed keys exactly as ``all_gather_into_tensor`` lays them out -> (scores, ids) [Q,k]."""
+    _abi.require_cuda(gathered)
+    R, Q, kk = gathered.shape
+    assert kk == k and gathered.is_contiguous()
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=gathered.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=gathered.device)
+    _abi.check(_abi.lib().asp_topk_merge_packed(_abi.ptr(gathered), R, Q, k, _abi.ptr(out_s), _abi.ptr(out_i),
+                                                _abi.stream_of(gathered.device)), "asp_topk_merge_packed")
+    return out_s, out_i
+
+
+def pack_keys(scores, ids):
+    """Host restatement of the library's packed key: order-preserving score bits << 32 | (2^32-1 - id); 0 = filler.
+    Used by the gloo tests (the kernels produce the same keys on the device)."""
+    b = scores.contiguous().view(torch.int32).to(torch.int64) & 0xffffffff
+    b = torch.where(scores == 0, torch.zeros_like(b), b)                      # -0 == +0
+    key = torch.where(b >= 0x80000000, (~b) & 0xffffffff, b | 0x80000000)
+    key = torch.where(torch.isnan(scores), torch.zeros_like(key), key)
+    packed = (key << 32) | (0xffffffff - ids)
+    return torch.where(ids < 0, torch.zeros_like(packed), packed)            # int64 storage of the uint64 key
+
+
+def unpack_keys(packed):
+    """Inverse of ``pack_keys`` -> (scores fp32, ids int64); fillers give (-inf, -1)."""
+    key = (packed >> 32) & 0xffffffff
+    b = torch.where(key >= 0x80000000, key & 0x7fffffff, (~key) & 0xffffffff)
+    scores = torch.where(b >= 0x80000000, b - (1 << 32), b).to(torch.int32).view(torch.float32)
+    ids = 0xffffffff - (packed & 0xffffffff)
+    fill = packed == 0
+    return torch.where(fill, torch.full_like(scores, float("-inf")), scores), torch.where(fill, torch.full_like(ids, -1), ids)
+
+
+def host_merge_packed(gathered, k):
+    """Host merge of [R,Q,k] packed keys (unsigned descending order) -- the checker of asp_topk_merge_packed."""
+    R, Q, _ = gathered.shape
+    flat = gathered.permute(1, 0, 2).reshape(Q, R * k)
+    # unsigned 64-bit descending order on int64 storage: flip the sign bit
+    order = torch.argsort(flat ^ (-(1 << 63)), dim=1, descending=True, stable=True)[:, :k]
+    return unpack_keys(torch.gather(flat, 1, order))
+
+
 def shard_bounds(n_items, world_size, rank):
     """Contiguous, balanced split of [0, n_items): first (n % world) shards get one extra item."""
     base, extra = divmod(n_items, world_size)
@@ -47,22 +105,31 @@ def shard_bounds(n_items, world_size, rank):
     return start, start + base + (1 if rank < extra else 0)
 
 
-def gather_topk(local_scores, local_ids, k, group=None, merge_fn=None):
-    """All-gather per-rank top-k lists ([Q,k] fp32 / int64 with global ids) and merge them on every rank.
+def gather_topk(local_scores, local_ids, k, group=None, merge_fn=None, packed=None, out=None):
+    """All-gather per-rank top-k lists ([Q,k] with GLOBAL ids) and merge them on every rank.
 
-    One collective per tensor (NCCL all_gather over NVLink on the GPU box; gloo in the CPU tests, where
-    ``merge_fn`` supplies a host merge because the CUDA library is absent).
-    """
+    ONE collective: the lists travel as packed 64-bit keys (``packed`` from ``topk(..., want_packed=True)``, else built
+    here) through one ``all_gather_into_tensor`` into a [R,Q,k] buffer (``out``: preallocated, optional) that
+    ``asp_topk_merge_packed`` reads in place -- no second collective for the ids, no concatenation.  NCCL over NVLink on
+    the GPU box; gloo in the CPU tests, where the host restatement of the merge runs (``merge_fn`` kept for callers that
+    supply their own host merge of (scores, ids) lists)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local_scores, local_ids
     world = dist.get_world_size(group)
-    gs = [torch.empty_like(local_scores) for _ in range(world)]
-    gi = [torch.empty_like(local_ids) for _ in range(world)]
-    dist.all_gather(gs, local_scores.contiguous(), group=group)
-    dist.all_gather(gi, local_ids.contiguous(), group=group)
-    all_s, all_i = torch.cat(gs, dim=1), torch.cat(gi, dim=1)
-    return (merge_fn or topk_merge)(all_s, all_i, k)
+    if packed is None:
+        packed = pack_keys(local_scores, local_ids)
+    Q = packed.shape[0]
+    if out is None:
+        out = torch.empty((world, Q, k), dtype=torch.int64, device=packed.device)
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+        return topk_merge_packed(out, k)
+    dist.all_gather(list(out.unbind(0)), packed.contiguous(), group=group)  # gloo: list API
+    if merge_fn is not None:
+        s, i = unpack_keys(out)
+        return merge_fn(s.permute(1, 0, 2).reshape(Q, world * k), i.permute(1, 0, 2).reshape(Q, world * k), k)
+    return host_merge_packed(out, k)
 
 
 def host_merge(scores, ids, k):

@@ -46,7 +46,8 @@ int asp_sm_count(void);
 long long asp_launch_count(void);
 /* Tuning/testing knobs (process-wide; the defaults are the product path).
  *   "ot_kernel"     0 auto, 1 force warp-per-pair (never fuse), 2 force thread-per-pair
- *   "ot_fused_mode" 1 Gram/Sinkhorn-warp fused kernel (default), 0 both phases per warp;  "ot_stagger" 1/0
+ *   "ot_varlen"     1 (default) one-kernel path for 11..32-sentence documents, 0 cost tensor + Sinkhorn kernels;
+ *                   "vl_flags" developer bits of that kernel (1 every pair on the 32x32 variant, 2 no shape sort)
  *   "gemm_kernel"   encoder GEMM: 3 persistent kernel, tile width picked per shape (default); 1 / 4 / 2 force 128- /
  *                   192- / 256-wide tiles; 0 one tile per CTA
  *   "gemm_cluster"  1 (default), 2 or 4 CTAs per cluster sharing W tiles by TMA multicast
@@ -275,6 +276,22 @@ int asp_topk(const float* scores, int Q, long long N, int k, long long base_id, 
 /* Merge R per-shard top-k lists (as gathered over NCCL) into one: in_scores/in_ids [Q,R*k] -> out [Q,k]. */
 int asp_topk_merge(const float* in_scores, const long long* in_ids, int Q, int R, int k, float* out_scores,
                    long long* out_ids, asp_stream_t stream);
+
+/* Single-pass top-k (k <= 128, ids < 2^32): the score matrix is read from HBM once (one CTA per 8192-score chunk keeps
+ * its scores in registers, selects its own top-k and a second kernel merges the chunk lists of a query).  Same order
+ * as asp_topk.  negate != 0 ranks by -scores (the OT distances of asp_ot_score: smaller = better) and returns the
+ * negated values, so no separate negation pass is needed (pp_gen_nearest.py:194-202 sorts -distance).
+ * out_packed [Q,k] (optional, uint64): the entries as sortable keys (order-preserving score bits << 32 | ~id; 0 =
+ * filler) -- the ONE tensor a candidate-sharded job all-gathers; asp_topk_merge_packed merges the gathered
+ * [R][Q][k] lists of R ranks in that layout (no concatenation) into out_scores / out_ids [Q,k].
+ * workspace: asp_topk_workspace_bytes(Q,N,k) bytes of device scratch; when that is 0 (k > 128 or more than 8192/k
+ * chunks) or no workspace is given the call falls back to asp_topk (negate / out_packed are then rejected). */
+size_t asp_topk_workspace_bytes(int Q, long long N, int k);
+int asp_topk_ws(const float* scores, int Q, long long N, int k, long long base_id, int negate, float* out_scores,
+                long long* out_ids, unsigned long long* out_packed, void* workspace, size_t workspace_bytes,
+                asp_stream_t stream);
+int asp_topk_merge_packed(const unsigned long long* gathered, int R, int Q, int k, float* out_scores, long long* out_ids,
+                          asp_stream_t stream);
 
 /* ---- host front end of the encoder: BERT word pieces + sequence assembly (no GPU involved) -------------------
  * Replaces tokenizer.tokenize + convert_tokens_to_ids per sentence (examples/ex_aspire_consent.py:131-133 =

@@ -65,6 +65,42 @@ def test_topk_order_and_ties(Q, N, k):
     assert torch.equal(ts.cpu(), ws)
 
 
+@pytest.mark.parametrize("Q,N,k", [(3, 8192 * 70 + 17, 128), (2, 700000, 100), (5, 9000, 7), (2, 100, 128)])
+def test_topk_single_pass_negate_packed_and_multilevel_merge(Q, N, k):
+    """asp_topk_ws: ranking by -scores inside the kernel, packed keys equal to the host restatement, and more chunk lists
+    per query than one merge CTA holds (8192 / k) -> a second merge level."""
+    from aspire_b200.ranking import topk, host_merge, pack_keys, unpack_keys
+    g = torch.Generator().manual_seed(N + k)
+    s = torch.randn(Q, N, generator=g)
+    s[:, ::5] = torch.round(s[:, ::5] * 2) / 2           # exact ties across chunks
+    s[0, 3] = 0.0
+    s[0, 4] = -0.0
+    ts, ti, tp = topk(s.cuda(), k, base_id=77, negate=True, want_packed=True)
+    ids = (torch.arange(N) + 77).unsqueeze(0).expand(Q, -1)
+    ws, wi = host_merge(-s, ids, k)
+    assert torch.equal(ti.cpu(), wi)
+    assert torch.equal(ts.cpu(), ws)
+    assert torch.equal(tp.cpu(), pack_keys(ws, wi))
+    us, ui = unpack_keys(tp.cpu())
+    assert torch.equal(us, ws) and torch.equal(ui, wi)
+
+
+def test_topk_merge_packed_in_gathered_layout():
+    """asp_topk_merge_packed reads the [R, Q, k] buffer an all_gather_into_tensor fills, in place."""
+    from aspire_b200.ranking import topk, topk_merge_packed, host_merge, shard_bounds
+    g = torch.Generator().manual_seed(4)
+    Q, N, k, R = 33, 20011, 100, 8
+    s = torch.round(torch.randn(Q, N, generator=g) * 16) / 16
+    sd = s.cuda()
+    gathered = torch.empty(R, Q, k, dtype=torch.int64, device="cuda")
+    for r in range(R):
+        lo, hi = shard_bounds(N, R, r)
+        gathered[r] = topk(sd[:, lo:hi].contiguous(), k, base_id=lo, want_packed=True)[2]
+    ms, mi = topk_merge_packed(gathered, k)
+    ws, wi = host_merge(s, torch.arange(N).unsqueeze(0).expand(Q, -1), k)
+    assert torch.equal(mi.cpu(), wi) and torch.equal(ms.cpu(), ws)
+
+
 def test_topk_merge_vs_host():
     from aspire_b200.ranking import topk_merge, host_merge
     g = torch.Generator().manual_seed(1)
@@ -158,6 +194,77 @@ def test_ranking_parity_map():
         maps_o.append(ar.average_precision([int(rel[qi, j]) for j in order_ref]))
     assert abs(np.mean(maps_k) - np.mean(maps_o)) <= 1e-3
     assert np.mean(maps_k) > 0.5  # the synthetic relevance signal is actually recovered
+
+
+def test_ranking_parity_set_at_spec_size_ot_and_ts():
+    """SURVEY 8d ranking-parity set at its stated size: 50 queries x 1000 candidates, 100 relevant candidates per query
+    (each copies k in 1..5 query sentence vectors + 0.1 randn into random slots), seed 5678.  Ranked by the kernels and
+    by the oracle, for BOTH otAspire (-OT_eps) and tsAspire (max -dist): mean average precision within 1e-3; the
+    tsAspire flat argmax equals the float64 argmax except where the float64 top-2 gap is below 1e-5."""
+    from aspire_b200 import ot_scores, epsilon_schedule
+    from aspire_b200.distances import l2max_scores
+    g = torch.Generator().manual_seed(5678)
+    NQ, NC, NREL, S, D = 50, 1000, 100, 10, 768
+    Q = 0.3 * torch.randn(NQ, S, D, generator=g)
+    C = 0.3 * torch.randn(NC, S, D, generator=g)
+    eps = epsilon_schedule(60.0, 0.05, 0.9)
+    lens_c = torch.full((NC,), S).int().cuda()
+    ap = {k: [] for k in ("ot_kernel", "ot_oracle", "ts_kernel", "ts_oracle")}
+    argmax_checked = argmax_ties = 0
+    for qi in range(NQ):
+        rel = torch.zeros(NC, dtype=torch.bool)
+        rel[torch.randperm(NC, generator=g)[:NREL]] = True
+        pool = C.clone()
+        for cj in torch.nonzero(rel).view(-1).tolist():
+            n = int(torch.randint(1, 6, (1,), generator=g))
+            pool[cj, torch.randperm(S, generator=g)[:n]] = Q[qi, torch.randperm(S, generator=g)[:n]] + \
+                0.1 * torch.randn(n, D, generator=g)
+        qd, pd = Q[qi:qi + 1].cuda(), pool.cuda()
+        ql1 = torch.tensor([S]).int().cuda()
+        ot_k = -ot_scores(qd, ql1, pd, lens_c, eps, broadcast_query=True)["dual"].cpu().numpy()
+        ot_o = -ar.ot_distance(Q[qi:qi + 1].expand(NC, -1, -1), [S] * NC, pool, [S] * NC, diameter=60.0).numpy()
+        ts_k, idx_k, _ = l2max_scores(qd, ql1, pd, lens_c, broadcast_query=True)
+        d64 = torch.cdist(Q[qi:qi + 1].double().expand(NC, -1, -1), pool.double())      # [NC, S, S]
+        flat = (-d64).flatten(1)
+        top2 = torch.topk(flat, 2, dim=1)
+        ts_o = top2.values[:, 0].numpy()
+        relv = rel.numpy().astype(int)
+        for name, sc in (("ot_kernel", ot_k), ("ot_oracle", ot_o), ("ts_kernel", ts_k.cpu().numpy()), ("ts_oracle", ts_o)):
+            order = np.argsort(-sc.astype(np.float64), kind="stable")
+            ap[name].append(ar.average_precision(relv[order].tolist()))
+        assert np.abs(ts_k.cpu().numpy() - ts_o).max() <= 2e-5
+        clear = (top2.values[:, 0] - top2.values[:, 1]) > 1e-5
+        argmax_checked += int(clear.sum())
+        argmax_ties += int((~clear).sum())
+        assert torch.equal(idx_k.cpu().long()[clear], top2.indices[:, 0][clear])
+    m = {k: float(np.mean(v)) for k, v in ap.items()}
+    assert abs(m["ot_kernel"] - m["ot_oracle"]) <= 1e-3, m
+    assert abs(m["ts_kernel"] - m["ts_oracle"]) <= 1e-3, m
+    assert m["ot_kernel"] > 0.5 and m["ts_kernel"] > 0.5, m   # the planted relevance signal is recovered
+    assert argmax_checked >= 0.99 * NQ * NC, (argmax_checked, argmax_ties)
+
+
+def test_topk_shard_invariance_on_one_gpu():
+    """Sharded == unsharded ON THE DEVICE: a [Q, N] score matrix is cut into 8 contiguous candidate shards (uneven sizes),
+    each shard's top-k taken with its base id (what every rank does), the 8 partial lists merged by ``asp_topk_merge``
+    -- the result must equal the top-k of the whole matrix bit for bit, duplicated scores included (order: score
+    descending, global id ascending)."""
+    from aspire_b200.ranking import topk, topk_merge, shard_bounds
+    g = torch.Generator(device="cuda").manual_seed(9)
+    Q, N, k, W = 64, 30011, 100, 8
+    scores = torch.randn(Q, N, device="cuda", generator=g)
+    scores[:, ::7] = scores[:, 3:4]            # heavy exact ties across shards
+    scores[5] = 1.25                           # a fully tied row
+    whole_s, whole_i = topk(scores, k)
+    parts_s, parts_i = [], []
+    for r in range(W):
+        lo, hi = shard_bounds(N, W, r)
+        s, i = topk(scores[:, lo:hi].contiguous(), k, base_id=lo)
+        parts_s.append(s)
+        parts_i.append(i)
+    ms, mi = topk_merge(torch.cat(parts_s, dim=1), torch.cat(parts_i, dim=1), k)
+    assert torch.equal(mi, whole_i) and torch.equal(ms, whole_s)
+    assert torch.equal(whole_i[5].cpu(), torch.arange(k, dtype=whole_i.dtype))
 
 
 def test_score_pools_host_matches_device_path_and_oracle():

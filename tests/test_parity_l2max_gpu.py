@@ -131,6 +131,52 @@ def test_allpairs_tensor_core_path_vs_pair_kernel_and_fp64(NQ, NC, S, D):
     assert (best.cpu() - scores.cpu()[2]).abs().max().item() <= 2e-5
 
 
+def test_config3_allpairs_100x20k_vs_fp64_top100_and_argmax():
+    """BASELINE configs[2] (tsAspire 1k x 100k) on a 100 x 20 000 slice -- 2e8 sentence pairs -- against float64:
+    every score within 2e-5, the flat argmax exact wherever the float64 top-2 gap of the pair exceeds 1e-5, and the
+    per-query top-100 (ids, in order) equal to the float64 ranking wherever neighbouring float64 scores are further apart
+    than the score tolerance."""
+    from aspire_b200.distances import l2max_allpairs
+    from aspire_b200.ranking import topk
+    g = torch.Generator(device="cuda").manual_seed(2345)
+    NQ, NC, S, D, K = 100, 20000, 10, 768, 100
+    q = 0.3 * torch.randn(NQ, S, D, device="cuda", generator=g)
+    c = 0.3 * torch.randn(NC, S, D, device="cuda", generator=g)
+    ql = torch.randint(6, S + 1, (NQ,), device="cuda", generator=g).int()
+    cl = torch.randint(3, S + 1, (NC,), device="cuda", generator=g).int()
+    rows = torch.arange(S, device="cuda")
+    q *= (rows[None, :] < ql[:, None])[:, :, None]
+    c *= (rows[None, :] < cl[:, None])[:, :, None]
+    c[77, 2] = q[5, 1]                                   # one exact duplicate sentence (distance 0)
+    scores, idx = l2max_allpairs(q, ql, c, cl, want_idx=True)
+    top_s, top_i = topk(scores, K)
+    # float64 checker on the GPU: |q|^2 + |c|^2 - 2 q.c in double (cancellation ~1e-13), masked by the lengths
+    q64, c64 = q.double().view(NQ * S, D), c.double().view(NC * S, D)
+    d2 = (q64 * q64).sum(1)[:, None] + (c64 * c64).sum(1)[None, :] - 2.0 * (q64 @ c64.T)
+    sim = -d2.clamp_min(0).sqrt().view(NQ, S, NC, S).permute(0, 2, 1, 3)            # [NQ, NC, S, S]
+    valid = (rows[None, None, :, None] < ql[:, None, None, None]) & (rows[None, None, None, :] < cl[None, :, None, None])
+    sim = torch.where(valid, sim, torch.full_like(sim, -1e9)).reshape(NQ, NC, S * S)
+    top2 = torch.topk(sim, 2, dim=2)
+    ref = top2.values[..., 0]
+    err = (scores.double() - ref).abs()
+    assert err.max().item() <= 2e-5
+    assert scores[5, 77].item() == 0.0                  # the duplicate is re-evaluated exactly, like cdist: distance 0
+    clear = (top2.values[..., 0] - top2.values[..., 1]) > 1e-5
+    assert clear.float().mean().item() > 0.999
+    assert torch.equal(idx.long()[clear], top2.indices[..., 0][clear])
+    ref_sorted, ref_order = torch.sort(ref, dim=1, descending=True, stable=True)
+    assert (top_s.double() - ref_sorted[:, :K]).abs().max().item() <= 2e-5
+    # the candidate the kernel puts at rank r is, in float64, as good as the float64 rank-r candidate (near-ties may swap)
+    picked = torch.gather(ref, 1, top_i)
+    assert (picked - ref_sorted[:, :K]).abs().max().item() <= 4e-5
+    # ... and is THE float64 rank-r candidate wherever that one is separated from both neighbours by more than 1e-4
+    below = ref_sorted[:, :K] - ref_sorted[:, 1:K + 1]
+    above = torch.cat([torch.full_like(below[:, :1], 1.0), below[:, :-1]], dim=1)
+    safe = (below > 1e-4) & (above > 1e-4)
+    assert safe.float().mean().item() > 0.2
+    assert torch.equal(top_i[safe], ref_order[:, :K][safe])
+
+
 def test_l2top2_and_attention_heads_vs_reference_golden():
     """allpair_masked_dist_l2topk and AllPairMaskedAttention (pair_distances.py:95-135,295-345) through
     asp_pair_cost + asp_pair_heads, against vectors produced by the unmodified reference (oracle/make_golden_heads.py)."""

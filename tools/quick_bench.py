@@ -39,14 +39,12 @@ def main():
             state["i"] += 1
             ot_scores(q, ql, cs[state["i"] % len(cs)], cl, eps, q_group=1000 if N >= 1000 else N, out=out, cost_workspace=ws)
         res = {}
-        for k, name, mode in ((0, "fused-v7", 1), (0, "fused-v6", 0), (1, "cost+warp", 1)):
+        for k, name in ((0, "fused"), (1, "cost+warp")):
             if name == "cost+warp" and N > 300000:
                 continue
             _abi.set_option("ot_kernel", k)
-            _abi.set_option("ot_fused_mode", mode)
             res[name] = timeit(call)
         _abi.set_option("ot_kernel", 0)
-        _abi.set_option("ot_fused_mode", 1)
         t_l2 = timeit(lambda: l2max_scores(q[:1], ql[:1], cs[0], cl, broadcast_query=True))
         gb = N * 30732 / 1e9
         print(f"N={N:8d} " + "  ".join(f"{n} {t:8.3f} ms ({N / t * 1e3:.3e} pairs/s, {gb / t * 1e3:7.1f} GB/s)"

@@ -35,12 +35,9 @@ def main():
         def call():
             st["i"] += 1
             ot_scores(q, ql, cs[st["i"] % 2], cl, eps, q_group=POOL, out=out)
-        for mode in (1, 0):
-            _abi.set_option("ot_fused_mode", mode)
-            t = timeit(call)
-            by = float(cl.sum().item()) * 768 * 4 + 12 * N
-            print(f"{name:28s} mode {'v7' if mode else 'v6'}: {t:.3f} ms  {N / t * 1e3:.3e} pairs/s  {by / t / 1e6:.0f} GB/s of valid rows", flush=True)
-        _abi.set_option("ot_fused_mode", 1)
+        t = timeit(call)
+        by = float(cl.sum().item()) * 768 * 4 + 12 * N
+        print(f"{name:28s}: {t:.3f} ms  {N / t * 1e3:.3e} pairs/s  {by / t / 1e6:.0f} GB/s of valid rows", flush=True)
         cs = [0.3 * torch.randn(N, 10, 768, device=dev, generator=g) for _ in range(2)]
 
 

@@ -7,8 +7,7 @@ from aspire_b200.distances import l2max_scores, pair_heads
 
 g = torch.Generator().manual_seed(0)
 eps = epsilon_schedule(30.0, 0.05, 0.9)[:12]
-for mode in (1, 0):
-    _abi.set_option("ot_fused_mode", mode)
+for _once in (0,):
     for (B, Sq, Sc, D, grp) in ((700, 10, 10, 768, 100), (333, 7, 9, 256, 1), (40, 10, 10, 768, 40)):
         nq = -(-B // grp)
         q = (0.3 * torch.randn(nq, Sq, D, generator=g)).cuda()
