@@ -68,6 +68,7 @@ def lib():
     L.asp_ot_score_workspace_bytes.argtypes = [ci, ci, ci, ci]
     L.asp_ot_score_indexed.argtypes = [vp, vp, ci, vp, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, ctypes.POINTER(AspOtOutputs), vp]
     L.asp_ot_score_allpairs.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, c_float_p, ci, cf, vp, vp, ctypes.c_size_t, vp]
+    L.asp_ot_score_allpairs_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
     L.asp_ot_sinkhorn_from_cost.argtypes = [vp, vp, ci, vp, ci, ci, ci, c_float_p, ci, cf,
                                             ctypes.POINTER(AspOtOutputs), vp]
     L.asp_gemm_bf16_tn.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
@@ -98,6 +99,7 @@ def lib():
     L.asp_l2max_allpairs_workspace_bytes.restype = ctypes.c_size_t
     L.asp_l2max_workspace_bytes.restype = ctypes.c_size_t
     L.asp_topk_workspace_bytes.restype = ctypes.c_size_t
+    L.asp_ot_score_allpairs_workspace_bytes.restype = ctypes.c_size_t
     L.asp_bert_workspace_bytes.restype = ctypes.c_size_t
     _lib = L
     return L

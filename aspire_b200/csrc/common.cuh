@@ -101,6 +101,11 @@ int l2max_varlen_launch(const float* q, const int32_t* q_lens, int q_group, cons
                         size_t workspace_bytes, cudaStream_t stream);
 size_t ot_varlen_workspace_bytes(int B);  // scratch for the shape sort (0: batch too small to bother)
 OtOut to_out(const asp_ot_outputs* o);
+// Q x C all-pairs otAspire on tcgen05 (ot_allpairs.cu): documents of <= 10 sentences, D % 64 == 0
+bool ot_allpairs_supported(int Sq, int Sc, int D);
+size_t ot_allpairs_workspace_bytes(int NQ, int NC, int Sq, int Sc, int D);
+int ot_allpairs_launch(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens, int NC, int Sq,
+                       int Sc, int D, const EpsSched& sched, float temp, float* scores, void* workspace, cudaStream_t stream);
 
 // ---- device math ------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2(float x) {

@@ -609,14 +609,28 @@ extern "C" int asp_ot_score(const float* q, const int32_t* q_lens, int q_group, 
     return asp::launch_sinkhorn(cost, q_lens, q_group, c_lens, B, Sq, Sc, sched, temp, o, (cudaStream_t)stream);
 }
 
-// Q x C all-pairs mode: every query document against every candidate document, dual values only.  One fused launch per
-// query on the caller's stream (the kernel is bound by fp32 issue, not by memory, so re-streaming the candidates for
-// every query costs nothing), scores[i * NC + j] = OT_eps(query i, candidate j).
+// Q x C all-pairs mode: every query document against every candidate document, dual values only,
+// scores[i * NC + j] = OT_eps(query i, candidate j).  Documents of <= 10 sentences with the split-operand workspace go to
+// the tcgen05 kernel (ot_allpairs.cu: a candidate tile in shared memory serves 12 query documents; Gram matrices on the
+// tensor cores, Sinkhorn on the MUFU pipe).  Otherwise -- longer documents, a single query, or a caller that only brought
+// the asp_ot_score workspace -- one 1 x N launch per query on the caller's stream.
 extern "C" int asp_ot_score_allpairs(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens,
                                      int NC, int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp,
                                      float* scores, void* workspace, size_t workspace_bytes, asp_stream_t stream) {
     ASP_REQUIRE(scores, "asp_ot_score_allpairs: scores is NULL");
     ASP_REQUIRE(NQ >= 0 && NC >= 0, "asp_ot_score_allpairs: bad shape NQ=%d NC=%d", NQ, NC);
+    if (NQ == 0 || NC == 0) return ASP_OK;
+    if (NQ >= 2 && asp::g_ot_kernel == 0 && asp::ot_allpairs_supported(Sq, Sc, D) && workspace &&
+        workspace_bytes >= asp::ot_allpairs_workspace_bytes(NQ, NC, Sq, Sc, D) && (long long)NQ * NC <= 0x7fffffffLL) {
+        int rc = asp::check_pair_args(q, q_lens, c, c_lens, NC, Sq, Sc, D);
+        if (rc) return rc;
+        ASP_REQUIRE(temp > 0.f, "asp_ot_score_allpairs: temp must be > 0");
+        asp::EpsSched sched;
+        rc = asp::make_sched(eps_host, n_eps, &sched);
+        if (rc) return rc;
+        return asp::ot_allpairs_launch(q, q_lens, NQ, c, c_lens, NC, Sq, Sc, D, sched, temp, scores, workspace,
+                                       (cudaStream_t)stream);
+    }
     for (int i = 0; i < NQ; ++i) {
         asp_ot_outputs out = {};
         out.dual = scores + (size_t)i * NC;

@@ -127,7 +127,8 @@ def ot_scores_allpairs(q, q_lens, c, c_lens, eps_list, temp=1.0, out=None):
     """otAspire dual values of EVERY query document against EVERY candidate document (``asp_ot_score_allpairs``).
 
     q [NQ,Sq,D], c [NC,Sc,D] contiguous fp32 CUDA, lens int32 CUDA.  Returns fp32 [NQ, NC] (distances; negate for
-    similarities).  One fused launch per query, all on the current stream."""
+    similarities).  Documents of <= 10 sentences: ONE launch of the tcgen05 all-pairs kernel (Gram matrices on the tensor
+    cores, Sinkhorn on the MUFU pipe); otherwise one fused 1 x N launch per query.  All on the current stream."""
     _abi.require_cuda(q, c, q_lens, c_lens)
     NQ, Sq, D = q.shape
     NC, Sc, _ = c.shape
@@ -135,8 +136,8 @@ def ot_scores_allpairs(q, q_lens, c, c_lens, eps_list, temp=1.0, out=None):
     dev = c.device
     scores = out if out is not None else torch.empty((NQ, NC), dtype=torch.float32, device=dev)
     L = _abi.lib()
-    need = int(L.asp_ot_score_workspace_bytes(NC, Sq, Sc, D))
-    ws = torch.empty(max(need // 4, 1), dtype=torch.float32, device=dev) if need else None
+    need = int(L.asp_ot_score_allpairs_workspace_bytes(NQ, NC, Sq, Sc, D))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
     eps32 = np.asarray(eps_list, dtype=np.float32)
     _abi.check(L.asp_ot_score_allpairs(_abi.ptr(q), _abi.ptr(q_lens), NQ, _abi.ptr(c), _abi.ptr(c_lens), NC, Sq, Sc, D,
                                        eps32.ctypes.data_as(_abi.c_float_p), len(eps32), float(temp), _abi.ptr(scores),

@@ -232,9 +232,14 @@ int asp_mix_cls_scores(float* scores, const float* q_cls, int q_group, const flo
 /*
  * Q x C all-pairs mode of asp_ot_score (dual values only): scores[i*NC + j] = OT_eps(query i, candidate j) for every
  * query document i < NQ (q [NQ,Sq,D], q_lens [NQ]) and candidate document j < NC (c [NC,Sc,D], c_lens [NC]) -- the
- * all-queries x whole-corpus use of compute_distance (pair_distances.py:21-92 reached from pp_gen_nearest.py:154-202
- * for every query of a pool file).  One fused launch per query on `stream`; workspace as for asp_ot_score with B = NC.
+ * all-queries x whole-corpus use of compute_distance (pair_distances.py:21-92 reached from pp_gen_nearest.py:131-204
+ * for every query of a pool file).  Documents of <= 10 sentences (D % 64 == 0, NQ >= 2, NQ*NC < 2^31) run ONE launch of
+ * the tcgen05 all-pairs kernel: the Gram matrices of 12 query x 16 candidate documents per tile on the tensor cores
+ * (fp32-equivalent bf16 hi/lo split operands, fp32 accumulators in TMEM), the Sinkhorn solves on the MUFU pipe; it needs
+ * asp_ot_score_allpairs_workspace_bytes() of scratch (bf16 hi/lo copies of q and c + their squared norms).  Other shapes,
+ * or a smaller workspace (>= asp_ot_score_workspace_bytes with B = NC), run one 1 x N launch per query.
  */
+size_t asp_ot_score_allpairs_workspace_bytes(int NQ, int NC, int Sq, int Sc, int D);
 int asp_ot_score_allpairs(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens, int NC,
                           int Sq, int Sc, int D, const float* eps_host, int n_eps, float temp, float* scores,
                           void* workspace, size_t workspace_bytes, asp_stream_t stream);

@@ -52,6 +52,27 @@ def main():
               f"{flops / t / 1e9:.0f} TFLOP/s algorithmic ({flops / t / 1e9 / PEAKS['bf16_tflops']:.3f} of measured bf16 peak; "
               f"the kernel issues 4 bf16 MMAs per product: {4 * flops / t / 1e9:.0f} TFLOP/s on the pipe)", flush=True)
         del q, c
+    if not only or "otallpairs" in only:
+        # config 4 per-GPU shape, shortened: 1k queries x NC candidates (10 sentences, 768-d) through the tcgen05 all-pairs
+        # OT kernel vs one 1 x N fused launch per query (the round-1 path), same 71-entry schedule as the headline bench
+        from aspire_b200 import ot_scores_allpairs
+        NQ, NC, S, D = 1000, int(os.environ.get('ASP_OTAP_NC', 20000)), 10, 768
+        q = 0.3 * torch.randn(NQ, S, D, device=dev, generator=g)
+        c = 0.3 * torch.randn(NC, S, D, device=dev, generator=g)
+        ql = torch.full((NQ,), S, dtype=torch.int32, device=dev)
+        cl = torch.full((NC,), S, dtype=torch.int32, device=dev)
+        eps = epsilon_schedule(65.0, 0.05, 0.9)
+        out = torch.empty(NQ, NC, device=dev)
+        t = timeit(lambda: ot_scores_allpairs(q, ql, c, cl, eps, out=out), iters=3, warm=1)
+        print(f"allpairs otAspire (tcgen05) {NQ}x{NC}: {t:.1f} ms  {NQ * NC / t * 1e3:.3e} pairs/s", flush=True)
+        ref = out.clone()
+        _abi.set_option("ot_kernel", 2)   # forces the per-query loop of 1 x N fused launches
+        nq_loop = 100
+        t = timeit(lambda: ot_scores_allpairs(q[:nq_loop], ql[:nq_loop], c, cl, eps, out=out[:nq_loop]), iters=2, warm=1)
+        _abi.set_option("ot_kernel", 0)
+        print(f"allpairs otAspire (1 x N launch per query) {nq_loop}x{NC}: {t:.1f} ms  {nq_loop * NC / t * 1e3:.3e} pairs/s; "
+              f"max rel diff between the two {((ref[:nq_loop] - out[:nq_loop]).abs() / out[:nq_loop].abs().clamp(min=1)).max().item():.2e}", flush=True)
+        del q, c, out, ref
     if not only or "varlen" in only:
         # config 5: paired documents with 2..30 sentences, 50-step schedule
         B, S, D = int(os.environ.get('ASP_VARLEN_B', 100000)), 30, 768
