@@ -66,6 +66,11 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_vl_flags = value;
         return ASP_OK;
     }
+    if (strcmp(key, "oa_warps") == 0) {  // developer switch: Sinkhorn warps per CTA of ot_allpairs.cu
+        ASP_REQUIRE(value == 8 || value == 12, "asp_set_option: oa_warps must be 8 or 12");
+        asp::g_oa_warps = value;
+        return ASP_OK;
+    }
     if (strcmp(key, "gemm_kernel") == 0) {  // developer switch: see bert/gemm.cu
         ASP_REQUIRE(value >= 0 && value <= 4, "asp_set_option: gemm_kernel must be 0..4");
         asp::g_gemm_kernel = value;

@@ -106,7 +106,10 @@ ot_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_const
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
-
+    // NW = 12: the 20 warps start at 96 registers (launch bound); the front warps hand theirs to the Sinkhorn warps:
+    // 8 x 56 + 12 x 120 = 1888 <= 2048 per lane slot (warpgroup-aligned: warps 0-7 / 8-19)
+    if (warp < kOaFrontWarps) {
+    if (NW > 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
         // ------------------------------ TMA producer ---------------------------------------------------------------
         if (lane == 0) {
@@ -199,8 +202,10 @@ ot_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_const
             mbar_arrive(&acc_empty[buf]);
             if (in_tile) mbar_arrive(&cfull[w]);  // release: this row's 16 x Sc costs are visible to the Sinkhorn warp
         }
-    } else if (warp >= kOaFrontWarps) {
+    }
+    } else {
         // ------------------------------ Sinkhorn: one pair per thread ----------------------------------------------
+        if (NW > 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         const int w = warp - kOaFrontWarps;
         OtOut out = {};
         out.dual = g.scores;
@@ -240,7 +245,25 @@ size_t ot_allpairs_workspace_bytes(int NQ, int NC, int Sq, int Sc, int D) {
     return split_rows_bytes((size_t)NQ * Sq, D) + split_rows_bytes((size_t)NC * Sc, D);
 }
 
-constexpr int kOaSinkWarps = 8;
+int g_oa_warps = 12;  // asp_set_option("oa_warps"): Sinkhorn warps per CTA (12: three per scheduler, default; 8)
+
+template <int NW>
+static int oa_launch(const CUtensorMap& tq_hi, const CUtensorMap& tq_lo, const CUtensorMap& tc_hi, const CUtensorMap& tc_lo,
+                     const OtAllPairsArgs& g, const EpsSched& sched, cudaStream_t stream) {
+    constexpr int smem = oa_smem_bytes<NW>();
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        ASP_CUDA(cudaFuncSetAttribute(ot_allpairs_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_dev = dev;
+    }
+    const long long ntiles = (long long)g.nqt * g.nct;
+    const int ctas = (int)std::min<long long>(sm_count(), ntiles);
+    ot_allpairs_kernel<NW><<<ctas, (kOaFrontWarps + NW) * 32, smem, stream>>>(tq_hi, tq_lo, tc_hi, tc_lo, g, sched);
+    ASP_LAUNCH_CHECK("ot_allpairs_kernel");
+    return ASP_OK;
+}
 
 int ot_allpairs_launch(const float* q, const int32_t* q_lens, int NQ, const float* c, const int32_t* c_lens, int NC, int Sq,
                        int Sc, int D, const EpsSched& sched, float temp, float* scores, void* workspace, cudaStream_t stream) {
@@ -258,20 +281,8 @@ int ot_allpairs_launch(const float* q, const int32_t* q_lens, int NQ, const floa
     if ((rc = make_tmap_bf16_k32(&tc_lo, cs.lo, (uint64_t)NC * Sc, D, kOaDocsN * Sc))) return rc;
     OtAllPairsArgs g{qs.norms, cs.norms, q_lens, c_lens, NQ, NC, Sq, Sc, D, (NQ + kOaDocsM - 1) / kOaDocsM,
                      (NC + kOaDocsN - 1) / kOaDocsN, 1.0f / temp, scores};
-    constexpr int smem = oa_smem_bytes<kOaSinkWarps>();
-    static thread_local int attr_dev = -1;
-    int dev = 0;
-    ASP_CUDA(cudaGetDevice(&dev));
-    if (attr_dev != dev) {
-        ASP_CUDA(cudaFuncSetAttribute(ot_allpairs_kernel<kOaSinkWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_dev = dev;
-    }
-    const long long ntiles = (long long)g.nqt * g.nct;
-    const int ctas = (int)std::min<long long>(sm_count(), ntiles);
-    ot_allpairs_kernel<kOaSinkWarps><<<ctas, (kOaFrontWarps + kOaSinkWarps) * 32, smem, stream>>>(tq_hi, tq_lo, tc_hi, tc_lo, g,
-                                                                                               sched);
-    ASP_LAUNCH_CHECK("ot_allpairs_kernel");
-    return ASP_OK;
+    return g_oa_warps == 12 ? oa_launch<12>(tq_hi, tq_lo, tc_hi, tc_lo, g, sched, stream)
+                            : oa_launch<8>(tq_hi, tq_lo, tc_hi, tc_lo, g, sched, stream);
 }
 
 }  // namespace asp

@@ -132,6 +132,37 @@ def gather_topk(local_scores, local_ids, k, group=None, merge_fn=None, packed=No
     return host_merge_packed(out, k)
 
 
+def rank_corpus_ot(q, q_lens, c, c_lens, eps_list, k, base_id=0, chunk=25000, temp=1.0, group=None):
+    """Every query document against a resident corpus (shard) with otAspire, top-k per query -- the whole-corpus use of
+    compute_distance behind src/pre_process/pp_gen_nearest.py:131-204 (one caching_score call per query there).
+
+    q [NQ,Sq,D], c [NC,Sc,D] fp32 CUDA (this rank's candidates, global ids base_id + row), lens int32.  Candidates go
+    through the Q x C kernel (``asp_ot_score_allpairs``) ``chunk`` documents at a time; each chunk's [NQ, chunk]
+    distances are reduced at once to per-query top-k lists of -distance (packed keys), the lists are merged on the
+    device, and with an initialised process group the per-rank lists are all-gathered and merged (``gather_topk``).
+    Returns (similarities [NQ,k] = -OT distance, ids int64 [NQ,k]); order: similarity descending, id ascending."""
+    from .distances import ot_scores_allpairs
+    NQ, NC = q.shape[0], c.shape[0]
+    chunk = max(1, min(chunk, NC, (2 ** 31 - 1) // max(NQ, 1)))
+    starts = list(range(0, NC, chunk))
+    per_merge = max(1, 8192 // k)                       # lists one merge CTA takes
+    lists = torch.empty((min(len(starts), per_merge), NQ, k), dtype=torch.int64, device=q.device)
+    scores = torch.empty((NQ, chunk), dtype=torch.float32, device=q.device)
+    n, best = 0, None
+    for s0 in starts:
+        m = min(chunk, NC - s0)
+        sc = scores[:, :m] if m == chunk else torch.empty((NQ, m), dtype=torch.float32, device=q.device)
+        ot_scores_allpairs(q, q_lens, c[s0:s0 + m], c_lens[s0:s0 + m], eps_list, temp=temp, out=sc)
+        lists[n] = topk(sc, k, base_id=base_id + s0, negate=True, want_packed=True)[2]
+        n += 1
+        if n == lists.shape[0] and s0 != starts[-1]:    # buffer full: fold it into its first slot
+            s_, i_ = topk_merge_packed(lists[:n].contiguous(), k)
+            lists[0] = pack_keys(s_, i_)
+            n = 1
+    best = topk_merge_packed(lists[:n].contiguous(), k)
+    return gather_topk(best[0], best[1], k, group=group)
+
+
 def host_merge(scores, ids, k):
     """Host restatement of the merge order (used by the gloo tests and as the checker of topk_merge)."""
     Q = scores.shape[0]

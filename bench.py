@@ -333,6 +333,18 @@ def side_kernels(dev, hbm_peak):
                           "tflops_on_pipe": 4 * fl / t / 1e9, "frac_of_bf16_burst_on_pipe": 4 * fl / t / 1e9 / tf_burst,
                           "cpu_baseline": {"pairs_per_s": 10 * 10000 / cpu_s, "kind": "numpy cdist + max (pp_gen_nearest.py:942-961)",
                                            "sample": "10 queries x 10 000 candidates, one thread (scipy), extrapolated linearly"}}
+    # ---- configs[3] per-GPU shape, shortened: otAspire 1k queries x 20k candidates on the tcgen05 all-pairs kernel ----
+    from aspire_b200 import epsilon_schedule, ot_scores_allpairs
+    NCo = 20000
+    eps_h = epsilon_schedule(DIAMETER, BLUR, SCALING)
+    so = torch.empty(NQ, NCo, device=dev)
+    t = timeit(lambda: ot_scores_allpairs(q, ql, c[:NCo], cl[:NCo], eps_h, out=so), iters=3, warm=1)
+    out["allpairs_ot"] = {"workload": f"BASELINE configs[3] per-GPU shape, shortened: otAspire {NQ} queries x {NCo} candidates, "
+                                      f"10 sents, 768-d, {len(eps_h)}-entry schedule, one launch (operand split included)",
+                          "ms": t, "pairs_per_s": NQ * NCo / t * 1e3,
+                          "mufu_bound_pairs_per_s": "16 MUFU/clk/SM: (100 ex2 + 20 lg2) x 73 steps per pair -> ~5e8 pairs/s at 1.9 GHz",
+                          "vs_headline_1xN_kernel": "see `value`: the 1 x N kernel re-streams candidates per query and is bound by fp32 issue"}
+    del so
     # ---- top-k alone: 1k x 100k scores ----
     sc_all = torch.randn(NQ, NC, device=dev, generator=g)
     t = timeit(lambda: topk(sc_all, TOPK), iters=5, warm=2)

@@ -101,6 +101,24 @@ def test_topk_merge_packed_in_gathered_layout():
     assert torch.equal(mi.cpu(), wi) and torch.equal(ms.cpu(), ws)
 
 
+def test_rank_corpus_ot_chunked_equals_one_shot():
+    """rank_corpus_ot (candidate chunks -> per-chunk packed top-k -> device merge, buffer folding when there are more
+    chunks than one merge takes) == top-k of the negated [NQ, NC] all-pairs matrix computed in one call."""
+    from aspire_b200 import ot_scores_allpairs, epsilon_schedule
+    from aspire_b200.ranking import rank_corpus_ot, topk
+    g = torch.Generator().manual_seed(12)
+    NQ, NC, S, D, k = 30, 3001, 10, 128, 100
+    q = (0.3 * torch.randn(NQ, S, D, generator=g)).cuda()
+    c = (0.3 * torch.randn(NC, S, D, generator=g)).cuda()
+    ql = torch.randint(1, S + 1, (NQ,), generator=g).int().cuda()
+    cl = torch.randint(1, S + 1, (NC,), generator=g).int().cuda()
+    eps = epsilon_schedule(20.0, 0.05, 0.9)
+    want_s, want_i = topk(ot_scores_allpairs(q, ql, c, cl, eps), k, base_id=500, negate=True)
+    for chunk in (1000, 32):      # 4 chunks; 94 chunks (> 81 lists per merge: the buffer is folded once)
+        got_s, got_i = rank_corpus_ot(q, ql, c, cl, eps, k, base_id=500, chunk=chunk)
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+
+
 def test_topk_merge_vs_host():
     from aspire_b200.ranking import topk_merge, host_merge
     g = torch.Generator().manual_seed(1)
