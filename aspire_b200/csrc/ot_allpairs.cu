@@ -37,6 +37,18 @@ constexpr int kOaGroups = kOaDocsM / 2;      // groups of 32 pairs per tile
 constexpr int kOaLd = kOaFT * kOaFT;         // cost floats per pair
 constexpr int kOaFrontWarps = 8;             // producer, MMA, 2 spare, 4 drain
 constexpr int kOaAccCols = 256;              // TMEM columns per accumulator buffer
+// Waits of the front warps are long (the Sinkhorn warps set the pace): sleep-polling, ns between barrier tests
+#ifndef ASP_OA_IDLE_FRONT
+#define ASP_OA_IDLE_FRONT 400
+#endif
+#ifndef ASP_OA_IDLE_DRAIN
+#define ASP_OA_IDLE_DRAIN 200
+#endif
+template <int NS>
+__device__ __forceinline__ void oa_wait(uint64_t* bar, uint32_t parity) {
+    if (NS == 0) mbar_wait_parked(bar, parity);
+    else mbar_wait_sleep<NS>(bar, parity);
+}
 
 struct OtAllPairsArgs {
     const float* qn;        // [NQ*Sq] squared norms of the query sentence rows
@@ -119,7 +131,7 @@ ot_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_const
                 const int m0 = (t % g.nqt) * rows_m, n0 = (t / g.nqt) * cols_n;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % kOaStages, ph = (it / kOaStages) & 1;
-                    mbar_wait_parked(&empty[s], ph ^ 1);
+                    oa_wait<ASP_OA_IDLE_FRONT>(&empty[s], ph ^ 1);
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(rows_m + cols_n) * (kApBlockK * 2) * 2);
                     uint8_t* sa = smem + s * kApStage;
                     tma_load_2d(sa, &tq_hi, &full[s], kb * kApBlockK, m0);
@@ -136,12 +148,12 @@ ot_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_const
             int it = 0;
             for (int k = 0; k < my_tiles; ++k) {
                 const int buf = k & 1;
-                mbar_wait_parked(&acc_empty[buf], ((k >> 1) & 1) ^ 1);  // drain warps are done with this accumulator
+                oa_wait<ASP_OA_IDLE_FRONT>(&acc_empty[buf], ((k >> 1) & 1) ^ 1);  // drain warps are done with this accumulator
                 tc_fence_after_sync();
                 const uint32_t acc = tmem_base + (uint32_t)(buf * kOaAccCols);
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % kOaStages, ph = (it / kOaStages) & 1;
-                    mbar_wait_parked(&full[s], ph);
+                    oa_wait<ASP_OA_IDLE_FRONT>(&full[s], ph);
                     tc_fence_after_sync();
                     const uint32_t sa = smem_u32(smem + s * kApStage);
                     const uint64_t a_hi = umma_desc_sw64(sa), a_lo = umma_desc_sw64(sa + kApABytes);
@@ -173,9 +185,9 @@ ot_allpairs_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_const
                 cn_s[buf][c] = (c < cols_n && n0 + c < g.NC * Sc) ? __ldg(g.cn + n0 + c) : 0.f;
             const float qn = (in_tile && m0 + r < g.NQ * Sq) ? __ldg(g.qn + m0 + r) : 0.f;
             const int G = k * kOaGroups + gi, w = G % NW, use = G / NW;
-            if (in_tile) mbar_wait_parked(&cempty[w], (use & 1) ^ 1);  // the Sinkhorn warp has finished its previous group
+            if (in_tile) oa_wait<ASP_OA_IDLE_DRAIN>(&cempty[w], (use & 1) ^ 1);  // the Sinkhorn warp has finished its previous group
             asm volatile("bar.sync 1, 128;" ::: "memory");               // cn_s staged
-            mbar_wait_parked(&acc_full[buf], (k >> 1) & 1);
+            oa_wait<ASP_OA_IDLE_DRAIN>(&acc_full[buf], (k >> 1) & 1);
             tc_fence_after_sync();
             float* dst = cost + ((size_t)(w * 32 + (qd & 1) * kOaDocsN) * kOaLd + i * kOaFT);
             int j = 0, cdoc = 0;

@@ -35,6 +35,16 @@
 #define ASP_VL_U_SMALL 8
 #define ASP_VL_U_BIG 4
 #endif
+// Idle waits (a Sinkhorn warp waiting for its next cost tile, a producer waiting for ring space): nanoseconds of plain
+// sleep between non-blocking barrier tests; 0 = mbarrier.try_wait with a suspend hint.  The hinted form wakes on every
+// barrier event of the CTA (measured: one retry per ~17 ns per waiting warp, 45 % of the kernel's issued instructions),
+// which takes issue slots from the Gram warp of the same scheduler; a plain sleep does not.
+#ifndef ASP_VL_IDLE_SINK
+#define ASP_VL_IDLE_SINK 0
+#endif
+#ifndef ASP_VL_IDLE_PROD
+#define ASP_VL_IDLE_PROD 0
+#endif
 
 namespace asp {
 
@@ -285,6 +295,25 @@ __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+template <int NS>
+__device__ __forceinline__ void ws_mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    if (NS == 0) {
+        ws_mbar_wait(bar, parity);
+        return;
+    }
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(vl_smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(NS);
+    }
+}
 template <int N>
 __device__ __forceinline__ void ws_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -383,7 +412,7 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
                     const int cc = sh.cons_count[g];
                     const int cv = sh.cons_vpos[g];  // read after the count: never older than it
                     if (vpos + waste + pu - cv <= kWsRingUnits && issued - cc < kWsSeq - 1) break;
-                    ws_mbar_wait(&sh.slice_empty[g][cc & (kWsSeq - 1)], (cc >> 4) & 1);
+                    ws_mbar_wait_idle<ASP_VL_IDLE_PROD>(&sh.slice_empty[g][cc & (kWsSeq - 1)], (cc >> 4) & 1);
                 }
                 // row r0 + 4m of each side; chunk position = chunk ^ (row & 7), which alternates with the parity of m
                 const uint32_t slot = ring_u32 + (uint32_t)o * 1024u;
@@ -589,7 +618,7 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
 #pragma unroll 1
     for (int t = 0;; ++t) {
         const int buf = t & 1;
-        ws_mbar_wait(&sh.tile_full[sw][buf], (t >> 1) & 1);
+        ws_mbar_wait_idle<ASP_VL_IDLE_SINK>(&sh.tile_full[sw][buf], (t >> 1) & 1);
         const int* tm = sh.tmeta[sw][buf];
         const int b = tm[0], ql = tm[1], cl = tm[2];
         if (b < 0) break;
