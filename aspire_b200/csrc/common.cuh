@@ -102,6 +102,12 @@ int l2max_varlen_launch(const float* q, const int32_t* q_lens, int q_group, cons
 size_t ot_varlen_workspace_bytes(int B);  // scratch for the shape sort (0: batch too small to bother)
 OtOut to_out(const asp_ot_outputs* o);
 // Q x C all-pairs otAspire on tcgen05 (ot_allpairs.cu): documents of <= 10 sentences, D % 64 == 0
+// pools (one query against >= 128 candidates): Gram tiles on tcgen05, candidates split to bf16 hi/lo by producer warps
+extern int g_ot_fused_tc;  // asp_set_option("ot_fused_tc")
+bool ot_fused_tc_supported(int q_group, int B, int Sq, int Sc, int D);
+int ot_fused_tc_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
+                       const int32_t* c_index, int B, int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out,
+                       cudaStream_t stream);
 extern int g_oa_warps;  // asp_set_option("oa_warps")
 bool ot_allpairs_supported(int Sq, int Sc, int D);
 size_t ot_allpairs_workspace_bytes(int NQ, int NC, int Sq, int Sc, int D);

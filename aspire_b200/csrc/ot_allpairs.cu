@@ -37,16 +37,17 @@ constexpr int kOaGroups = kOaDocsM / 2;      // groups of 32 pairs per tile
 constexpr int kOaLd = kOaFT * kOaFT;         // cost floats per pair
 constexpr int kOaFrontWarps = 8;             // producer, MMA, 2 spare, 4 drain
 constexpr int kOaAccCols = 256;              // TMEM columns per accumulator buffer
-// Waits of the front warps are long (the Sinkhorn warps set the pace): sleep-polling, ns between barrier tests
+// Waits of the front warps are long (the Sinkhorn warps set the pace).  ns > 0: sleep-polling between barrier tests
+// instead of the hinted try_wait -- measured to make no difference (3.82e8 vs 3.84e8 pairs/s, profiles/r02_r_polling_ab.txt)
 #ifndef ASP_OA_IDLE_FRONT
-#define ASP_OA_IDLE_FRONT 400
+#define ASP_OA_IDLE_FRONT 0
 #endif
 #ifndef ASP_OA_IDLE_DRAIN
-#define ASP_OA_IDLE_DRAIN 200
+#define ASP_OA_IDLE_DRAIN 0
 #endif
 template <int NS>
 __device__ __forceinline__ void oa_wait(uint64_t* bar, uint32_t parity) {
-    if (NS == 0) mbar_wait_parked(bar, parity);
+    if constexpr (NS == 0) mbar_wait_parked(bar, parity);
     else mbar_wait_sleep<NS>(bar, parity);
 }
 

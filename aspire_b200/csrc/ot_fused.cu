@@ -527,6 +527,8 @@ bool ot_fused_supported(int Sq, int Sc, int D) {
 int ot_fused_launch(const float* q, const int32_t* q_lens, int q_group, const float* c, const int32_t* c_lens,
                     const int32_t* c_index, int B, int Sq, int Sc, int D, const EpsSched& sched, float temp, const OtOut& out,
                     cudaStream_t stream) {
+    if (ot_fused_tc_supported(q_group, B, Sq, Sc, D))
+        return ot_fused_tc_launch(q, q_lens, q_group, c, c_lens, c_index, B, Sq, Sc, D, sched, temp, out, stream);
     static std::atomic<unsigned int> next_slot{0};
     const int smem = kV7Smem * (int)sizeof(float);
     static thread_local int attr_dev = -1;

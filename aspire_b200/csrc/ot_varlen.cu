@@ -256,7 +256,10 @@ __device__ __forceinline__ void vl_sinkhorn_steps(const float2 (&Cr)[16], const 
 //               stream their slices into the Gram warp's byte ring with cp.async; completion is signalled per slice on
 //               an mbarrier (cp.async.mbarrier.arrive.noinc), ring space comes back through two shared counters.
 constexpr int kWsGram = 4, kWsSink = 8, kWsWarps = 16;
-constexpr int kWsRingUnits = 28;                               // per Gram warp: 28 KB
+#ifndef ASP_VL_RING_UNITS
+#define ASP_VL_RING_UNITS 28
+#endif
+constexpr int kWsRingUnits = ASP_VL_RING_UNITS;                // per Gram warp: 28 KB
 constexpr int kWsRingFloats = kWsRingUnits * kVlUnitFloats;
 constexpr int kWsSeq = 16;                                     // slice barriers per Gram warp (slices in flight < 16)
 constexpr int kWsQueue = 8;                                    // pair descriptors per Gram warp
@@ -297,21 +300,21 @@ __device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 template <int NS>
 __device__ __forceinline__ void ws_mbar_wait_idle(uint64_t* bar, uint32_t parity) {
-    if (NS == 0) {
+    if constexpr (NS == 0) {
         ws_mbar_wait(bar, parity);
-        return;
-    }
-    for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(vl_smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) break;
-        __nanosleep(NS);
+    } else {
+        for (;;) {
+            uint32_t ok;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(vl_smem_u32(bar)), "r"(parity)
+                : "memory");
+            if (ok) break;
+            __nanosleep(NS);
+        }
     }
 }
 template <int N>

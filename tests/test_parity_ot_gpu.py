@@ -372,3 +372,53 @@ def test_allpairs_tcgen05_kernel_vs_oracle(NQ, NC, Sq, Sc, D, full):
     for i in sel:
         ref = ar.ot_distance(q[i:i + 1].expand(NC, -1, -1), [int(ql[i])] * NC, c, cl.tolist(), diameter=40.0).numpy()
         assert rel_err(got[i], ref).max() <= 1e-4, (i, rel_err(got[i], ref).max())
+
+
+@pytest.mark.parametrize("B,grp,Sq,Sc,D,full,indexed", [(12000, 1000, 10, 10, 768, True, False),
+                                                       (11111, 700, 10, 10, 768, False, False),
+                                                       (10000, 128, 7, 9, 256, False, False),
+                                                       (9600, 4800, 10, 10, 384, False, True)])
+def test_pool_kernel_on_tensor_cores_equals_fma_kernel_and_oracle(B, grp, Sq, Sc, D, full, indexed):
+    """ot_fused_tc.cu (pools, q_group >= 128: Gram tiles on tcgen05 from bf16 hi/lo halves split in registers) against
+    ot_fused.cu (fp32 FFMA2) on the same input -- dual values and potentials to 2e-5 relative, the primal value and the
+    plan (which amplify cost differences by 1/blur = 20x; the tensor core's fp32 accumulation differs from an FFMA chain
+    by ~1e-6 relative per distance) to 1e-4 -- and against the oracle on a subsample:
+    full and ragged documents, q_group not dividing B (partial tiles, partial last Sinkhorn group), short padded shapes,
+    candidates addressed through an index list."""
+    from aspire_b200 import ot_scores, epsilon_schedule, _abi
+    g = torch.Generator().manual_seed(B + grp)
+    nq = -(-B // grp)
+    N = B + 100 if indexed else B
+    q = 0.3 * torch.randn(nq, Sq, D, generator=g)
+    c = 0.3 * torch.randn(N, Sc, D, generator=g)
+    ql = torch.full((nq,), Sq).int() if full else torch.randint(1, Sq + 1, (nq,), generator=g).int()
+    cl = torch.full((N,), Sc).int() if full else torch.randint(1, Sc + 1, (N,), generator=g).int()
+    c = c * (torch.arange(Sc)[None, :] < cl[:, None])[:, :, None]
+    q = q * (torch.arange(Sq)[None, :] < ql[:, None])[:, :, None]
+    idx = torch.randperm(N, generator=g)[:B].int() if indexed else None
+    eps = epsilon_schedule(40.0, 0.05, 0.9)
+    want = ("dual", "primal", "f", "g", "alpha", "beta", "plan")
+    res = {}
+    for mode in (1, 0):
+        _abi.set_option("ot_fused_tc", mode)
+        try:
+            res[mode] = ot_scores(q.cuda(), ql.cuda(), c.cuda(), cl.cuda(), eps, q_group=grp, want=want,
+                                  c_index=None if idx is None else idx.cuda())
+        finally:
+            _abi.set_option("ot_fused_tc", 0)   # the library default (the FFMA2 kernel is the faster one, see ot_fused_tc.cu)
+    for key in want:
+        x, y = res[1][key].cpu().numpy(), res[0][key].cpu().numpy()
+        assert np.isfinite(x).all(), key
+        if key in ("dual", "f", "g", "primal"):
+            # f and g carry a gauge direction (f + k, g - k) that the symmetric updates pin only weakly: individually
+            # they move more than the dual value they add up to
+            tol = {"dual": 2e-5, "primal": 1e-4, "f": 3e-4, "g": 3e-4}[key]
+            assert rel_err(x, y).max() <= tol, (key, rel_err(x, y).max())
+        else:
+            tol = (1e-4 if key == "plan" else 2e-5) * max(1.0, float(np.abs(y).max()))
+            assert np.abs(x - y).max() <= tol, (key, np.abs(x - y).max())
+    sub = torch.arange(0, B, max(1, B // 300))
+    cs = c[idx.long()[sub]] if indexed else c[sub]
+    cls = cl[idx.long()[sub]] if indexed else cl[sub]
+    ref = ar.ot_distance(q[sub // grp], ql[sub // grp].tolist(), cs, cls.tolist(), diameter=40.0).numpy()
+    assert rel_err(res[1]["dual"].cpu().numpy()[sub.numpy()], ref).max() <= 1e-4

@@ -17,6 +17,9 @@ ql = torch.full((N // POOL,), 10, dtype=torch.int32, device=dev)
 cl = torch.full((N,), 10, dtype=torch.int32, device=dev)
 out = {"dual": torch.empty(N, device=dev)}
 name = os.path.basename(os.environ.get("ASPIRE_B200_LIB", "in-tree"))
+if "ASP_TC" in os.environ:
+    _abi.set_option("ot_fused_tc", int(os.environ["ASP_TC"]))
+    name += f" ot_fused_tc={os.environ['ASP_TC']}"
 for rep in range(2):
     t_end = time.time() + 1.0
     i = 0
@@ -24,7 +27,7 @@ for rep in range(2):
         ot_scores(q, ql, cs[i % 3], cl, eps, q_group=POOL, out=out); i += 1
         torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 1000
+    n = int(os.environ.get("ASP_STEPS", 1000))
     a.record()
     for k in range(n):
         ot_scores(q, ql, cs[k % 3], cl, eps, q_group=POOL, out=out)
