@@ -48,6 +48,9 @@ long long asp_launch_count(void);
  *   "ot_kernel"     0 auto, 1 force warp-per-pair (never fuse), 2 force thread-per-pair
  *   "ot_varlen"     1 (default) one-kernel path for 11..32-sentence documents, 0 cost tensor + Sinkhorn kernels;
  *                   "vl_flags" developer bits of that kernel (1 every pair on the 32x32 variant, 2 no shape sort)
+ *   "ot_fused_tc"   0 (default) the FFMA2 1 x N kernel; 1 pools of >= 128 candidates per query on the tcgen05 prototype
+ *                   (ot_fused_tc.cu: same results, measured slower)
+ *   "oa_warps"      Sinkhorn warps per CTA of the Q x C all-pairs otAspire kernel: 12 (default) or 8
  *   "gemm_kernel"   encoder GEMM: 3 persistent kernel, tile width picked per shape (default); 1 / 4 / 2 force 128- /
  *                   192- / 256-wide tiles; 0 one tile per CTA
  *   "gemm_cluster"  1 (default), 2 or 4 CTAs per cluster sharing W tiles by TMA multicast
