@@ -137,6 +137,26 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// tsAspire's reference distance is torch.cdist / scipy cdist (pair_distances.py:167, pp_gen_nearest.py:942), which for
+// abstracts (<= 25 sentences) is the DIRECT sum (q - c)^2: identical sentences are at distance exactly 0, where
+// |q|^2 + |c|^2 - 2 q.c leaves cancellation noise (and the 1e-8 clamp of geomloss' formula leaves 1e-4).  The winning
+// sentence pair of a document pair is therefore re-evaluated directly when its squared distance is small against the
+// norms (near-duplicates: rare, and exactly where the ranking is decided).  One warp, rows from L1/L2.
+#ifdef __CUDACC__
+__device__ __forceinline__ float l2max_refine(const float* qrow, const float* crow, int D, int lane) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int k4 = lane; k4 < (D >> 2); k4 += 32) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(qrow) + k4), y = __ldg(reinterpret_cast<const float4*>(crow) + k4);
+        const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s0 = fmaf(d2, d2, s0); s1 = fmaf(d3, d3, s1);
+    }
+    return -sqrtf(warp_sum(s0 + s1));
+}
+__device__ __forceinline__ bool l2max_needs_refine(float best, float norm_sum) {
+    return best > kPadNeg && best * best < 0.01f * norm_sum;
+}
+#endif
+
 // Streaming 128-bit load that does not allocate in L1 (data read exactly once).
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;

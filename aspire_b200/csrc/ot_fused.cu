@@ -36,7 +36,13 @@ constexpr int kFT = 10;        // max sentences per document on the fused path
 constexpr int kHR = kFT / 2;   // query rows per half-warp
 constexpr int kCostLd = 101;   // floats per pair in a padded cost tile (default of phase1's LD)
 constexpr int kRedVals = 64;   // 50 dot products + 5 candidate norms, padded for the 16-lane transpose-reduce
-constexpr int kRing = 5;                   // candidate slices in the per-warp cp.async ring (kRing-1 in flight)
+#ifndef ASP_V7_RING
+#define ASP_V7_RING 5
+#endif
+#ifndef ASP_V7_SLOTS
+#define ASP_V7_SLOTS 4
+#endif
+constexpr int kRing = ASP_V7_RING;         // candidate slices in the per-warp cp.async ring (kRing-1 in flight)
 constexpr int kSliceFloats = kFT * 64;     // one slice: 64 floats of each of the kFT rows
 constexpr int kSliceBytes = kSliceFloats * 4;
 constexpr int kCounterSlots = 1024;
@@ -340,7 +346,7 @@ __device__ __forceinline__ void phase1(const FusedArgs& a, int base, int npairs,
 constexpr int kV7Gram = 8, kV7Warps = 12;
 constexpr int kV7Half = 16;                 // pairs per Gram tile
 constexpr int kV7Ld = kFT * kFT;            // cost floats per pair (16-byte aligned rows; LDS.128 conflict-free)
-constexpr int kV7Slots = 4;                 // half-tiles per scheduler
+constexpr int kV7Slots = ASP_V7_SLOTS;      // half-tiles per scheduler
 constexpr int kV7SlotFloats = kV7Half * kV7Ld;
 // dynamic shared memory, floats: [4 schedulers][kV7Slots] half-tiles | per Gram warp: reduced values, query norms, ring
 constexpr int kV7GramSmem = 2 * kRedVals + 16 + kRing * kSliceFloats;

@@ -584,6 +584,11 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
                     run_idx = oi;
                 }
             }
+            if (run_idx != 0x7fffffff) {  // near-duplicate winner: re-evaluate it directly (common.cuh: l2max_refine)
+                const int wi = run_idx / a.Sc, wj = run_idx - wi * a.Sc;
+                if (l2max_needs_refine(run_best, nrm[wi] + nrm[32 + wj]))
+                    run_best = l2max_refine(a.q + ((size_t)(b / a.q_group) * a.Sq + wi) * D, a.c + ((size_t)b * a.Sc + wj) * D, D, lane);
+            }
             if (lane == 0) {
                 a.best[b] = run_best;
                 if (a.flat_idx) a.flat_idx[b] = (run_idx == 0x7fffffff) ? 0 : run_idx;

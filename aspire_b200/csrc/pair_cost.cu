@@ -45,7 +45,7 @@ pair_cost_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_lens
         const float* qbase = q + (size_t)qb * Sq * D;
         const float* cbase = c + (size_t)b * Sc * D;
         float* out = cost ? cost + (size_t)b * Sq * Sc : nullptr;
-        float run_best = kPadNeg;
+        float run_best = kPadNeg, run_ns = 0.f;
         int run_idx = 0x7fffffff;
         if (MODE == MODE_L2MAX && (ql == 0 || cl == 0)) run_idx = 0;
         for (int ti = 0; ti < ql; ti += TI) {
@@ -67,6 +67,7 @@ pair_cost_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_lens
                             if (sim > run_best || (sim == run_best && idx < run_idx)) {
                                 run_best = sim;
                                 run_idx = idx;
+                                run_ns = red[T::kEntries + i] + red[T::kEntries + TI + j];
                             }
                         }
                     }
@@ -87,11 +88,15 @@ pair_cost_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_lens
             for (int s = 16; s > 0; s >>= 1) {
                 const float ob = __shfl_xor_sync(0xffffffffu, run_best, s);
                 const int oi = __shfl_xor_sync(0xffffffffu, run_idx, s);
+                const float on = __shfl_xor_sync(0xffffffffu, run_ns, s);
                 if (ob > run_best || (ob == run_best && oi < run_idx)) {
                     run_best = ob;
                     run_idx = oi;
+                    run_ns = on;
                 }
             }
+            if (l2max_needs_refine(run_best, run_ns) && run_idx != 0x7fffffff)  // warp-uniform after the butterfly
+                run_best = l2max_refine(qbase + (size_t)(run_idx / Sc) * D, cbase + (size_t)(run_idx % Sc) * D, D, lane);
             if (lane == 0) {
                 best[b] = run_best;
                 if (flat_idx) flat_idx[b] = (run_idx == 0x7fffffff) ? 0 : run_idx;
@@ -111,7 +116,7 @@ pair_cost_cta_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_
                      float* __restrict__ cost, float* __restrict__ best, int32_t* __restrict__ flat_idx) {
     using T = GramTile<TI, TJ>;
     __shared__ float red_all[WARPS][T::NV];
-    __shared__ float best_s[WARPS];
+    __shared__ float best_s[WARPS], ns_s[WARPS];
     __shared__ int idx_s[WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* red = red_all[warp];
@@ -121,7 +126,7 @@ pair_cost_cta_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_
         const float* qbase = q + (size_t)qb * Sq * D;
         const float* cbase = c + (size_t)b * Sc * D;
         float* out = cost ? cost + (size_t)b * Sq * Sc : nullptr;
-        float run_best = kPadNeg;
+        float run_best = kPadNeg, run_ns = 0.f;
         int run_idx = 0x7fffffff;
         const int nti = (ql + TI - 1) / TI, ntj = (cl + TJ - 1) / TJ;
         for (int t = warp; t < nti * ntj; t += WARPS) {
@@ -142,6 +147,7 @@ pair_cost_cta_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_
                         if (sim > run_best || (sim == run_best && idx < run_idx)) {
                             run_best = sim;
                             run_idx = idx;
+                            run_ns = red[T::kEntries + i] + red[T::kEntries + TI + j];
                         }
                     }
                 }
@@ -160,24 +166,35 @@ pair_cost_cta_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_
             for (int s = 16; s > 0; s >>= 1) {
                 const float ob = __shfl_xor_sync(0xffffffffu, run_best, s);
                 const int oi = __shfl_xor_sync(0xffffffffu, run_idx, s);
+                const float on = __shfl_xor_sync(0xffffffffu, run_ns, s);
                 if (ob > run_best || (ob == run_best && oi < run_idx)) {
                     run_best = ob;
                     run_idx = oi;
+                    run_ns = on;
                 }
             }
             if (lane == 0) {
                 best_s[warp] = run_best;
                 idx_s[warp] = run_idx;
+                ns_s[warp] = run_ns;
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (warp == 0) {  // every lane of warp 0 merges the WARPS candidates identically, then refines together
+                run_best = best_s[0];
+                run_idx = idx_s[0];
+                run_ns = ns_s[0];
                 for (int w = 1; w < WARPS; ++w)
                     if (best_s[w] > run_best || (best_s[w] == run_best && idx_s[w] < run_idx)) {
                         run_best = best_s[w];
                         run_idx = idx_s[w];
+                        run_ns = ns_s[w];
                     }
-                best[b] = run_best;
-                if (flat_idx) flat_idx[b] = (run_idx == 0x7fffffff) ? 0 : run_idx;
+                if (l2max_needs_refine(run_best, run_ns) && run_idx != 0x7fffffff)
+                    run_best = l2max_refine(qbase + (size_t)(run_idx / Sc) * D, cbase + (size_t)(run_idx % Sc) * D, D, lane);
+                if (lane == 0) {
+                    best[b] = run_best;
+                    if (flat_idx) flat_idx[b] = (run_idx == 0x7fffffff) ? 0 : run_idx;
+                }
             }
             __syncthreads();
         }

@@ -183,16 +183,15 @@ topk_merge_kernel(const float* __restrict__ in_scores, const long long* __restri
 // ---------------------------------------------------------------------------------------------------------------------
 // Single-pass top-k (k <= 128): the score matrix is read from HBM ONCE.
 //
-//   topk_chunk_kernel  -- one CTA per (query, chunk of 8192 scores).  Every thread keeps its 32 scores in registers as
-//     order-preserving 32-bit keys.  The k-th largest of the 256 per-thread maxima, tau, is a lower bound of the chunk's
-//     k-th largest score (k threads hold an element >= tau), so the chunk's top-k are among the elements >= tau:
-//     the ones strictly above it (at most 32 (k-1): only k-1 thread maxima exceed tau) are all collected, and of the
-//     ones equal to it the first (k - #greater) in index order (ties rank by smallest id).  For continuous scores that
-//     is ~250 survivors per chunk; they are sorted in shared memory (composite key: score key << 32 | ~global id) and the
-//     best k go to a scratch list.
-//   topk_merge_packed_kernel -- one CTA per query sorts its nlists x k composite keys and writes the best k, decoded
-//     (score, id) and / or still packed.  The same kernel merges the lists of R ranks after the all-gather of packed
-//     keys ([R][Q][k] as gathered, no concatenation on the host side).
+//   topk_stream_kernel -- a CTA walks 4 consecutive 8192-score chunks of one row through a 3-stage cp.async ring (64 KB in
+//     flight per CTA, two CTAs per SM); per chunk every thread turns its 32 scores into order-preserving 32-bit keys, a
+//     sort-free bound tau <= (chunk's k-th largest) comes from the thread maxima (warp shuffles only), and every score
+//     >= tau (~190 of 8192) is appended unsorted to the chunk's list as a composite key (score key << 32 | ~global id).
+//   topk_exact_kernel  -- redoes, exactly and sorted, the rare chunk with more than L scores at or above its bound
+//     (heavy ties): everything above the k-th largest thread maximum plus the first of its equals in index order.
+//   topk_merge_packed_kernel -- one CTA per query gathers its chunk lists, narrows them with the same bound and sorts a
+//     few hundred keys; writes the best k decoded (score, id) and / or still packed.  The same kernel merges the lists
+//     of R ranks after the all-gather of packed keys ([R][Q][k] as gathered, no concatenation on the host side).
 // The 5-pass radix select above stays for k > 128.
 constexpr int kTkThreads = 256, kTkPer = 32, kTkChunk = kTkThreads * kTkPer;
 constexpr int kTkMaxK = 128;
@@ -241,24 +240,44 @@ __device__ __forceinline__ unsigned int block_scan_excl(unsigned int v, unsigned
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kTkThreads)
-topk_chunk_kernel(const float* __restrict__ scores, long long N, int k, int negate, long long base_id, int nchunks,
-                  unsigned long long* __restrict__ lists, int cap) {
-    extern __shared__ unsigned long long surv[];  // cap composite keys
-    __shared__ uint32_t tmax[kTkThreads];
-    __shared__ unsigned int warp_tot[kTkThreads / 32];
-    const int tid = threadIdx.x;
-    const long long row = blockIdx.y, start = (long long)blockIdx.x * kTkChunk;
-    const int n = (int)min((long long)kTkChunk, N - start);
-    const float* src = scores + row * N + start;
-    // element e = 4 * (tid + 256 j) + c  (j < 8, c < 4): coalesced 16-byte loads when the chunk start is 16-byte aligned
-    uint32_t key[kTkPer];
-    const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+// descending bitonic sort of one value per lane inside a warp (registers + shuffles)
+__device__ __forceinline__ uint32_t warp_sort_desc(uint32_t v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, v, stride);
+            const bool lower = (lane & stride) == 0;           // this lane keeps the larger of the pair in a descending run
+            const bool desc = (lane & size) == 0 || size == 32;
+            v = (lower == desc) ? max(v, o) : min(v, o);
+        }
+    }
+    return v;
+}
+
+// The chunk step.  FAST PATH: a lower bound tau of the chunk's k-th largest score is taken from the thread maxima without
+// any block-wide sort -- every warp sorts its 32 thread maxima with shuffles, tau = the minimum over the 8 warps of each
+// warp's ceil(k/8)-th largest, so at least k thread maxima (hence k scores) are >= tau -- and EVERY score >= tau is
+// appended, unsorted, to the chunk's list (typically 150-250 of 8192; ties included, so the list is a superset of the
+// chunk's top-k under the (score desc, id asc) order).  The merge kernel does the only sort.  A chunk with more than L
+// such scores (heavy ties) is flagged (count = kTkOverflow) and redone by topk_exact_kernel: k-th largest thread maximum
+// by a block-wide sort, everything above it, the first of its equals in index order, sorted, k entries.
+constexpr unsigned int kTkOverflow = 0xffffffffu;
+
+// keys of the thread's 32 elements e = 4 * (tid + 256 j) + c.  STAGED: from the shared-memory stage the thread filled
+// itself with cp.async; else straight from global memory (FULL: 8192 scores, 16-byte aligned, no bounds checks).
+template <bool FULL, bool STAGED>
+__device__ __forceinline__ void topk_load_keys(const float* __restrict__ src, const float4* staged, int n, int negate, int tid,
+                                               uint32_t (&key)[kTkPer]) {
+    const bool vec = FULL || ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int e0 = 4 * (tid + kTkThreads * j);
         float v[4];
-        if (vec && e0 + 3 < n) {
+        if (STAGED) {
+            const float4 f = staged[tid + kTkThreads * j];
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else if (FULL || (vec && e0 + 3 < n)) {
             const float4 f = ldg_stream(reinterpret_cast<const float4*>(src + e0));
             v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
         } else {
@@ -266,93 +285,294 @@ topk_chunk_kernel(const float* __restrict__ scores, long long N, int k, int nega
             for (int c = 0; c < 4; ++c) v[c] = (e0 + c < n) ? __ldg(src + e0 + c) : 0.f;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) key[4 * j + c] = (e0 + c < n) ? score_key(negate ? -v[c] : v[c]) : 0u;
+        for (int c = 0; c < 4; ++c) key[4 * j + c] = (FULL || e0 + c < n) ? score_key(negate ? -v[c] : v[c]) : 0u;
     }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void topk_chunk_fast(const uint32_t (&key)[kTkPer], int n, int k, unsigned int id0,
+                                                unsigned long long* __restrict__ out, unsigned int* __restrict__ count_out, int L) {
+    __shared__ uint32_t wsel[kTkThreads / 32];
+    __shared__ unsigned int n_ge, n_out;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t m = 0u;
 #pragma unroll
     for (int i = 0; i < kTkPer; ++i) m = max(m, key[i]);
-    tmax[tid] = m;
-    bitonic_desc_u32(tmax, kTkThreads);
+    __syncthreads();  // the previous chunk of this CTA is done with wsel / n_ge / n_out
+    if (tid == 0) { n_ge = 0u; n_out = 0u; }
     const int keff = min(k, n);
-    const uint32_t tau = (keff >= 1 && keff <= kTkThreads) ? tmax[keff - 1] : 0u;
-    // ---- survivors strictly above tau: all of them ----
-    unsigned int cg = 0, ce = 0;
-#pragma unroll
-    for (int i = 0; i < kTkPer; ++i) {
-        const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
-        cg += (e < n && key[i] > tau);
-        ce += (e < n && key[i] == tau);
-    }
-    unsigned int G, E;
-    unsigned int og = block_scan_excl(cg, warp_tot, G);
-    for (int i = tid; i < cap; i += kTkThreads) surv[i] = 0ull;
+    const int jsel = (keff + 7) / 8;                       // every warp contributes its jsel-th largest thread maximum
+    const uint32_t sorted = warp_sort_desc(m, lane);
+    if (lane == min(jsel, 32) - 1) wsel[warp] = sorted;
     __syncthreads();
+    uint32_t tau = wsel[0];
+#pragma unroll
+    for (int w = 1; w < kTkThreads / 32; ++w) tau = min(tau, wsel[w]);
+    unsigned int cge = 0;
 #pragma unroll
     for (int i = 0; i < kTkPer; ++i) {
         const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
-        if (e < n && key[i] > tau)
-            surv[og++] = ((unsigned long long)key[i] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(base_id + start + e));
+        cge += ((FULL || e < n) && key[i] >= tau);
     }
-    // ---- of the elements equal to tau: the first (keff - G) in index order.  Index order = j slab by slab (1024
-    //      consecutive elements each), inside a slab thread by thread, inside a thread component by component ----
-    int need = (int)keff - (int)min(G, (unsigned)keff);
-    unsigned int pos = G;
-    (void)block_scan_excl(ce, warp_tot, E);
-    if (need > 0 && E > 0) {
+    unsigned int wsum = cge;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (need <= 0) break;  // block-uniform
-            unsigned int c_slab = 0;
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if (lane == 0 && wsum) atomicAdd(&n_ge, wsum);
+    __syncthreads();
+    const unsigned int total = n_ge;
+    if (total <= (unsigned)L) {
+        unsigned int pos = cge ? atomicAdd(&n_out, cge) : 0u;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int e = 4 * (tid + kTkThreads * j) + c;
-                c_slab += (e < n && key[4 * j + c] == tau);
-            }
-            unsigned int tot;
-            unsigned int off = block_scan_excl(c_slab, warp_tot, tot);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int e = 4 * (tid + kTkThreads * j) + c;
-                if (e < n && key[4 * j + c] == tau) {
-                    if ((int)off < need)
-                        surv[pos + off] = ((unsigned long long)tau << 32) |
-                                          (unsigned long long)(0xffffffffu - (uint32_t)(base_id + start + e));
-                    ++off;
-                }
-            }
-            const int took = min((int)tot, need);
-            pos += took;
-            need -= took;
+        for (int i = 0; i < kTkPer; ++i) {
+            const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
+            if ((FULL || e < n) && key[i] >= tau)
+                out[pos++] = ((unsigned long long)key[i] << 32) | (unsigned long long)(0xffffffffu - (id0 + (unsigned)e));
         }
     }
-    __syncthreads();
-    // ---- sort the survivors, best k to the scratch list of this chunk ----
-    int npad = 2;
-    while (npad < (int)pos) npad <<= 1;
-    bitonic_desc_u64(surv, min(npad, cap));
-    unsigned long long* out = lists + ((size_t)row * nchunks + blockIdx.x) * k;
-    for (int i = tid; i < k; i += kTkThreads) out[i] = (i < (int)pos) ? surv[i] : 0ull;
+    if (tid == 0) *count_out = (total <= (unsigned)L) ? total : kTkOverflow;
 }
 
-// lists: nlists lists of k composite keys per query; list l of query q starts at lists[l * l_stride + q * q_stride].
-// CTA (q, grp) merges lists [grp * group, min(nlists, (grp + 1) * group)) into the grp-th output list of query q
-// (gridDim.y output lists per query; the decoded outputs are only meaningful when gridDim.y == 1).
-__global__ void __launch_bounds__(1024)
-topk_merge_packed_kernel(const unsigned long long* __restrict__ lists, int nlists, size_t l_stride, size_t q_stride, int k,
-                         int group, float* __restrict__ out_scores, long long* __restrict__ out_ids,
-                         unsigned long long* __restrict__ out_packed, int npad) {
-    extern __shared__ unsigned long long mk[];
-    const int q = blockIdx.x, l0 = blockIdx.y * group;
-    const int n_in = min(group, nlists - l0) * k;
-    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-        unsigned long long v = 0ull;
-        if (i < n_in) v = lists[(size_t)(l0 + i / k) * l_stride + (size_t)q * q_stride + (i % k)];
-        mk[i] = v;
+// Streaming kernel: CTA (x, row) walks `span` consecutive chunks of one row.  Whole, 16-byte-aligned chunks come in through
+// a 3-stage cp.async ring in shared memory (each thread copies exactly the 128 bytes it will read back, so the ring needs
+// no block-wide synchronisation; two chunks = 64 KB are in flight per CTA while a third is being selected from, two CTAs
+// per SM); a ragged or unaligned chunk is read directly.
+constexpr int kTkStages = 3;
+#ifndef ASP_TK_SPAN
+#define ASP_TK_SPAN 4
+#endif
+constexpr int kTkSpan = ASP_TK_SPAN;
+__device__ __forceinline__ void tk_cp_async16(uint32_t dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(kTkThreads, 2)
+topk_stream_kernel(const float* __restrict__ scores, long long N, int k, int negate, long long base_id, int nchunks,
+                   unsigned long long* __restrict__ lists, unsigned int* __restrict__ counts, int L) {
+    extern __shared__ __align__(16) float ring[];  // [kTkStages][8192]
+    const int tid = threadIdx.x;
+    const long long row = blockIdx.y;
+    const int c0 = blockIdx.x * kTkSpan, c1 = min(c0 + kTkSpan, nchunks);
+    const float* rowp = scores + row * N;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+    auto staged_ok = [&](int c) {
+        return (N - (long long)c * kTkChunk >= kTkChunk) && ((reinterpret_cast<uintptr_t>(rowp + (long long)c * kTkChunk) & 15u) == 0);
+    };
+    auto issue = [&](int c) {  // this thread's 8 x 16 bytes of chunk c into stage c % kTkStages (empty group when not staged)
+        if (c < c1 && staged_ok(c)) {
+            const float* src = rowp + (long long)c * kTkChunk;
+            const uint32_t dst = ring_u32 + (uint32_t)((c % kTkStages) * kTkChunk * 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tk_cp_async16(dst + 16u * (tid + kTkThreads * j), src + 4 * (tid + kTkThreads * j));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(c0);
+    issue(c0 + 1);
+    for (int c = c0; c < c1; ++c) {
+        issue(c + 2);                                              // its stage was read by this thread one iteration ago
+        asm volatile("cp.async.wait_group 2;" ::: "memory");      // chunk c has landed (groups complete in order)
+        const long long start = (long long)c * kTkChunk;
+        unsigned long long* out = lists + ((size_t)row * nchunks + c) * L;
+        unsigned int* cnt = counts + (size_t)row * nchunks + c;
+        uint32_t key[kTkPer];
+        if (staged_ok(c)) {
+            topk_load_keys<true, true>(nullptr, reinterpret_cast<const float4*>(ring + (size_t)(c % kTkStages) * kTkChunk), kTkChunk,
+                                       negate, tid, key);
+            topk_chunk_fast<true>(key, kTkChunk, k, (unsigned)(base_id + start), out, cnt, L);
+        } else {
+            const int n = (int)min((long long)kTkChunk, N - start);
+            topk_load_keys<false, false>(rowp + start, nullptr, n, negate, tid, key);
+            topk_chunk_fast<false>(key, n, k, (unsigned)(base_id + start), out, cnt, L);
+        }
     }
-    bitonic_desc_u64(mk, npad);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Exact redo of the chunks the streaming kernel flagged (more than L scores at or above its bound: heavy ties).  A small
+// persistent grid scans the counts; a flagged chunk gets the k-th largest thread maximum by a block-wide sort, everything
+// above it, the first of its equals in index order, sorted: k entries.
+__global__ void __launch_bounds__(kTkThreads)
+topk_exact_kernel(const float* __restrict__ scores, long long N, int k, int negate, long long base_id, int nchunks, int Q,
+                  unsigned long long* __restrict__ lists, unsigned int* __restrict__ counts, int L, int cap) {
+    extern __shared__ unsigned long long surv[];  // cap composite keys
+    __shared__ uint32_t tmax[kTkThreads];
+    __shared__ unsigned int warp_tot[kTkThreads / 32];
+    const int tid = threadIdx.x;
+    const long long nl = (long long)Q * nchunks;
+    // stripe of this CTA: lists [lo, hi); 256 flags are tested per step, flagged lists are then redone one by one
+    const long long per = (nl + gridDim.x - 1) / gridDim.x, lo = per * blockIdx.x, hi = min(nl, lo + per);
+    for (long long base = lo; base < hi; base += kTkThreads) {
+        const bool mine = base + tid < hi && counts[base + tid] == kTkOverflow;
+        if (!__syncthreads_or(mine)) continue;
+        for (long long list = base; list < min(hi, base + kTkThreads); ++list) {
+        if (counts[list] != kTkOverflow) continue;  // block-uniform
+        const long long row = list / nchunks, start = (list - row * nchunks) * kTkChunk;
+        const int n = (int)min((long long)kTkChunk, N - start);
+        uint32_t key[kTkPer];
+        topk_load_keys<false, false>(scores + row * N + start, nullptr, n, negate, tid, key);
+        uint32_t m = 0u;
+#pragma unroll
+        for (int i = 0; i < kTkPer; ++i) m = max(m, key[i]);
+        __syncthreads();
+        tmax[tid] = m;
+        bitonic_desc_u32(tmax, kTkThreads);
+        const int keff = min(k, n);
+        const uint32_t tau = (keff >= 1 && keff <= kTkThreads) ? tmax[keff - 1] : 0u;
+        unsigned int cg = 0, ce = 0;
+#pragma unroll
+        for (int i = 0; i < kTkPer; ++i) {
+            const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
+            cg += (e < n && key[i] > tau);
+            ce += (e < n && key[i] == tau);
+        }
+        unsigned int G, E;
+        unsigned int og = block_scan_excl(cg, warp_tot, G);
+        for (int i = tid; i < cap; i += kTkThreads) surv[i] = 0ull;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kTkPer; ++i) {
+            const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
+            if (e < n && key[i] > tau)
+                surv[og++] = ((unsigned long long)key[i] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(base_id + start + e));
+        }
+        // of the elements equal to tau: the first (keff - G) in index order.  Index order = j slab by slab (1024
+        // consecutive elements each), inside a slab thread by thread, inside a thread component by component
+        int need = (int)keff - (int)min(G, (unsigned)keff);
+        unsigned int pos = G;
+        (void)block_scan_excl(ce, warp_tot, E);
+        if (need > 0 && E > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (need <= 0) break;  // block-uniform
+                unsigned int c_slab = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int e = 4 * (tid + kTkThreads * j) + c;
+                    c_slab += (e < n && key[4 * j + c] == tau);
+                }
+                unsigned int tot;
+                unsigned int off = block_scan_excl(c_slab, warp_tot, tot);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int e = 4 * (tid + kTkThreads * j) + c;
+                    if (e < n && key[4 * j + c] == tau) {
+                        if ((int)off < need)
+                            surv[pos + off] = ((unsigned long long)tau << 32) |
+                                              (unsigned long long)(0xffffffffu - (uint32_t)(base_id + start + e));
+                        ++off;
+                    }
+                }
+                const int took = min((int)tot, need);
+                pos += took;
+                need -= took;
+            }
+        }
+        __syncthreads();
+        int npad = 2;
+        while (npad < (int)pos) npad <<= 1;
+        bitonic_desc_u64(surv, min(npad, cap));
+        const int nout = min((int)pos, k);
+        unsigned long long* out = lists + (size_t)list * L;
+        for (int i = tid; i < nout; i += kTkThreads) out[i] = surv[i];
+        if (tid == 0) counts[list] = (unsigned)nout;
+        __syncthreads();
+        }
+    }
+}
+
+// descending bitonic sort of one 64-bit value per lane inside a warp
+__device__ __forceinline__ unsigned long long warp_sort_desc64(unsigned long long v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, stride);
+            const bool lower = (lane & stride) == 0, desc = (lane & size) == 0;
+            v = (lower == desc) ? max(v, o) : min(v, o);
+        }
+    }
+    return v;
+}
+
+constexpr int kTkSel = 1024;  // survivors the merge sorts after its selection step
+
+// Merge: CTA (q, grp) gathers lists [grp * group, min(nlists, (grp + 1) * group)) of query q -- list l starts at
+// lists[l * l_stride + q * q_stride] and holds counts[q * nlists + l] entries (counts == NULL: exactly k, zeros = fillers)
+// -- and writes the best k as the grp-th output list of query q (gridDim.y lists per query; the decoded outputs are
+// meaningful when gridDim.y == 1).  Composite keys are distinct, so the best k are simply the k largest: the same bound
+// as in the chunk kernel (minimum over the warps of each warp's ceil(k / warps)-th largest thread maximum) leaves a few
+// hundred of the ~3 000 gathered keys, and only those are sorted (a 45-stage sort of 512 instead of a 78-stage sort of
+// 4 096); more than kTkSel survivors, or a k the bound does not cover, sort everything.
+__global__ void __launch_bounds__(1024)
+topk_merge_packed_kernel(const unsigned long long* __restrict__ lists, const unsigned int* __restrict__ counts, int nlists,
+                         size_t l_stride, size_t q_stride, int k, int group, float* __restrict__ out_scores,
+                         long long* __restrict__ out_ids, unsigned long long* __restrict__ out_packed, int cap) {
+    extern __shared__ unsigned long long mk[];
+    __shared__ unsigned long long sel[kTkSel];
+    __shared__ unsigned long long wsel[32];
+    __shared__ int off_s[129];
+    __shared__ unsigned int n_ge, n_out;
+    const int q = blockIdx.x, l0 = blockIdx.y * group, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int nl = min(group, nlists - l0);
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int l = 0; l < nl; ++l) {
+            off_s[l] = run;
+            run += counts ? (int)counts[(size_t)q * nlists + l0 + l] : k;
+        }
+        off_s[nl] = min(run, cap);
+        n_ge = 0u;
+        n_out = 0u;
+    }
+    __syncthreads();
+    const int total = off_s[nl];
+    for (int l = 0; l < nl; ++l) {
+        const int o = off_s[l], c = min(off_s[l + 1], total) - o;
+        const unsigned long long* srcl = lists + (size_t)(l0 + l) * l_stride + (size_t)q * q_stride;
+        for (int i = threadIdx.x; i < c; i += blockDim.x) mk[o + i] = srcl[i];
+    }
+    __syncthreads();
+    unsigned long long* sorted = mk;
+    int npad = 2;
+    const int jsel = (k + nwarps - 1) / nwarps;
+    bool selected = false;
+    if (total > kTkSel && jsel <= 32) {
+        unsigned long long m = 0ull;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) m = max(m, mk[i]);
+        const unsigned long long srt = warp_sort_desc64(m, lane);
+        if (lane == jsel - 1) wsel[warp] = srt;
+        __syncthreads();
+        unsigned long long tau = wsel[0];
+        for (int w = 1; w < nwarps; ++w) tau = min(tau, wsel[w]);
+        unsigned int c = 0;
+        if (tau != 0ull)
+            for (int i = threadIdx.x; i < total; i += blockDim.x) c += (mk[i] >= tau);
+        unsigned int wsum = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        if (lane == 0 && wsum) atomicAdd(&n_ge, wsum);
+        __syncthreads();
+        if (tau != 0ull && n_ge <= (unsigned)kTkSel) {  // block-uniform
+            unsigned int pos = c ? atomicAdd(&n_out, c) : 0u;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const unsigned long long x = mk[i];
+                if (x >= tau) sel[pos++] = x;
+            }
+            while (npad < (int)n_ge) npad <<= 1;
+            for (int i = (int)n_ge + threadIdx.x; i < npad; i += blockDim.x) sel[i] = 0ull;
+            sorted = sel;
+            selected = true;
+        }
+    }
+    if (!selected) {
+        while (npad < total) npad <<= 1;
+        for (int i = total + threadIdx.x; i < npad; i += blockDim.x) mk[i] = 0ull;
+    }
+    bitonic_desc_u64(sorted, npad);
     const size_t o = ((size_t)q * gridDim.y + blockIdx.y) * k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        const unsigned long long x = (i < npad) ? mk[i] : 0ull;
+        const unsigned long long x = (i < npad) ? sorted[i] : 0ull;
         if (out_packed) out_packed[o + i] = x;
         if (out_scores) out_scores[o + i] = x ? key_score((uint32_t)(x >> 32)) : -INFINITY;
         if (out_ids) out_ids[o + i] = x ? (long long)(0xffffffffu - (uint32_t)(x & 0xffffffffull)) : -1;
@@ -408,18 +628,39 @@ extern "C" int asp_topk_merge(const float* in_scores, const long long* in_ids, i
 namespace asp {
 constexpr int kTkMergeCap = 8192;  // composite keys one merge CTA sorts in shared memory (64 KB)
 static long long tk_chunks(long long N) { return (N + kTkChunk - 1) / kTkChunk; }
-static int tk_group(int k) { return kTkMergeCap / k; }  // lists one merge CTA takes (k <= 128 -> >= 64)
+static int tk_list_len(int k) {  // entries of a chunk list: room for every score at or above the chunk's bound
+    int L = 64;
+    while (L < 4 * k) L <<= 1;
+    return L;  // <= 512 for k <= 128
+}
+struct TkPlan {
+    long long nchunks;
+    int L, group0;                 // chunk lists: length, lists per merge CTA of the first level
+    size_t lists0, counts0, rest;  // bytes: chunk lists, their counts, lists of the later merge levels
+};
+static TkPlan tk_plan(int Q, long long N, int k) {
+    TkPlan p;
+    p.nchunks = tk_chunks(N);
+    p.L = tk_list_len(k);
+    p.group0 = std::min(kTkMergeCap / p.L, 128);
+    const size_t q = (size_t)(Q > 0 ? Q : 1);
+    p.lists0 = q * p.nchunks * p.L * sizeof(unsigned long long);
+    p.counts0 = (q * p.nchunks * sizeof(unsigned int) + 255) & ~(size_t)255;
+    long long lists = (p.nchunks + p.group0 - 1) / p.group0, total = 0;
+    const int group = std::min(kTkMergeCap / k, 128);
+    while (lists > 1) {  // level outputs of k entries each, merged `group` at a time
+        total += lists;
+        lists = (lists + group - 1) / group;
+    }
+    p.rest = q * (size_t)total * k * sizeof(unsigned long long);
+    return p;
+}
 }  // namespace asp
 
 extern "C" size_t asp_topk_workspace_bytes(int Q, long long N, int k) {
     if (k < 1 || k > asp::kTkMaxK || N < 1 || Q < 0) return 0;
-    // chunk lists + the lists of the intermediate merge levels (each level shrinks the list count by >= 64x)
-    long long lists = asp::tk_chunks(N), total = lists;
-    while (lists > asp::tk_group(k)) {
-        lists = (lists + asp::tk_group(k) - 1) / asp::tk_group(k);
-        total += lists;
-    }
-    return (size_t)(Q > 0 ? Q : 1) * (size_t)total * k * sizeof(unsigned long long);
+    const asp::TkPlan p = asp::tk_plan(Q, N, k);
+    return p.lists0 + p.counts0 + p.rest;
 }
 
 extern "C" int asp_topk_ws(const float* scores, int Q, long long N, int k, long long base_id, int negate, float* out_scores,
@@ -438,7 +679,8 @@ extern "C" int asp_topk_ws(const float* scores, int Q, long long N, int k, long 
                     kTkMaxK);
         return asp_topk(scores, Q, N, k, base_id, out_scores, out_ids, stream_);
     }
-    int nlists = (int)tk_chunks(N);
+    const TkPlan p = tk_plan(Q, N, k);
+    int nlists = (int)p.nchunks;
     int cap = 2;
     while (cap < 32 * (k - 1) + k) cap <<= 1;
     const size_t smem = (size_t)cap * sizeof(unsigned long long);
@@ -446,27 +688,42 @@ extern "C" int asp_topk_ws(const float* scores, int Q, long long N, int k, long 
     int dev = 0;
     ASP_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        ASP_CUDA(cudaFuncSetAttribute(topk_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        ASP_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTkStages * kTkChunk * 4));
+        ASP_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ASP_CUDA(cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         ASP_CUDA(cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        ASP_CUDA(cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_dev = dev;
     }
-    unsigned long long* lists = static_cast<unsigned long long*>(workspace);
-    topk_chunk_kernel<<<dim3(nlists, Q), kTkThreads, smem, stream>>>(scores, N, k, negate, base_id, nlists, lists, cap);
-    ASP_LAUNCH_CHECK("topk_chunk_kernel");
-    const int group = tk_group(k);
-    for (;;) {  // lists of query q: lists[(q * nlists + l) * k]
+    char* w = static_cast<char*>(workspace);
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(w);
+    unsigned int* counts = reinterpret_cast<unsigned int*>(w + p.lists0);
+    unsigned long long* next = reinterpret_cast<unsigned long long*>(w + p.lists0 + p.counts0);
+    topk_stream_kernel<<<dim3((nlists + kTkSpan - 1) / kTkSpan, Q), kTkThreads, kTkStages * kTkChunk * 4, stream>>>(
+        scores, N, k, negate, base_id, nlists, lists, counts, p.L);
+    ASP_LAUNCH_CHECK("topk_stream_kernel");
+    const long long nl_all = (long long)Q * nlists;
+    topk_exact_kernel<<<(unsigned)std::min<long long>(nl_all, 2LL * sm_count()), kTkThreads, smem, stream>>>(
+        scores, N, k, negate, base_id, nlists, Q, lists, counts, p.L, cap);
+    ASP_LAUNCH_CHECK("topk_exact_kernel");
+    // level 0: variable-length chunk lists; later levels: lists of exactly k sorted entries
+    int group = p.group0, stride = p.L;
+    const unsigned int* cnt = counts;
+    for (;;) {  // list l of query q: lists[(q * nlists + l) * stride]
         const bool last = nlists <= group;
         const int ngroups = (nlists + group - 1) / group;
-        const int n_in = (last ? nlists : group) * k;
-        const int npad = next_pow2(n_in < 2 ? 2 : n_in);
-        unsigned long long* next = lists + (size_t)Q * nlists * k;
-        topk_merge_packed_kernel<<<dim3(Q, ngroups), 1024, (size_t)npad * 8, stream>>>(
-            lists, nlists, (size_t)k, (size_t)nlists * k, k, group, last ? out_scores : nullptr, last ? out_ids : nullptr,
-            last ? out_packed : next, npad);
+        const size_t cap_keys = std::min<size_t>((size_t)next_pow2(std::min(nlists, group) * stride), kTkMergeCap);
+        topk_merge_packed_kernel<<<dim3(Q, ngroups), 1024, cap_keys * 8, stream>>>(
+            lists, cnt, nlists, (size_t)stride, (size_t)nlists * stride, k, group, last ? out_scores : nullptr,
+            last ? out_ids : nullptr, last ? out_packed : next, (int)cap_keys);
         ASP_LAUNCH_CHECK("topk_merge_packed_kernel");
         if (last) break;
         lists = next;
+        next += (size_t)Q * ngroups * k;
         nlists = ngroups;
+        stride = k;
+        cnt = nullptr;
+        group = std::min(kTkMergeCap / k, 128);
     }
     return ASP_OK;
 }
@@ -476,17 +733,17 @@ extern "C" int asp_topk_merge_packed(const unsigned long long* gathered, int R, 
     using namespace asp;
     ASP_REQUIRE(gathered && (out_scores || out_ids), "asp_topk_merge_packed: NULL pointer");
     ASP_REQUIRE(R >= 1 && Q >= 0 && k >= 1, "asp_topk_merge_packed: bad shape R=%d Q=%d k=%d", R, Q, k);
-    if ((long long)R * k > kTkMergeCap) {
-        set_error("asp_topk_merge_packed: R*k=%lld exceeds %d", (long long)R * k, kTkMergeCap);
+    if ((long long)R * k > kTkMergeCap || R > 128) {
+        set_error("asp_topk_merge_packed: R=%d lists of k=%d exceed one merge (R <= 128, R*k <= %d)", R, k, kTkMergeCap);
         return ASP_ERR_UNSUPPORTED;
     }
     if (Q == 0) return ASP_OK;
-    const int npad = next_pow2(R * k < 2 ? 2 : R * k);
-    if ((size_t)npad * 8 > 48 * 1024)
+    const size_t cap_keys = (size_t)next_pow2(R * k < 2 ? 2 : R * k);
+    if (cap_keys * 8 > 48 * 1024)
         ASP_CUDA(cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     // gathered[r][q][k]: list r of query q
-    topk_merge_packed_kernel<<<Q, 1024, (size_t)npad * 8, (cudaStream_t)stream>>>(gathered, R, (size_t)Q * k, (size_t)k, k, R,
-                                                                                 out_scores, out_ids, nullptr, npad);
+    topk_merge_packed_kernel<<<Q, 1024, cap_keys * 8, (cudaStream_t)stream>>>(gathered, nullptr, R, (size_t)Q * k, (size_t)k, k, R,
+                                                                             out_scores, out_ids, nullptr, (int)cap_keys);
     ASP_LAUNCH_CHECK("topk_merge_packed_kernel");
     return ASP_OK;
 }

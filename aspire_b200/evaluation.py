@@ -64,6 +64,28 @@ class EvalDataset:
     def get_gold_test_data(self, facet=None):
         return {q: dict(zip(v['cands'], v['relevance_adju'])) for q, v in self.get_test_pool(facet).items()}
 
+    def get_test_dev_split(self):
+        """{qpid: 'dev'|'test'} from ``{name}-evaluation_splits.json`` (datasets.py:106-116); None for csfcube (all test)
+        and when the file is absent."""
+        if self.name == 'csfcube':
+            return None
+        fname = os.path.join(self.root_path, f'{self.name}-evaluation_splits.json')
+        if not os.path.exists(fname):
+            return None
+        with codecs.open(fname, 'r', 'utf-8') as fp:
+            return json.load(fp)
+
+    def get_query_metadata(self):
+        """{pid: {'title': ...}} of the test-pool queries: ``{name}-queries-release.csv`` (datasets.py:96-104) when it
+        exists, else the titles of the abstracts file."""
+        fname = os.path.join(self.root_path, f'{self.name}-queries-release.csv')
+        if os.path.exists(fname):
+            import pandas as pd
+            md = pd.read_csv(fname, index_col='pid')
+            md.index = md.index.astype(str)
+            return {pid: {'title': row['title']} for pid, row in md.iterrows()}
+        return {pid: {'title': p['TITLE']} for pid, p in self.dataset.items()}
+
     def get_threshold_grade(self):
         return 1 if self.name in {'treccovid', 'scidcite', 'scidcocite', 'scidcoread', 'scidcoview'} else 2
 
@@ -189,33 +211,56 @@ def sorted_relevancies(results, dataset, facet=None):
     return {q: [gold[q][cand] for cand, _ in ranked] for q, ranked in results.items()}
 
 
+FACETS = ('background', 'method', 'result')  # evaluate.py:19
+
+
 def evaluate(results, dataset, facet=None, results_dir=None, pr_atks=(5, 10, 20), split_of=None):
     """Per-query and aggregated ranking metrics of a scored test pool (evaluate.py:85-157).
 
-    Returns (per_query: list of dicts, aggregated: list of dicts, one per (facet, split)).  When ``results_dir`` is
-    given, writes ``query-evaluations[-facet].csv`` and ``aggregated-evaluations[-facet].csv`` there with the
-    reference's columns (utils/utils.py:62-65); aggregated values are rounded to 4 places as in the reference.
-    ``split_of``: optional {qpid: 'dev'|'test'} (``{ds}-evaluation_splits.json`` in evaluate.py's reading); default 'test'.
+    ``results``: what ``score`` returns / writes for ``facet``; for ``facet='all'`` a dict {facet_i: results_i} over
+    FACETS (the reference loads the three facet score files, :103-106).  Returns (per_query: list of dicts, aggregated:
+    list of dicts, one per (facet, split) -- plus, for 'all', one per split over every facet's queries, :147-154).
+    When ``results_dir`` is given, writes ``query-evaluations[-facet].csv`` and ``aggregated-evaluations[-facet].csv``
+    there with the reference's columns (utils/utils.py:62-65); aggregated values are rounded to 4 places.
+    ``split_of``: {qpid: 'dev'|'test'}; default ``dataset.get_test_dev_split()`` (``{ds}-evaluation_splits.json``, none
+    for csfcube => every query is 'test').
     """
     from . import metrics as M
-    facet_key = 'unfaceted' if facet is None else facet
+    by_facet = results if facet == 'all' else {('unfaceted' if facet is None else facet): results}
+    if split_of is None and hasattr(dataset, 'get_test_dev_split'):
+        split_of = dataset.get_test_dev_split()
+    titles = dataset.get_query_metadata() if hasattr(dataset, 'get_query_metadata') else None
     thr = dataset.get_threshold_grade()
     per_query = []
-    for qpid, rels in sorted_relevancies(results, dataset, facet).items():
-        m = M.compute_metrics(rels, pr_atks=list(pr_atks), threshold_grade=thr)
-        m['facet'] = facet_key
-        m['split'] = 'test' if split_of is None else split_of[qpid]
-        m['paper_id'] = qpid
-        m['title'] = dataset.get(qpid)['TITLE']
-        per_query.append(m)
+    for facet_key, facet_results in by_facet.items():
+        for qpid, rels in sorted_relevancies(facet_results, dataset, None if facet_key == 'unfaceted' else facet_key).items():
+            m = M.compute_metrics(rels, pr_atks=list(pr_atks), threshold_grade=thr)
+            m['facet'] = facet_key
+            m['split'] = 'test' if split_of is None else split_of[qpid]
+            m['paper_id'] = qpid
+            m['title'] = titles[qpid]['title'] if titles is not None and qpid in titles else dataset.get(qpid)['TITLE']
+            per_query.append(m)
     metric_cols = [k for k in per_query[0] if k not in ('facet', 'split', 'paper_id', 'title')] if per_query else []
+
+    def first_seen(values):
+        return list(dict.fromkeys(values))  # pandas .unique() order, as the reference iterates (:135-137)
     aggregated = []
-    for split in sorted({m['split'] for m in per_query}):
-        rows = [m for m in per_query if m['split'] == split]
-        agg = {k: round(float(np.mean([r[k] for r in rows])), 4) for k in metric_cols}
-        agg['facet'] = facet_key
-        agg['split'] = split
-        aggregated.append(agg)
+    for facet_key in first_seen(m['facet'] for m in per_query):
+        for split in first_seen(m['split'] for m in per_query):
+            rows = [m for m in per_query if m['split'] == split and m['facet'] == facet_key]
+            if not rows:
+                continue
+            agg = {k: round(float(np.mean([r[k] for r in rows])), 4) for k in metric_cols}
+            agg['facet'] = facet_key
+            agg['split'] = split
+            aggregated.append(agg)
+    if facet == 'all':
+        for split in first_seen(m['split'] for m in per_query):
+            rows = [m for m in per_query if m['split'] == split]
+            agg = {k: round(float(np.mean([r[k] for r in rows])), 4) for k in metric_cols}
+            agg['facet'] = facet
+            agg['split'] = split
+            aggregated.append(agg)
     if results_dir is not None:
         import pandas as pd
         os.makedirs(results_dir, exist_ok=True)

@@ -89,3 +89,33 @@ def test_evaluate_writes_reference_csvs(tmp_path):
     a = pd.read_csv(os.path.join(out_dir, "aggregated-evaluations.csv"))
     assert {"av_precision", "ndcg%20", "precision@5", "recall@20", "r_precision", "facet", "split", "paper_id", "title"} <= set(q.columns)
     assert len(q) == 2 and len(a) == 1 and abs(a["ndcg%20"][0] - agg[0]["ndcg%20"]) < 1e-12
+
+
+def test_evaluate_reads_dev_test_split_and_aggregates_all_facets(tmp_path):
+    """evaluate.py:103-154: {ds}-evaluation_splits.json assigns every query to dev or test (separate aggregate rows, in
+    first-seen order); facet='all' takes one result set per facet and adds the per-split aggregate over all of them."""
+    from aspire_b200.evaluation import evaluate
+    name, pool = _write_dataset(str(tmp_path), n=30)
+    with open(os.path.join(str(tmp_path), f"{name}-evaluation_splits.json"), "w") as fh:
+        json.dump({"1000": "dev", "1001": "test"}, fh)
+    with open(os.path.join(str(tmp_path), f"{name}-queries-release.csv"), "w") as fh:
+        fh.write("pid,title\n1000,Query zero\n1001,Query one\n")
+    ds = EvalDataset(name, str(tmp_path))
+    assert ds.get_test_dev_split() == {"1000": "dev", "1001": "test"}
+    res = score(_LenModel(name="len", encoding_type="sentence"), ds, None, None)
+    per_query, agg = evaluate(res, ds, None)
+    assert [m["split"] for m in per_query] == ["dev", "test"] and per_query[0]["title"] == "Query zero"
+    assert [(a["facet"], a["split"]) for a in agg] == [("unfaceted", "dev"), ("unfaceted", "test")]
+    assert agg[0]["av_precision"] == round(per_query[0]["av_precision"], 4)
+    # facet = 'all': the same pool file serves as every facet's pool here
+    for f in ("background", "method", "result"):
+        with open(os.path.join(str(tmp_path), f"test-pid2anns-{name}-{f}.json"), "w") as fh:
+            json.dump(pool, fh)
+    per_query, agg = evaluate({f: res for f in ("background", "method", "result")}, ds, "all", results_dir=str(tmp_path / "r"))
+    assert len(per_query) == 6
+    assert [(a["facet"], a["split"]) for a in agg] == [("background", "dev"), ("background", "test"), ("method", "dev"),
+                                                       ("method", "test"), ("result", "dev"), ("result", "test"),
+                                                       ("all", "dev"), ("all", "test")]
+    assert os.path.exists(os.path.join(str(tmp_path / "r"), "aggregated-evaluations-all.csv"))
+    # csfcube has no split file by definition: every query is 'test'
+    assert EvalDataset.get_test_dev_split(type("D", (), {"name": "csfcube", "root_path": str(tmp_path)})()) is None

@@ -205,3 +205,26 @@ def test_l2top2_and_attention_heads_vs_reference_golden():
         sm = softmax.cpu().numpy()
         for b, (a_, b_) in enumerate(zip(ql, cl)):
             assert np.all(sm[b, a_:] == 0) and np.all(sm[b, :, b_:] == 0)
+
+
+@pytest.mark.parametrize("S", [10, 30])
+def test_duplicate_sentences_score_exactly_zero_like_cdist(S):
+    """torch.cdist / scipy cdist (pair_distances.py:167, pp_gen_nearest.py:942) compute abstracts' distances directly:
+    an identical sentence in query and candidate is at distance exactly 0 (not the 1e-4 that the clamped
+    |q|^2 + |c|^2 - 2 q.c formula leaves), and near-duplicates keep their digits.  Both paired kernels (<= 10 sentences:
+    pair_cost.cu, <= 32: ot_varlen.cu) re-evaluate a small winning distance directly."""
+    from aspire_b200.distances import l2max_scores
+    g = torch.Generator().manual_seed(S)
+    B, D = 300, 768
+    q = 3.0 * torch.randn(B, S, D, generator=g)            # BERT-scale norms (~80): cancellation noise would be ~1e-2
+    c = 3.0 * torch.randn(B, S, D, generator=g)
+    ql = torch.randint(2, S + 1, (B,), generator=g).int()
+    cl = torch.randint(2, S + 1, (B,), generator=g).int()
+    c[::3, 1] = q[::3, 0]                                  # exact duplicates
+    c[1::3, 0] = q[1::3, 1] + 1e-4 * torch.randn(len(range(1, B, 3)), D, generator=g)   # near-duplicates, distance ~2.8e-3
+    best, idx, _ = l2max_scores(q.cuda(), ql.cuda(), c.cuda(), cl.cuda())
+    best, idx = best.cpu(), idx.cpu()
+    assert (best[::3] == 0).all() and (idx[::3] == 0 * S + 1).all()
+    ref = -torch.cdist(q[1::3].double(), c[1::3].double())[:, 1, 0]
+    assert (idx[1::3] == 1 * S + 0).all()
+    assert ((best[1::3].double() - ref).abs() <= 1e-6).all()
