@@ -70,6 +70,10 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_ot_fused_tc = value != 0;
         return ASP_OK;
     }
+    if (strcmp(key, "attn_tc") == 0) {  // developer switch: 1 tcgen05 attention (plain bf16, L <= 256), 0 mma.sync attention
+        asp::g_attn_tc = value != 0;
+        return ASP_OK;
+    }
     if (strcmp(key, "oa_warps") == 0) {  // developer switch: Sinkhorn warps per CTA of ot_allpairs.cu
         ASP_REQUIRE(value == 8 || value == 12, "asp_set_option: oa_warps must be 8 or 12");
         asp::g_oa_warps = value;

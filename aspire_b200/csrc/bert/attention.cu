@@ -239,9 +239,15 @@ static int attention_launch_as(const void* qkv_hi, const void* qkv_lo, const int
     return ASP_OK;
 }
 
+bool attention_tc_supported(const void* qkv_lo, int L, int H, int heads);
+int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int L, int H, int heads, void* ctx_hi,
+                        cudaStream_t stream);
+
 int attention_launch(const void* qkv_hi, const void* qkv_lo, const int32_t* seq_lens, int B, int L, int H, int heads,
                      void* ctx_hi, void* ctx_lo, cudaStream_t stream) {
     ASP_REQUIRE(H == heads * kHeadDim, "attention: head size must be 64 (hidden %d, heads %d)", H, heads);
+    // plain bf16, L <= 256: both contractions on tcgen05 (attention_tc.cu); longer sequences and the bf16x3 mode stay here
+    if (attention_tc_supported(qkv_lo, L, H, heads)) return attention_tc_launch(qkv_hi, seq_lens, B, L, H, heads, ctx_hi, stream);
     // (128 query rows per CTA -- QW = 8 -- halve the K/V staging per query but measured 1 % slower at B=32, L=256: two
     // 8-warp CTAs per SM hide the softmax latency worse than four 4-warp ones.)
     if (qkv_lo) return attention_launch_as<true, 4>(qkv_hi, qkv_lo, seq_lens, B, L, H, heads, ctx_hi, ctx_lo, stream);

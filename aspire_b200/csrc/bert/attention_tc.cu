@@ -1,0 +1,285 @@
+// K0 self-attention on tcgen05 (plain bf16 mode, L <= 256): softmax(Q K^T / 8 + key-padding mask) V per (document, head).
+//
+// Replaces BertSelfAttention as reached from examples/ex_aspire_consent.py:72 -- the same contraction attention.cu runs
+// on mma.sync fragments (38.5 us per layer at 8192 tokens, 17 % of the encoder's time for 5 % of its FLOPs).  One CTA =
+// 128 query rows of one (document, head), all <= 256 keys at once, no online softmax:
+//   TMA      Q [128 x 64], K [256 x 64], V [256 x 64] boxes straight out of the fused QKV activation [tokens, 3 * hidden]
+//            (128-byte rows, 128B swizzle); rows past the batch are zero-filled, keys past the document are masked
+//   MMA 1    S[128 x 256] = Q K^T: 4 tcgen05.mma (M 128, N 256, K 16), fp32 in 256 TMEM columns
+//   meanwhile the four warps transpose V into V^T [64 x 256] (the B operand of P V must be K-major; 8 x 8 blocks through
+//            ldmatrix.trans / stmatrix, swizzled both sides)
+//   softmax  one thread per query row: row max, then p = 2^((s - max) / 8 * log2 e) straight from TMEM (tcgen05.ld, 32
+//            columns at a time), row sum in fp32, P as bf16 into shared memory in the A-operand layout (it reuses the
+//            Q / K / V staging, which MMA 1 and the transposition are done with)
+//   MMA 2    O[128 x 64] = P V: 16 tcgen05.mma (M 128, N 64, K 16) into TMEM columns 0-63 (S is consumed by then)
+//   epilogue O / row sum -> bf16 context rows
+// 112 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, one's softmax under the other's loads and MMAs.
+#include <cuda_bf16.h>
+#include "../common.cuh"
+#include "tc05.cuh"
+
+namespace asp {
+
+using namespace tc;
+
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+constexpr int kAtQ = 128, kAtKeys = 256, kAtD = 64;
+constexpr int kAtQBytes = kAtQ * 128, kAtKBytes = kAtKeys * 128;              // 16 KB, 32 KB
+constexpr int kAtOffK = kAtQBytes, kAtOffV = kAtOffK + kAtKBytes, kAtOffVt = kAtOffV + kAtKBytes;  // 16, 48, 80 KB
+constexpr int kAtVtBlock = kAtD * 128;                                        // one 64-key K block of V^T: 8 KB
+constexpr int kAtPBlock = kAtQ * 128;                                         // one 64-key K block of P: 16 KB (P at offset 0)
+constexpr int kAtOffBar = kAtOffVt + 4 * kAtVtBlock;                          // 3 mbarriers + the TMEM address
+constexpr int kAtSmem = kAtOffBar + 64;  // 112 KB + 64 B: with the 1 KB the system keeps per CTA, two CTAs fit in 227 KB.
+                                         // No static shared memory and no alignment slack: the dynamic window of a kernel
+                                         // without static shared memory starts 1024-byte aligned (checked at run time).
+
+__device__ __forceinline__ void at_ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void at_stmatrix_x4(uint32_t addr, const uint32_t (&r)[4]) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3])
+                 : "memory");
+}
+
+constexpr int kAtThreads = 256;
+constexpr float kAtSafeExp = 100.f;  // largest exponent of 2 a probability may carry before the exact path takes over
+
+// one 32-key piece of a row: p = 2^((s - m) c) into the P tile as bf16; returns the sum of the probabilities and tracks
+// the largest exponent.  nvalid = keys of the piece inside the document: 32 (no per-element test), 1..31, or 0 (zeros).
+__device__ __forceinline__ float at_softmax_piece(const float (&v)[32], int c0, int nvalid, float sc, float off, uint8_t* smem, int r,
+                                                  float& xmax) {
+    uint32_t pk[16];
+    float sum = 0.f;
+    if (nvalid >= 32) {  // warp-uniform
+        float s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+            const float x0 = fmaf(v[e], sc, -off), x1 = fmaf(v[e + 1], sc, -off);
+            xmax = fmaxf(xmax, fmaxf(x0, x1));
+            const float p0 = ex2(x0), p1 = ex2(x1);
+            sum += p0;
+            s1 += p1;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        sum += s1;
+    } else if (nvalid > 0) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+            const float x0 = fmaf(v[e], sc, -off), x1 = fmaf(v[e + 1], sc, -off);
+            const bool in0 = e < nvalid, in1 = e + 1 < nvalid;
+            xmax = fmaxf(xmax, fmaxf(in0 ? x0 : -INFINITY, in1 ? x1 : -INFINITY));
+            const float p0 = in0 ? ex2(x0) : 0.f, p1 = in1 ? ex2(x1) : 0.f;
+            sum += p0 + p1;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+    }
+    uint8_t* prow = smem + (c0 >> 6) * kAtPBlock + (r >> 3) * 1024 + (r & 7) * 128;
+    const int ch0 = (c0 & 63) >> 3;  // first 16-byte chunk (8 keys) of this 32-key piece inside its 64-key block
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(prow + ((((ch0 + q) ^ r) & 7) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    return sum;
+}
+
+__global__ void __launch_bounds__(kAtThreads, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tkv,
+                    const int32_t* __restrict__ seq_lens, int L, int H, __nv_bfloat16* __restrict__ ctx) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023u) __trap();  // the swizzled tiles need 1024-byte alignment
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAtOffBar);
+    uint64_t &bar_load = bars[0], &bar_s = bars[1], &bar_o = bars[2];
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 3);
+    // [2 halves][128 rows] row maxima, then row sums: in the part of the V staging that P does not cover (free once V^T exists)
+    float* xch = reinterpret_cast<float*>(smem + 4 * kAtPBlock);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kAtQ, head = blockIdx.y, b = blockIdx.z;
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tq);
+        tma_prefetch_desc(&tkv);
+        mbar_init(&bar_load, 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_o, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t sbase = smem_u32(smem);
+    const int nkeys = min(max(seq_lens[b], 1), min(L, kAtKeys));
+
+    if (threadIdx.x == 0) {
+        pdl_wait();  // the QKV projection has written its output
+        mbar_arrive_expect_tx(&bar_load, kAtQBytes + 2 * kAtKBytes);
+        tma_load_2d(smem, &tq, &bar_load, head * kAtD, b * L + q0);
+        tma_load_2d(smem + kAtOffK, &tkv, &bar_load, H + head * kAtD, b * L);
+        tma_load_2d(smem + kAtOffV, &tkv, &bar_load, 2 * H + head * kAtD, b * L);
+    }
+    mbar_wait(&bar_load, 0);
+    if (threadIdx.x == 0) {
+        tc_fence_after_sync();
+        constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtKeys);
+        const uint64_t qd = umma_desc_sw128(sbase), kd = umma_desc_sw128(sbase + kAtOffK);
+#pragma unroll
+        for (int kk = 0; kk < kAtD / 16; ++kk) umma_bf16(tmem_base, qd + 2 * kk, kd + 2 * kk, idesc, kk != 0);
+        umma_commit(&bar_s);
+    }
+    __syncwarp();
+    // ---- V -> V^T while MMA 1 runs: 8 x 8 blocks, four at a time (same 8 keys, four 8-wide slices of d) ----
+    {
+        const int mtx = lane >> 3, i = lane & 7;  // ldmatrix / stmatrix: lanes 8m..8m+7 address the rows of matrix m
+#pragma unroll 4
+        for (int t = warp; t < 2 * (kAtKeys / 8); t += kAtThreads / 32) {
+            const int k0 = (t >> 1) * 8, d0 = (t & 1) * 32 + mtx * 8;
+            const int key = k0 + i;
+            const uint32_t src = sbase + kAtOffV + key * 128 + ((((d0 >> 3) ^ key) & 7) << 4);
+            uint32_t r[4];
+            at_ldmatrix_x4_trans(r, src);
+            const int drow = d0 + i;
+            const uint32_t dst = sbase + kAtOffVt + (k0 >> 6) * kAtVtBlock + drow * 128 + (((((k0 & 63) >> 3)) ^ drow) & 7) * 16;
+            at_stmatrix_x4(dst, r);
+        }
+    }
+    __syncthreads();  // V^T complete, nobody reads the V staging any more: P may overwrite Q / K / V
+    // ---- softmax: two threads per query row (warps w and w + 4 share TMEM lane quadrant w), 128 keys each.  S is read
+    //      from TMEM ONCE (64 B per clk per SM: a second pass over the 128 KB tile would cost as much as everything else):
+    //      the shift m is the maximum over the FIRST 32 keys of each half, not the row maximum.  Any m within 2^100 of the
+    //      row maximum gives the same normalised probabilities (bf16 and fp32 share the exponent range, the row sum is
+    //      fp32); a row whose exponents exceed 100 anyway sends the tile through the exact two-pass form. ----
+    mbar_wait(&bar_s, 0);
+    tc_fence_after_sync();
+    const int half = warp >> 2, r = (warp & 3) * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int cbeg = half * 128;
+    const float sc = 0.125f * kLog2e;
+    float v[32];
+    float mloc = -INFINITY;
+    if (cbeg < nkeys) {  // warp-uniform
+        tmem_ld32(trow + cbeg, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+            if (cbeg + e < nkeys) mloc = fmaxf(mloc, v[e]);
+    }
+    xch[half * 128 + r] = mloc;
+    __syncthreads();
+    float m = fmaxf(xch[r], xch[128 + r]);
+    float off = m * sc, sum = 0.f, xmax = -INFINITY;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+        if (c0 != cbeg && c0 < nkeys) tmem_ld32(trow + c0, v);   // (the first piece is still in registers)
+        sum += at_softmax_piece(v, c0, min(max(nkeys - c0, 0), 32), sc, off, smem, r, xmax);  // beyond the document: zeros
+    }
+    if (__syncthreads_or(xmax > kAtSafeExp)) {
+        // exact form (rare): row maximum over all keys first, then the probabilities again
+        float me = -INFINITY;
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + 128 && c0 < nkeys; c0 += 32) {
+            tmem_ld32(trow + c0, v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                if (c0 + e < nkeys) me = fmaxf(me, v[e]);
+        }
+        __syncthreads();
+        xch[half * 128 + r] = me;
+        __syncthreads();
+        m = fmaxf(xch[r], xch[128 + r]);
+        off = m * sc;
+        sum = 0.f;
+#pragma unroll 1
+        for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+            if (c0 < nkeys) tmem_ld32(trow + c0, v);
+            sum += at_softmax_piece(v, c0, min(max(nkeys - c0, 0), 32), sc, off, smem, r, xmax);
+        }
+    }
+    __syncthreads();
+    xch[half * 128 + r] = sum;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P and V^T were written through the generic proxy
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_fence_after_sync();
+        constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtD);
+#pragma unroll
+        for (int kb = 0; kb < kAtKeys / 64; ++kb) {
+            const uint64_t pd = umma_desc_sw128(sbase + kb * kAtPBlock), vd = umma_desc_sw128(sbase + kAtOffVt + kb * kAtVtBlock);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, pd + 2 * kk, vd + 2 * kk, idesc, (kb | kk) != 0);
+        }
+        umma_commit(&bar_o);
+    }
+    __syncwarp();
+    const float inv = 1.0f / (xch[r] + xch[128 + r]);
+    mbar_wait(&bar_o, 0);
+    tc_fence_after_sync();
+    // ---- epilogue: the half-th 32 columns of O for row r ----
+    {
+        tmem_ld32(trow + half * 32, v);
+        if (q0 + r < L) {
+            __nv_bfloat16* dst = ctx + ((size_t)b * L + q0 + r) * H + head * kAtD + half * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * q + 2 * e] * inv, v[8 * q + 2 * e + 1] * inv);
+                    w[e] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+int g_attn_tc = 1;  // asp_set_option("attn_tc"): 1 = plain-bf16 attention with L <= 256 on tcgen05, 0 = always mma.sync
+
+bool attention_tc_supported(const void* qkv_lo, int L, int H, int heads) {
+    return g_attn_tc && qkv_lo == nullptr && L >= 1 && L <= kAtKeys && H == heads * kAtD;
+}
+
+int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int L, int H, int heads, void* ctx_hi,
+                        cudaStream_t stream) {
+    // tensor maps of the QKV activation, cached: the encoder calls this once per layer with the same workspace
+    struct Cached {
+        const void* ptr = nullptr;
+        uint64_t rows = 0, cols = 0;
+        CUtensorMap q, kv;
+    };
+    static thread_local Cached cache;
+    const uint64_t rows = (uint64_t)B * L, cols = 3ull * H;
+    if (cache.ptr != qkv_hi || cache.rows != rows || cache.cols != cols) {
+        int rc;
+        if ((rc = make_tmap_bf16(&cache.q, qkv_hi, rows, cols, kAtQ))) return rc;
+        if ((rc = make_tmap_bf16(&cache.kv, qkv_hi, rows, cols, kAtKeys))) return rc;
+        cache.ptr = qkv_hi;
+        cache.rows = rows;
+        cache.cols = cols;
+    }
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    ASP_CUDA(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+        attr_dev = dev;
+    }
+    dim3 grid((L + kAtQ - 1) / kAtQ, heads, B);
+    ASP_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(kAtThreads), (size_t)kAtSmem, stream, cache.q, cache.kv, seq_lens, L, H,
+                        (__nv_bfloat16*)ctx_hi));
+    ASP_LAUNCH_CHECK("attention_tc_kernel");
+    return ASP_OK;
+}
+
+}  // namespace asp

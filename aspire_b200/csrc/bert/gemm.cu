@@ -25,6 +25,7 @@
 // resolution).  The producer simply picks the tensor map of the pass; nothing else changes.
 #include <algorithm>
 #include "../common.cuh"
+#include <unordered_map>
 #include "tc05.cuh"
 
 namespace asp {
@@ -624,7 +625,32 @@ static EncodeTiledFn encode_fn() {
 }
 
 // Row-major bf16 matrix [rows, cols] (cols contiguous) -> tensor map with a [box_rows x 64] box and 128B swizzle.
+// Encoded maps are kept per thread, keyed by (pointer, shape, box): a forward pass asks for the same ~100 maps (every
+// weight, the activation workspaces) on every call, and cuTensorMapEncodeTiled costs about a microsecond each -- 288
+// encodes per forward were a fifth of the host time of a small batch.
+struct TmapKey {
+    const void* ptr;
+    uint64_t rows, cols;
+    uint32_t box_rows;
+    bool operator==(const TmapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h ^= k.rows * 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+        h ^= k.cols * 0xc2b2ae3d27d4eb4full + (h << 6) + (h >> 2);
+        return h ^ (k.box_rows * 0x165667b19e3779f9ull);
+    }
+};
+
 int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+    const TmapKey key{ptr, rows, cols, box_rows};
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *m = it->second;
+        return ASP_OK;
+    }
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -642,6 +668,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols
                   (unsigned long long)rows, (unsigned long long)cols);
         return ASP_ERR_CUDA;
     }
+    if (cache.size() >= 4096) cache.clear();  // bounded: a long-lived process that keeps reallocating its buffers
+    cache.emplace(key, *m);
     return ASP_OK;
 }
 

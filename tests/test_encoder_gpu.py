@@ -126,3 +126,34 @@ def test_encode_stream_matches_batchwise_encode():
             _, reps = model.forward(bert_batch=bb, abs_lens=al, sent_tok_idxs=sti)
         for i, n in enumerate(al):
             assert torch.equal(got[s + i], reps[i, :n])
+
+
+@pytest.mark.parametrize("B,L,lens", [(3, 256, [256, 130, 7]), (4, 129, [129, 64, 65, 2]), (2, 70, [70, 33]), (2, 200, [1, 200])])
+def test_tcgen05_attention_equals_mma_sync_attention(B, L, lens):
+    """attention_tc.cu (plain bf16, L <= 256: Q K^T and P V on tcgen05, V transposed in shared memory, softmax straight
+    from TMEM) against attention.cu (mma.sync fragments, online softmax) inside the same 2-layer encoder: both round Q, K,
+    V and P to bf16 and accumulate in fp32, so the hidden states agree to bf16 round-off -- on pad positions too -- and
+    both stay within the bf16 tolerance of the fp32 Hugging Face forward."""
+    from aspire_b200 import _abi
+    from aspire_b200.encoder import B200BertEncoder
+    model = ref_shims.seeded_bert(seed=5, num_hidden_layers=2)
+    g = torch.Generator().manual_seed(L)
+    ids = torch.randint(1000, 31000, (B, L), generator=g)
+    for b, n in enumerate(lens):
+        ids[b, n:] = 0
+    enc = B200BertEncoder(model)
+    out = {}
+    for mode in (1, 0):
+        _abi.set_option("attn_tc", mode)
+        try:
+            out[mode] = enc.forward(ids, lens, precision="bf16").clone()
+            torch.cuda.synchronize()
+        finally:
+            _abi.set_option("attn_tc", 1)
+    assert torch.isfinite(out[1]).all()
+    rel = ((out[1] - out[0]).norm() / out[0].norm()).item()
+    assert rel <= 6e-3, f"tcgen05 vs mma.sync attention: relative L2 {rel:.3e}"
+    ref = _hf_reference(model, ids, lens)
+    valid = (torch.arange(L)[None, :] < torch.tensor(lens)[:, None]).cuda()
+    rel_ref = ((out[1] - ref)[valid].norm() / ref[valid].norm()).item()
+    assert rel_ref <= 3e-2, f"tcgen05 attention vs HF fp32: relative L2 {rel_ref:.3e}"
