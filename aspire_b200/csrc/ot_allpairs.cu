@@ -45,6 +45,12 @@ constexpr int kOaAccCols = 256;              // TMEM columns per accumulator buf
 #ifndef ASP_OA_IDLE_DRAIN
 #define ASP_OA_IDLE_DRAIN 0
 #endif
+// 1: a quarter of the exponentials on the FMA / ALU pipes (ot_pair.cuh: ex2_poly2) to relieve the MUFU pipe.  Measured
+// SLOWER with 12 Sinkhorn warps (3.64e8 vs 3.83e8 pairs/s, profiles/r02_3d_otallpairs_poly_ab.txt): 15 issue slots per
+// two exponentials instead of 2 -- at 0.75 of the MUFU bound the warps are as short of issue slots as of MUFU results.
+#ifndef ASP_OA_POLY
+#define ASP_OA_POLY 0
+#endif
 template <int NS>
 __device__ __forceinline__ void oa_wait(uint64_t* bar, uint32_t parity) {
     if constexpr (NS == 0) mbar_wait_parked(bar, parity);
@@ -67,11 +73,11 @@ constexpr int oa_smem_bytes() { return kOaStages * kApStage + NW * 32 * kOaLd * 
 
 __device__ __forceinline__ void oa_phase2(float* Cs, int ql, int cl, int b, int Sq, int Sc, const float* eps_s, int n_eps,
                                           float inv_temp, const OtOut& out) {
-    solve_pair_thread_stream<kOaFT, kOaFT, false>(Cs, ql, cl, b, Sq, Sc, eps_s, n_eps, inv_temp, out);
+    solve_pair_thread_stream<kOaFT, kOaFT, false, ASP_OA_POLY != 0>(Cs, ql, cl, b, Sq, Sc, eps_s, n_eps, inv_temp, out);
 }
 __device__ __forceinline__ void oa_phase2_full(float* Cs, int b, const float* eps_s, int n_eps, float inv_temp,
                                                const OtOut& out) {
-    solve_pair_thread_stream<kOaFT, kOaFT, true>(Cs, kOaFT, kOaFT, b, kOaFT, kOaFT, eps_s, n_eps, inv_temp, out);
+    solve_pair_thread_stream<kOaFT, kOaFT, true, ASP_OA_POLY != 0>(Cs, kOaFT, kOaFT, b, kOaFT, kOaFT, eps_s, n_eps, inv_temp, out);
 }
 
 template <int NW>

@@ -273,6 +273,25 @@ __device__ __forceinline__ void solve_pair_thread(LoadCost load_cost, int ql_in,
 // Same arithmetic, same order of operations per entry as sinkhorn_step / solve_pair_thread above.
 namespace asp {
 
+// 2^x for a pair of exponents on the FMA / ALU pipes instead of the MUFU pipe: round-to-nearest split x = n + f with the
+// 1.5 * 2^23 trick, a degree-5 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.5e-7, the class of ex2.approx),
+// and n added into the exponent field.  Exponents are clamped to [-126, 126]: below that the true value is < 2^-126
+// anyway; above it the caller must take the stabilised path (it tracks the largest exponent it passed in).
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fminf(fmaxf(x.x, -126.f), 126.f);
+    x.y = fminf(fmaxf(x.y, -126.f), 126.f);
+    const float2 t = __fadd2_rn(x, dup2(12582912.f));
+    const float2 nf = __fadd2_rn(t, dup2(-12582912.f));
+    const float2 f = __ffma2_rn(nf, dup2(-1.f), x);
+    float2 p = __ffma2_rn(dup2(0.0013400432653725147f), f, dup2(0.009676037356257439f));
+    p = __ffma2_rn(p, f, dup2(0.05550327152013779f));
+    p = __ffma2_rn(p, f, dup2(0.2402210682630539f));
+    p = __ffma2_rn(p, f, dup2(0.6931471824645996f));
+    p = __ffma2_rn(p, f, dup2(1.0000001192092896f));
+    return f2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+              __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 template <int TQ, int TC>
 struct PairStateS {
     float la[TQ], f[TQ];
@@ -307,7 +326,11 @@ static __device__ __noinline__ void stabilised_step_mem(const float* Cs, int TQ,
     }
 }
 
-template <int TQ, int TC, bool FULL>
+// POLY: every fourth pair of exponentials is evaluated by ex2_poly2 on the FMA / ALU pipes.  For a kernel whose Sinkhorn
+// warps are bound by the MUFU pipe (the Q x C all-pairs kernel: 120 MUFU results per pair and step against ~200 packed
+// FMA-pipe instructions) that moves a quarter of the exponentials to pipes with room; the 1 x N kernel, bound by fp32
+// issue, keeps POLY = false.
+template <int TQ, int TC, bool FULL, bool POLY = false>
 __device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, const float* Cs, int ql_in, int cl_in, float eps,
                                                      float weight) {
     static_assert((TQ * TC) % 4 == 0 && TC % 2 == 0, "tile is read as float4 chunks holding whole column pairs");
@@ -323,6 +346,7 @@ __device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, con
         S[j] = f2(0.f, 0.f);
     }
     float chk = 0.f;
+    float xpoly = -INFINITY;  // largest exponent handed to ex2_poly2 (which saturates instead of overflowing)
     float fnew[TQ];
     float2 R = f2(0.f, 0.f);
     const float4* C4 = reinterpret_cast<const float4*>(Cs);
@@ -339,7 +363,13 @@ __device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, con
             const float2 cc = hlf ? f2(cv.z, cv.w) : f2(cv.x, cv.y);
             const float2 uu = dup2(fmaf(st.f[i], t, st.la[i]));
             const float2 x = __ffma2_rn(cc, nt2, __fadd2_rn(uu, v[j]));
-            const float2 ex = f2(ex2(x.x), ex2(x.y));
+            float2 ex;
+            if (POLY && ((2 * c + hlf) & 3) == 3) {  // compile-time after unrolling
+                xpoly = fmaxf(xpoly, fmaxf(x.x, x.y));
+                ex = ex2_poly2(x);
+            } else {
+                ex = f2(ex2(x.x), ex2(x.y));
+            }
             R = __fadd2_rn(R, ex);
             S[j] = __fadd2_rn(S[j], ex);
             if (j == TP - 1) {  // row i complete
@@ -357,7 +387,7 @@ __device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, con
         gnew[j] = __ffma2_rn(nscale2, __fadd2_rn(l, f2(-st.lb[j].x, -st.lb[j].y)), st.g[j]);
         chk = fmaxf(chk, fmaxf((2 * j < cl) ? fabsf(l.x) : 0.f, (2 * j + 1 < cl) ? fabsf(l.y) : 0.f));
     }
-    const bool bad = !(chk < 1e30f);
+    const bool bad = !(chk < 1e30f) || (POLY && xpoly > 120.f);
     if (__builtin_expect(bad, 0)) {
         // max-stabilised recomputation of both half-steps from the old potentials (rare): out of line, rolled loops
         float buf[4 * TQ + 4 * TC];  // la, f, fnew | lb, g, gnew  (the helper works on memory)
@@ -388,7 +418,7 @@ __device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, con
 // Solve one pair in the calling thread with the cost tile in shared memory.  On entry Cs[i*TC+j] holds the distance for
 // i < ql, j < cl and anything >= 1e30 elsewhere (what phase 1 of the fused kernel writes); padded entries are
 // overwritten with 0 (any finite value works: their weight is exactly 0).
-template <int TQ, int TC, bool FULL>
+template <int TQ, int TC, bool FULL, bool POLY = false>
 __device__ __forceinline__ void solve_pair_thread_stream(float* Cs, int ql_in, int cl_in, int b, int Sq_in, int Sc_in,
                                                          const float* eps_sched, int n_eps, float inv_temp,
                                                          const OtOut& out) {
@@ -454,7 +484,7 @@ __device__ __forceinline__ void solve_pair_thread_stream(float* Cs, int ql_in, i
 #pragma unroll 1
         for (int k = -1; k <= n_eps; ++k) {
             const bool plain = (k < 0) | (k == n_eps);
-            sinkhorn_step_stream<TQ, TC, FULL>(st, Cs, ql, cl, eps_sched[min(max(k, 0), n_eps - 1)], plain ? 1.0f : 0.5f);
+            sinkhorn_step_stream<TQ, TC, FULL, POLY>(st, Cs, ql, cl, eps_sched[min(max(k, 0), n_eps - 1)], plain ? 1.0f : 0.5f);
         }
     }
 

@@ -249,6 +249,44 @@ def workload_config(n_gpus, nq):
                            else "single GPU"}
 
 
+def cpu_call_patterns(ref, q, c, threads):
+    """the reference's three call patterns for otAspire and its tsAspire twin, timed on the host cores on one
+    query x its pool (bounded samples).  q [1,S,D], c [POOL,S,D] CPU tensors; ``ref`` = the mirrored reference module."""
+    import collections
+    torch.set_num_threads(threads)
+    rl = collections.namedtuple("RepLen", ["embed", "abs_lens"])
+    scorer = ref.AllPairMaskedWasserstein({"geoml_blur": BLUR, "geoml_scaling": SCALING, "sent_sm_temp": TEMP})
+    out = {"cores": threads}
+
+    def tup(x, n):
+        return rl(embed=x.permute(0, 2, 1), abs_lens=[SENTS] * n)
+    # (i) one compute_distance call per pair -- what evaluate.py's get_similarity loop does (utils/models.py:185-196)
+    n = 100
+    t0 = time.perf_counter()
+    for j in range(n):
+        scorer.compute_distance(query=tup(q, 1), cand=tup(c[j:j + 1], 1))
+    out["per_pair_calls"] = {"pairs_per_s": n / (time.perf_counter() - t0), "sample": f"{n} pairs"}
+    # (ii) 64-candidate chunks with return_pair_sims=True (pp_gen_nearest.py:182-202)
+    t0 = time.perf_counter()
+    for s0 in range(0, POOL, 64):
+        m = min(64, POOL - s0)
+        scorer.compute_distance(query=tup(q.expand(m, -1, -1), m), cand=tup(c[s0:s0 + m], m), return_pair_sims=True)
+    out["chunks_of_64_with_plans"] = {"pairs_per_s": POOL / (time.perf_counter() - t0), "sample": f"{POOL} pairs"}
+    # (iii) one call for the whole pool
+    t0 = time.perf_counter()
+    scorer.compute_distance(query=tup(q.expand(POOL, -1, -1), POOL), cand=tup(c, POOL))
+    out["one_call_per_pool"] = {"pairs_per_s": POOL / (time.perf_counter() - t0), "sample": f"{POOL} pairs"}
+    # (iv) tsAspire, torch path (pair_distances.allpair_masked_dist_l2max)
+    try:
+        from src.learning.facetid_models import pair_distances as pd_ref
+        t0 = time.perf_counter()
+        pd_ref.allpair_masked_dist_l2max(query=tup(q.expand(POOL, -1, -1), POOL), cand=tup(c, POOL))
+        out["tsaspire_torch_l2max"] = {"pairs_per_s": POOL / (time.perf_counter() - t0), "sample": f"{POOL} pairs"}
+    except Exception as e:  # the mirror may lack the training-side module
+        out["tsaspire_torch_l2max"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ the other kernel families
 def side_kernels(dev, hbm_peak):
     """Every kernel family of the path besides the headline one, each at its BASELINE config size, timed with CUDA events
@@ -532,6 +570,28 @@ def main():
     lb.record()
     torch.cuda.synchronize()
     lat_ms = la.elapsed_time(lb) / 200
+    # the same pool scored the way pp_gen_nearest.py:182-202 calls it: 64 candidates per call, plans requested
+    ch_out = {k: torch.empty(s_, dtype=torch.float32, device=dev) for k, s_ in
+              (("primal", (64,)), ("alpha", (64, SENTS)), ("beta", (64, SENTS)), ("neg_cost", (64, SENTS, SENTS)),
+               ("plan", (64, SENTS, SENTS)), ("weighted", (64, SENTS, SENTS)))}
+    cl64 = c_lens[:64].contiguous()
+
+    def chunks(i):
+        p = i % args.pools
+        off = (i % NQ) * POOL
+        for s0 in range(0, POOL, 64):
+            m = min(64, POOL - s0)
+            ot_scores(q1, ql1, pools[p][off + s0:off + s0 + m], cl64[:m], eps, temp=TEMP, want=tuple(ch_out), broadcast_query=True,
+                      out={k: v[:m] for k, v in ch_out.items()})
+    for i in range(3):
+        chunks(i)
+    torch.cuda.synchronize()
+    la.record()
+    for i in range(20):
+        chunks(i)
+    lb.record()
+    torch.cuda.synchronize()
+    chunk_ms = la.elapsed_time(lb) / 20
 
     # ---- e2e: host buffers in, host scores out, through the public API ------------------------------
     from aspire_b200.similarity import score_pools_host
@@ -592,7 +652,9 @@ def main():
                   "hbm_frac": BYTES_PER_PAIR * NP / (burst_ms * 1e-3) / 1e9 / peak,
                   "note": "first steps of the process (rank 0's clock), before the SM clock settles under the 1 kW power "
                           "cap; `value` above is the sustained figure"},
-        "latency_1x1k": {"pairs_per_launch": POOL, "ms_per_launch": lat_ms, "pairs_per_s": POOL / (lat_ms * 1e-3)},
+        "latency_1x1k": {"pairs_per_launch": POOL, "ms_per_launch": lat_ms, "pairs_per_s": POOL / (lat_ms * 1e-3),
+                         "as_64_candidate_calls_with_plans": {"ms_per_pool": chunk_ms, "pairs_per_s": POOL / (chunk_ms * 1e-3),
+                                                              "calls_per_pool": -(-POOL // 64)}},
     }
     if world == 1 and not args.no_side:
         del host_pools, host_q
@@ -620,6 +682,11 @@ def main():
         _, dref = cpu_reference_step(ar, qc, pc, threads, None)
         got = ot_scores(queries[0], q_lens, pools[0], c_lens, eps, temp=TEMP, q_group=POOL)["dual"][:CPU_QUERIES * POOL].cpu()
         rel = ((got - dref).abs() / dref.abs().clamp(min=1)).max().item()
+        if ref is not None:
+            try:
+                line["cpu_call_patterns"] = cpu_call_patterns(ref, qc[:1], pc[:POOL], threads)
+            except Exception as e:
+                line["cpu_call_patterns"] = {"error": f"{type(e).__name__}: {e}"}
         line["cpu_baseline"] = {"value": CPU_QUERIES * POOL * n / tot, "unit": "pairs/s", "cores": threads, "kind": kind,
                                 "sample": f"{n} passes over {CPU_QUERIES} of the step's queries x {POOL} candidates "
                                           f"({tot:.1f} s): {what}",
