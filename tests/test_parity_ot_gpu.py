@@ -422,3 +422,24 @@ def test_pool_kernel_on_tensor_cores_equals_fma_kernel_and_oracle(B, grp, Sq, Sc
     cls = cl[idx.long()[sub]] if indexed else cl[sub]
     ref = ar.ot_distance(q[sub // grp], ql[sub // grp].tolist(), cs, cls.tolist(), diameter=40.0).numpy()
     assert rel_err(res[1]["dual"].cpu().numpy()[sub.numpy()], ref).max() <= 1e-4
+
+
+def test_allpairs_kernel_empty_documents_and_single_query():
+    """Edge cases of asp_ot_score_allpairs: documents with zero sentences (no mass to move: distance 0, as the 1 x N kernel
+    returns), one query (takes the 1 x N launch), one candidate, and sizes that leave most of a tile empty."""
+    from aspire_b200 import ot_scores, ot_scores_allpairs, epsilon_schedule
+    g = torch.Generator().manual_seed(31)
+    eps = epsilon_schedule(30.0, 0.05, 0.9)
+    for NQ, NC in ((3, 5), (1, 40), (25, 1), (14, 17)):
+        q = (0.3 * torch.randn(NQ, 10, 128, generator=g)).cuda()
+        c = (0.3 * torch.randn(NC, 10, 128, generator=g)).cuda()
+        ql = torch.randint(0, 11, (NQ,), generator=g).int()
+        cl = torch.randint(0, 11, (NC,), generator=g).int()
+        ql[0] = 0
+        cl[-1] = 0
+        got = ot_scores_allpairs(q, ql.cuda(), c, cl.cuda(), eps)
+        assert torch.isfinite(got).all()
+        for i in range(NQ):
+            one = ot_scores(q[i:i + 1].contiguous(), ql[i:i + 1].cuda(), c, cl.cuda(), eps, broadcast_query=True)["dual"]
+            assert rel_err(got[i].cpu().numpy(), one.cpu().numpy()).max() <= 1e-5
+        assert (got[0] == 0).all() and (got[:, -1] == 0).all()
