@@ -70,6 +70,10 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_ot_fused_tc = value != 0;
         return ASP_OK;
     }
+    if (strcmp(key, "span_tma") == 0) {  // developer switch: 1 span pooling staged by cp.async.bulk, 0 streaming loads
+        asp::g_span_tma = value != 0;
+        return ASP_OK;
+    }
     if (strcmp(key, "attn_tc") == 0) {  // developer switch: 1 tcgen05 attention (plain bf16, L <= 256), 0 mma.sync attention
         asp::g_attn_tc = value != 0;
         return ASP_OK;

@@ -69,6 +69,7 @@ extern int g_gemm_kernel;    // asp_set_option("gemm_kernel")
 extern int g_gemm_cluster;   // asp_set_option("gemm_cluster")
 extern int g_gemm_pair;      // asp_set_option("gemm_pair")
 extern int g_attn_tc;        // asp_set_option("attn_tc")
+extern int g_span_tma;       // asp_set_option("span_tma")
 
 // Epsilon schedule passed by value in kernel parameter space (uniform, read through the constant bank).
 struct EpsSched {

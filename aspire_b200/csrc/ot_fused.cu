@@ -629,7 +629,8 @@ extern "C" int asp_ot_score_allpairs(const float* q, const int32_t* q_lens, int 
     ASP_REQUIRE(NQ >= 0 && NC >= 0, "asp_ot_score_allpairs: bad shape NQ=%d NC=%d", NQ, NC);
     if (NQ == 0 || NC == 0) return ASP_OK;
     if (NQ >= 2 && asp::g_ot_kernel == 0 && asp::ot_allpairs_supported(Sq, Sc, D) && workspace &&
-        workspace_bytes >= asp::ot_allpairs_workspace_bytes(NQ, NC, Sq, Sc, D) && (long long)NQ * NC <= 0x7fffffffLL) {
+        workspace_bytes >= asp::ot_allpairs_workspace_bytes(NQ, NC, Sq, Sc, D) && (long long)NQ * NC <= 0x7fffffffLL &&
+        (long long)NC * Sc <= 0x7fffffffLL && (long long)NQ * Sq <= 0x7fffffffLL) {
         int rc = asp::check_pair_args(q, q_lens, c, c_lens, NC, Sq, Sc, D);
         if (rc) return rc;
         ASP_REQUIRE(temp > 0.f, "asp_ot_score_allpairs: temp must be > 0");

@@ -51,6 +51,99 @@ span_mean_pool_kernel(const float* __restrict__ hidden, const int32_t* __restric
     }
 }
 
+// TMA variant.  A sentence span is a run of whole token rows, i.e. ONE contiguous byte range of the hidden state
+// ((end - start) * D * 4 bytes), so it is staged by the bulk-copy engine (cp.async.bulk, no tensor map needed): one thread
+// issues kSpRows rows per stage into a kSpStages-deep shared-memory ring and arms the stage's mbarrier with the byte count;
+// all threads then add up their 128-bit column slices from shared memory (conflict-free).  48 KB per CTA, four CTAs per SM.
+constexpr int kSpRows = 4, kSpStages = 4, kSpThreads = 192, kSpMaxSlices = 4;  // D <= 4 * 192 * 4 = 3072
+
+__device__ __forceinline__ void sp_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kSpThreads)
+span_mean_pool_tma_kernel(const float* __restrict__ hidden, const int32_t* __restrict__ spans, int L, int D, int Smax,
+                          float* __restrict__ sent_reps, float* __restrict__ cls_reps) {
+    extern __shared__ __align__(128) float sp_ring[];  // [kSpStages][kSpRows * D]
+    __shared__ uint64_t full[kSpStages];
+    const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
+    const int d4 = D >> 2;
+    const float* hb = hidden + (size_t)b * L * D;
+    if (s == Smax) {  // CLS row
+        if (cls_reps) {
+            float4* o = reinterpret_cast<float4*>(cls_reps + (size_t)b * D);
+            for (int k = tid; k < d4; k += kSpThreads) o[k] = reinterpret_cast<const float4*>(hb)[k];
+        }
+        return;
+    }
+    int start = spans[((size_t)b * Smax + s) * 2], end = spans[((size_t)b * Smax + s) * 2 + 1];
+    start = max(start, 0);
+    end = min(end, L);
+    const int n = max(end - start, 0);
+    const int nchunks = (n + kSpRows - 1) / kSpRows;
+    const uint32_t ring_u = (uint32_t)__cvta_generic_to_shared(sp_ring), bar_u = (uint32_t)__cvta_generic_to_shared(full);
+    if (tid == 0) {
+        for (int i = 0; i < kSpStages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u + 8u * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int c) {  // thread 0: rows [c * kSpRows, ...) of the span into stage c % kSpStages
+        const int rows = min(kSpRows, n - c * kSpRows);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)D * 4u, st = (uint32_t)(c % kSpStages);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_u + 8u * st), "r"(bytes) : "memory");
+        sp_bulk_load(ring_u + st * (uint32_t)(kSpRows * D * 4), hb + (size_t)(start + c * kSpRows) * D, bytes, bar_u + 8u * st);
+    };
+    if (tid == 0)
+        for (int c = 0; c < min(nchunks, kSpStages); ++c) issue(c);
+    float4 acc[kSpMaxSlices];
+#pragma unroll
+    for (int m = 0; m < kSpMaxSlices; ++m) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < nchunks; ++c) {
+        const uint32_t st = (uint32_t)(c % kSpStages), parity = (uint32_t)((c / kSpStages) & 1);
+        uint32_t ok = 0;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar_u + 8u * st), "r"(parity)
+                : "memory");
+        } while (!ok);
+        const int rows = min(kSpRows, n - c * kSpRows);
+        const float4* stage = reinterpret_cast<const float4*>(sp_ring + (size_t)st * kSpRows * D);
+#pragma unroll
+        for (int m = 0; m < kSpMaxSlices; ++m) {
+            const int k = tid + m * kSpThreads;
+            if (k < d4)
+                for (int r = 0; r < rows; ++r) {  // rows in span order: the same summation order as the streaming kernel
+                    const float4 a = stage[(size_t)r * d4 + k];
+                    acc[m].x += a.x; acc[m].y += a.y; acc[m].z += a.z; acc[m].w += a.w;
+                }
+        }
+        if (c + kSpStages < nchunks) {  // block-uniform: the stage is refilled once every thread has read it
+            __syncthreads();
+            if (tid == 0) issue(c + kSpStages);
+        }
+    }
+    float4* o = reinterpret_cast<float4*>(sent_reps + ((size_t)b * Smax + s) * D);
+    const float cnt = (float)max(n, 1);  // reference: sum / clamp(count, 1)
+#pragma unroll
+    for (int m = 0; m < kSpMaxSlices; ++m) {
+        const int k = tid + m * kSpThreads;
+        if (k < d4) {
+            float4 v = acc[m];
+            if (n > 0) { v.x /= cnt; v.y /= cnt; v.z /= cnt; v.w /= cnt; }
+            o[k] = v;
+        }
+    }
+}
+
+int g_span_tma = 1;  // asp_set_option("span_tma"): 1 = bulk-copy staging (D <= 3072), 0 = streaming 128-bit loads
+
 // ---- bounding-box diameter (geomloss max_diameter) ---------------------------------------------------
 __device__ __forceinline__ void atomic_min_f(float* a, float v) {
     int old = __float_as_int(*a);
@@ -132,6 +225,22 @@ extern "C" int asp_span_mean_pool(const float* hidden, const int32_t* spans, int
     if (B == 0) return ASP_OK;
     ASP_REQUIRE(B <= 65535, "asp_span_mean_pool: B=%d exceeds 65535 documents per call", B);
     dim3 grid(Smax + 1, B);
+    if (asp::g_span_tma && D <= asp::kSpMaxSlices * asp::kSpThreads * 4) {
+        const int smem = asp::kSpStages * asp::kSpRows * D * 4;
+        static thread_local int attr_dev = -1, attr_smem = 0;
+        int dev = 0;
+        ASP_CUDA(cudaGetDevice(&dev));
+        if (attr_dev != dev || attr_smem < smem) {
+            ASP_CUDA(cudaFuncSetAttribute(asp::span_mean_pool_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ASP_CUDA(cudaFuncSetAttribute(asp::span_mean_pool_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            attr_dev = dev;
+            attr_smem = smem;
+        }
+        asp::span_mean_pool_tma_kernel<<<grid, asp::kSpThreads, smem, (cudaStream_t)stream>>>(hidden, spans, L, D, Smax,
+                                                                                           sent_reps, cls_reps);
+        ASP_LAUNCH_CHECK("span_mean_pool_tma_kernel");
+        return ASP_OK;
+    }
     asp::span_mean_pool_kernel<<<grid, 192, 0, (cudaStream_t)stream>>>(hidden, spans, L, D, Smax, sent_reps,
                                                                        cls_reps);
     ASP_LAUNCH_CHECK("span_mean_pool_kernel");

@@ -42,6 +42,33 @@ def test_span_pool_large_random_vs_oracle():
     np.testing.assert_allclose(reps.cpu().numpy(), rr.numpy(), rtol=0, atol=5e-6)
 
 
+def test_span_pool_bulk_copy_staging_is_bit_identical_to_streaming_loads():
+    """asp_span_mean_pool with the spans staged by cp.async.bulk through a shared-memory ring (default) against the
+    streaming-load kernel: same summation order, so bit-identical -- empty spans, one-token spans, spans longer than the
+    ring (17+ rows), spans clipped at L, D = 768 and a small D."""
+    from aspire_b200 import _abi
+    from aspire_b200.consent import span_mean_pool
+    g = torch.Generator().manual_seed(11)
+    for B, L, D, S in ((7, 502, 768, 12), (3, 64, 128, 5)):
+        hidden = torch.randn(B, L, D, generator=g).cuda()
+        spans = torch.zeros(B, S, 2, dtype=torch.int32)
+        for b in range(B):
+            for s_ in range(S):
+                a = int(torch.randint(0, L, (1,), generator=g))
+                n = int(torch.randint(0, 60, (1,), generator=g)) if s_ % 3 else int(torch.randint(0, 3, (1,), generator=g))
+                spans[b, s_] = torch.tensor([a, a + n])          # may run past L: clipped
+        spans[0, 0] = torch.tensor([-1, -1])                      # missing sentence
+        out = {}
+        for mode in (1, 0):
+            _abi.set_option("span_tma", mode)
+            try:
+                out[mode] = [t.clone() for t in span_mean_pool(hidden, spans.cuda())]
+            finally:
+                _abi.set_option("span_tma", 1)
+        assert torch.equal(out[1][0], out[0][0]) and torch.equal(out[1][1], out[0][1])
+        assert (out[1][1][0, 0] == 0).all()
+
+
 def test_bbox_diameter():
     from aspire_b200 import bbox_diameter
     g = torch.Generator().manual_seed(9)
