@@ -75,7 +75,8 @@ extern "C" int asp_set_option(const char* key, int value) {
         return ASP_OK;
     }
     if (strcmp(key, "attn_tc") == 0) {  // developer switch: 1 tcgen05 attention (plain bf16, L <= 256), 0 mma.sync attention
-        asp::g_attn_tc = value != 0;
+        ASP_REQUIRE(value >= 0 && value <= 2, "asp_set_option: attn_tc must be 0, 1 or 2");
+        asp::g_attn_tc = value;
         return ASP_OK;
     }
     if (strcmp(key, "oa_warps") == 0) {  // developer switch: Sinkhorn warps per CTA of ot_allpairs.cu

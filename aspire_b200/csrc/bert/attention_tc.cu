@@ -14,6 +14,7 @@
 //   MMA 2    O[128 x 64] = P V: 16 tcgen05.mma (M 128, N 64, K 16) into TMEM columns 0-63 (S is consumed by then)
 //   epilogue O / row sum -> bf16 context rows
 // 112 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, one's softmax under the other's loads and MMAs.
+#include <algorithm>
 #include <cuda_bf16.h>
 #include "../common.cuh"
 #include "tc05.cuh"
@@ -244,7 +245,213 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-int g_attn_tc = 1;  // asp_set_option("attn_tc"): 1 = plain-bf16 attention with L <= 256 on tcgen05, 0 = always mma.sync
+// ---- persistent, warp-specialised version -----------------------------------------------------------------------------
+// One CTA per SM walks (document, head, query block) tiles.  Warp 0 is the producer: TMA loads of tile k + 1, MMA 1 of tile
+// k + 1 and MMA 2 of tile k are issued while the eight worker warps (256 threads, two per query row) run the transposition,
+// softmax and epilogue of tile k.  Two stages of shared memory (112 KB each: Q | K | V | V^T, P aliasing Q / K / V) and two
+// 256-column TMEM buffers (S, then O in its first 64 columns), one mbarrier per hand-over and stage.
+constexpr int kAtpThreads = 288;
+constexpr int kAtStage = kAtOffVt + 4 * kAtVtBlock;               // 112 KB
+constexpr int kAtpOffBar = 2 * kAtStage;
+constexpr int kAtpSmem = kAtpOffBar + 128;
+
+__device__ __forceinline__ void atp_workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kAtpThreads, 1)
+attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tkv,
+                               const int32_t* __restrict__ seq_lens, int B, int L, int H, int heads,
+                               __nv_bfloat16* __restrict__ ctx) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023u) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAtpOffBar);
+    uint64_t *loaded = bars, *s_ready = bars + 2, *p_ready = bars + 4, *o_ready = bars + 6, *stage_free = bars + 8;
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 10);
+    int* flag = reinterpret_cast<int*>(bars + 11);  // [2]: a row of the stage's tile needs the exact softmax
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nqb = (L + kAtQ - 1) / kAtQ;
+    const int ntiles = nqb * heads * B;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tq);
+        tma_prefetch_desc(&tkv);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&loaded[i], 1);
+            mbar_init(&s_ready[i], 1);
+            mbar_init(&p_ready[i], 256);
+            mbar_init(&o_ready[i], 1);
+            mbar_init(&stage_free[i], 256);
+            flag[i] = 0;
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (warp == 0) {
+        // ------------------------------ producer: TMA + MMA issue -------------------------------------------------
+        if (lane == 0) {
+            auto load_tile = [&](int k) {
+                const int t = blockIdx.x + k * gridDim.x, s = k & 1;
+                const int qb = t % nqb, head = (t / nqb) % heads, b = t / (nqb * heads);
+                uint8_t* st = smem + s * kAtStage;
+                mbar_arrive_expect_tx(&loaded[s], kAtQBytes + 2 * kAtKBytes);
+                tma_load_2d(st, &tq, &loaded[s], head * kAtD, b * L + qb * kAtQ);
+                tma_load_2d(st + kAtOffK, &tkv, &loaded[s], H + head * kAtD, b * L);
+                tma_load_2d(st + kAtOffV, &tkv, &loaded[s], 2 * H + head * kAtD, b * L);
+            };
+            auto mma2 = [&](int k) {
+                const int s = k & 1;
+                mbar_wait(&p_ready[s], (k >> 1) & 1);
+                tc_fence_after_sync();
+                constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtD);
+                const uint32_t st = sbase + s * kAtStage;
+#pragma unroll
+                for (int kb = 0; kb < kAtKeys / 64; ++kb) {
+                    const uint64_t pd = umma_desc_sw128(st + kb * kAtPBlock), vd = umma_desc_sw128(st + kAtOffVt + kb * kAtVtBlock);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base + s * 256, pd + 2 * kk, vd + 2 * kk, idesc, (kb | kk) != 0);
+                }
+                umma_commit(&o_ready[s]);
+            };
+            pdl_wait();  // the QKV projection has written its output
+            if (my_tiles > 0) load_tile(0);
+            for (int k = 0; k < my_tiles; ++k) {
+                const int s = k & 1;
+                mbar_wait(&loaded[s], (k >> 1) & 1);
+                tc_fence_after_sync();
+                {
+                    constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtKeys);
+                    const uint32_t st = sbase + s * kAtStage;
+                    const uint64_t qd = umma_desc_sw128(st), kd = umma_desc_sw128(st + kAtOffK);
+#pragma unroll
+                    for (int kk = 0; kk < kAtD / 16; ++kk) umma_bf16(tmem_base + s * 256, qd + 2 * kk, kd + 2 * kk, idesc, kk != 0);
+                    umma_commit(&s_ready[s]);
+                }
+                if (k >= 1) mma2(k - 1);
+                if (k + 1 < my_tiles) {
+                    // the other stage (and TMEM buffer) is free once the workers have stored tile k - 1
+                    if (k >= 1) mbar_wait(&stage_free[s ^ 1], ((k - 1) >> 1) & 1);
+                    load_tile(k + 1);
+                }
+            }
+            if (my_tiles > 0) mma2(my_tiles - 1);
+        }
+    } else {
+        // ------------------------------ workers: transposition, softmax, epilogue ---------------------------------
+        const int wid = warp - 1;                       // 0..7
+        const int half = wid >> 2, quad = warp & 3;     // TMEM lane quadrant is fixed by the hardware warp id
+        const int r = quad * 32 + lane;
+        const float sc = 0.125f * kLog2e;
+        for (int k = 0; k < my_tiles; ++k) {
+            const int t = blockIdx.x + k * gridDim.x, s = k & 1;
+            const uint32_t par = (k >> 1) & 1;
+            const int qb = t % nqb, head = (t / nqb) % heads, b = t / (nqb * heads);
+            const int q0 = qb * kAtQ;
+            const int nkeys = min(max(seq_lens[b], 1), min(L, kAtKeys));
+            uint8_t* st = smem + s * kAtStage;
+            const uint32_t stu = sbase + s * kAtStage;
+            float* xch = reinterpret_cast<float*>(st + 4 * kAtPBlock);
+            mbar_wait(&loaded[s], par);
+            {   // V -> V^T
+                const int mtx = lane >> 3, i = lane & 7;
+#pragma unroll 4
+                for (int tt = wid; tt < 2 * (kAtKeys / 8); tt += 8) {
+                    const int k0 = (tt >> 1) * 8, d0 = (tt & 1) * 32 + mtx * 8;
+                    const int key = k0 + i;
+                    uint32_t rr[4];
+                    at_ldmatrix_x4_trans(rr, stu + kAtOffV + key * 128 + ((((d0 >> 3) ^ key) & 7) << 4));
+                    const int drow = d0 + i;
+                    at_stmatrix_x4(stu + kAtOffVt + (k0 >> 6) * kAtVtBlock + drow * 128 + (((((k0 & 63) >> 3)) ^ drow) & 7) * 16, rr);
+                }
+            }
+            atp_workers_sync();          // V^T complete; the V staging is free
+            mbar_wait(&s_ready[s], par); // MMA 1 is done with Q and K: P may overwrite them
+            tc_fence_after_sync();
+            const uint32_t trow = tmem_base + s * 256 + ((uint32_t)(quad * 32) << 16);
+            const int cbeg = half * 128;
+            float v[32];
+            float mloc = -INFINITY;
+            if (cbeg < nkeys) {
+                tmem_ld32(trow + cbeg, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (cbeg + e < nkeys) mloc = fmaxf(mloc, v[e]);
+            }
+            xch[half * 128 + r] = mloc;
+            atp_workers_sync();
+            float m = fmaxf(xch[r], xch[128 + r]);
+            float off = m * sc, sum = 0.f, xmax = -INFINITY;
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+                if (c0 != cbeg && c0 < nkeys) tmem_ld32(trow + c0, v);
+                sum += at_softmax_piece(v, c0, min(max(nkeys - c0, 0), 32), sc, off, st, r, xmax);
+            }
+            if (xmax > kAtSafeExp) flag[s] = 1;
+            atp_workers_sync();
+            if (flag[s]) {  // exact two-pass form (rare), block-uniform
+                float me = -INFINITY;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + 128 && c0 < nkeys; c0 += 32) {
+                    tmem_ld32(trow + c0, v);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < nkeys) me = fmaxf(me, v[e]);
+                }
+                atp_workers_sync();
+                xch[half * 128 + r] = me;
+                atp_workers_sync();
+                m = fmaxf(xch[r], xch[128 + r]);
+                off = m * sc;
+                sum = 0.f;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+                    if (c0 < nkeys) tmem_ld32(trow + c0, v);
+                    sum += at_softmax_piece(v, c0, min(max(nkeys - c0, 0), 32), sc, off, st, r, xmax);
+                }
+                atp_workers_sync();
+                if (threadIdx.x == 32) flag[s] = 0;
+            }
+            atp_workers_sync();
+            xch[half * 128 + r] = sum;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P, V^T: generic-proxy writes the MMA will read
+            tc_fence_before_sync();
+            mbar_arrive(&p_ready[s]);
+            mbar_wait(&o_ready[s], par);
+            tc_fence_after_sync();
+            const float inv = 1.0f / (xch[r] + xch[128 + r]);  // (both halves stored their sums before arriving on p_ready)
+            tmem_ld32(trow + half * 32, v);
+            if (q0 + r < L) {
+                __nv_bfloat16* dst = ctx + ((size_t)b * L + q0 + r) * H + head * kAtD + half * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * q + 2 * e] * inv, v[8 * q + 2 * e + 1] * inv);
+                        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&stage_free[s]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// asp_set_option("attn_tc"): plain-bf16 attention with L <= 256 on tcgen05: 1 (default) = one tile per CTA, two CTAs per SM;
+// 2 = the persistent warp-specialised kernel (bit-identical; measured SLOWER, 2.21 vs 2.15 ms per B=32 L=256 forward,
+// profiles/r02_3h_attention_persistent_ab.txt: its eight worker warps run transposition, softmax and epilogue of a tile
+// back to back -- ~12 k clk -- where two independent CTAs overlap them); 0 = always mma.sync
+int g_attn_tc = 1;
 
 bool attention_tc_supported(const void* qkv_lo, int L, int H, int heads) {
     return g_attn_tc && qkv_lo == nullptr && L >= 1 && L <= kAtKeys && H == heads * kAtD;
@@ -274,6 +481,18 @@ int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int 
     if (attr_dev != dev) {
         ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
         attr_dev = dev;
+    }
+    if (g_attn_tc == 2) {
+        static thread_local int attr_dev2 = -1;
+        if (attr_dev2 != dev) {
+            ASP_CUDA(cudaFuncSetAttribute(attention_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtpSmem));
+            attr_dev2 = dev;
+        }
+        const int ntiles = ((L + kAtQ - 1) / kAtQ) * heads * B;
+        ASP_CUDA(launch_pdl(attention_tc_persistent_kernel, dim3(std::min(ntiles, sm_count())), dim3(kAtpThreads), (size_t)kAtpSmem,
+                            stream, cache.q, cache.kv, seq_lens, B, L, H, heads, (__nv_bfloat16*)ctx_hi));
+        ASP_LAUNCH_CHECK("attention_tc_persistent_kernel");
+        return ASP_OK;
     }
     dim3 grid((L + kAtQ - 1) / kAtQ, heads, B);
     ASP_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(kAtThreads), (size_t)kAtSmem, stream, cache.q, cache.kv, seq_lens, L, H,

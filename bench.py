@@ -305,15 +305,20 @@ def side_kernels(dev, hbm_peak):
     except Exception:
         tf_sus, tf_burst = 1400.0, 1590.0
 
-    def timeit(fn, iters=3, warm=1):
+    def timeit(fn, iters=3, warm=1, reps=1):
+        """median over `iters` of the time of `reps` back-to-back calls, per call (reps > 1 for kernels of tens of
+        microseconds, where a single launch is mostly launch gap)"""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         ts = []
         for _ in range(iters):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record(); torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
+            a.record()
+            for _r in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / reps)
         return float(np.median(ts))
 
     out = {}
@@ -341,7 +346,7 @@ def side_kernels(dev, hbm_peak):
     spans = torch.zeros(Bp, Sp, 2, dtype=torch.int32, device=dev)
     starts = torch.arange(Sp, device=dev) * 24 + 10
     spans[:, :, 0], spans[:, :, 1] = starts, starts + 24
-    t = timeit(lambda: span_mean_pool(h, spans), iters=5, warm=2)
+    t = timeit(lambda: span_mean_pool(h, spans), iters=5, warm=2, reps=10)  # 395 MB per call: nothing stays in L2
     by = Bp * Sp * 24 * DIM * 4 + Bp * Sp * DIM * 4 + Bp * DIM * 4
     out["span_pool"] = {"shape": f"B={Bp} L={Lp} S={Sp}", "ms": t, "gbs": by / t / 1e6, "frac_of_hbm": by / t / 1e6 / hbm_peak}
     del h
@@ -385,7 +390,7 @@ def side_kernels(dev, hbm_peak):
     del so
     # ---- top-k alone: 1k x 100k scores ----
     sc_all = torch.randn(NQ, NC, device=dev, generator=g)
-    t = timeit(lambda: topk(sc_all, TOPK), iters=5, warm=2)
+    t = timeit(lambda: topk(sc_all, TOPK), iters=5, warm=2, reps=5)
     out["topk"] = {"shape": f"top-{TOPK} of {NQ} x {NC}", "ms": t, "gbs": NQ * NC * 4 / t / 1e6,
                    "frac_of_hbm": NQ * NC * 4 / t / 1e6 / hbm_peak}
     del q, c, sc_all
