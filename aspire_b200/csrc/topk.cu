@@ -350,8 +350,8 @@ topk_stream_kernel(const float* __restrict__ scores, long long N, int k, int neg
                    unsigned long long* __restrict__ lists, unsigned int* __restrict__ counts, int L) {
     extern __shared__ __align__(16) float ring[];  // [kTkStages][8192]
     const int tid = threadIdx.x;
-    const long long row = blockIdx.y;
-    const int c0 = blockIdx.x * kTkSpan, c1 = min(c0 + kTkSpan, nchunks);
+    const long long row = blockIdx.x;  // rows on grid.x (up to 2^31 - 1 queries), chunk groups on grid.y
+    const int c0 = blockIdx.y * kTkSpan, c1 = min(c0 + kTkSpan, nchunks);
     const float* rowp = scores + row * N;
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
     auto staged_ok = [&](int c) {
@@ -699,7 +699,9 @@ extern "C" int asp_topk_ws(const float* scores, int Q, long long N, int k, long 
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(w);
     unsigned int* counts = reinterpret_cast<unsigned int*>(w + p.lists0);
     unsigned long long* next = reinterpret_cast<unsigned long long*>(w + p.lists0 + p.counts0);
-    topk_stream_kernel<<<dim3((nlists + kTkSpan - 1) / kTkSpan, Q), kTkThreads, kTkStages * kTkChunk * 4, stream>>>(
+    ASP_REQUIRE((nlists + kTkSpan - 1) / kTkSpan <= 65535, "asp_topk_ws: N=%lld exceeds %lld scores per row", N,
+                65535LL * kTkSpan * kTkChunk);
+    topk_stream_kernel<<<dim3(Q, (nlists + kTkSpan - 1) / kTkSpan), kTkThreads, kTkStages * kTkChunk * 4, stream>>>(
         scores, N, k, negate, base_id, nlists, lists, counts, p.L);
     ASP_LAUNCH_CHECK("topk_stream_kernel");
     const long long nl_all = (long long)Q * nlists;
