@@ -279,9 +279,16 @@ def cpu_call_patterns(ref, q, c, threads):
     # (iv) tsAspire, torch path (pair_distances.allpair_masked_dist_l2max)
     try:
         from src.learning.facetid_models import pair_distances as pd_ref
-        t0 = time.perf_counter()
-        pd_ref.allpair_masked_dist_l2max(query=tup(q.expand(POOL, -1, -1), POOL), cand=tup(c, POOL))
-        out["tsaspire_torch_l2max"] = {"pairs_per_s": POOL / (time.perf_counter() - t0), "sample": f"{POOL} pairs"}
+        # the training-side twin moves its mask to the GPU whenever one is visible (pair_distances.py:162-163); this is the
+        # CPU measurement, so it is told there is none for the duration of the call
+        avail = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False
+        try:
+            t0 = time.perf_counter()
+            pd_ref.allpair_masked_dist_l2max(query=tup(q.expand(POOL, -1, -1), POOL), cand=tup(c, POOL))
+            out["tsaspire_torch_l2max"] = {"pairs_per_s": POOL / (time.perf_counter() - t0), "sample": f"{POOL} pairs"}
+        finally:
+            torch.cuda.is_available = avail
     except Exception as e:  # the mirror may lack the training-side module
         out["tsaspire_torch_l2max"] = {"error": f"{type(e).__name__}: {e}"}
     return out
