@@ -19,6 +19,14 @@ __device__ __forceinline__ uint32_t score_key(float x) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// the same key in five instructions (chunk kernels): x + 0 folds -0 into +0, the sign mask comes from an arithmetic shift
+__device__ __forceinline__ uint32_t score_key_fast(float x, uint32_t negmask) {
+    const float y = __uint_as_float(__float_as_uint(x) ^ negmask) + 0.f;
+    const uint32_t b = __float_as_uint(y);
+    const uint32_t key = b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
+    return (y != y) ? 0u : key;
+}
+
 constexpr int kTopkThreads = 1024;
 constexpr int kTopkMaxK = 2048;
 
@@ -285,13 +293,17 @@ __device__ __forceinline__ void topk_load_keys(const float* __restrict__ src, co
             for (int c = 0; c < 4; ++c) v[c] = (e0 + c < n) ? __ldg(src + e0 + c) : 0.f;
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) key[4 * j + c] = (FULL || e0 + c < n) ? score_key(negate ? -v[c] : v[c]) : 0u;
+        for (int c = 0; c < 4; ++c) key[4 * j + c] = (FULL || e0 + c < n) ? score_key_fast(v[c], negate ? 0x80000000u : 0u) : 0u;
     }
 }
 
+// stage_f: the chunk's raw scores in shared memory (staged chunks) or NULL.  With it the few survivors of a thread are
+// emitted by a loop over the set bits of its 32-bit survivor mask (the key is rebuilt from the staged score), instead of 32
+// predicated store sequences.
 template <bool FULL>
-__device__ __forceinline__ void topk_chunk_fast(const uint32_t (&key)[kTkPer], int n, int k, unsigned int id0,
-                                                unsigned long long* __restrict__ out, unsigned int* __restrict__ count_out, int L) {
+__device__ __forceinline__ void topk_chunk_fast(const uint32_t (&key)[kTkPer], int n, int k, unsigned int id0, int negate,
+                                                const float* stage_f, unsigned long long* __restrict__ out,
+                                                unsigned int* __restrict__ count_out, int L) {
     __shared__ uint32_t wsel[kTkThreads / 32];
     __shared__ unsigned int n_ge, n_out;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -308,12 +320,13 @@ __device__ __forceinline__ void topk_chunk_fast(const uint32_t (&key)[kTkPer], i
     uint32_t tau = wsel[0];
 #pragma unroll
     for (int w = 1; w < kTkThreads / 32; ++w) tau = min(tau, wsel[w]);
-    unsigned int cge = 0;
+    uint32_t gm = 0u;  // bit i: element i of this thread is at or above the bound
 #pragma unroll
     for (int i = 0; i < kTkPer; ++i) {
         const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
-        cge += ((FULL || e < n) && key[i] >= tau);
+        if ((FULL || e < n) && key[i] >= tau) gm |= 1u << i;
     }
+    const unsigned int cge = __popc(gm);
     unsigned int wsum = cge;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
@@ -322,11 +335,22 @@ __device__ __forceinline__ void topk_chunk_fast(const uint32_t (&key)[kTkPer], i
     const unsigned int total = n_ge;
     if (total <= (unsigned)L) {
         unsigned int pos = cge ? atomicAdd(&n_out, cge) : 0u;
+        if (stage_f) {
+            const uint32_t negmask = negate ? 0x80000000u : 0u;
+            while (gm) {
+                const int i = __ffs(gm) - 1;
+                gm &= gm - 1;
+                const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
+                const uint32_t ki = score_key_fast(stage_f[e], negmask);
+                out[pos++] = ((unsigned long long)ki << 32) | (unsigned long long)(0xffffffffu - (id0 + (unsigned)e));
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < kTkPer; ++i) {
-            const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
-            if ((FULL || e < n) && key[i] >= tau)
-                out[pos++] = ((unsigned long long)key[i] << 32) | (unsigned long long)(0xffffffffu - (id0 + (unsigned)e));
+            for (int i = 0; i < kTkPer; ++i) {
+                const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
+                if (gm & (1u << i))
+                    out[pos++] = ((unsigned long long)key[i] << 32) | (unsigned long long)(0xffffffffu - (id0 + (unsigned)e));
+            }
         }
     }
     if (tid == 0) *count_out = (total <= (unsigned)L) ? total : kTkOverflow;
@@ -378,11 +402,12 @@ topk_stream_kernel(const float* __restrict__ scores, long long N, int k, int neg
         if (staged_ok(c)) {
             topk_load_keys<true, true>(nullptr, reinterpret_cast<const float4*>(ring + (size_t)(c % kTkStages) * kTkChunk), kTkChunk,
                                        negate, tid, key);
-            topk_chunk_fast<true>(key, kTkChunk, k, (unsigned)(base_id + start), out, cnt, L);
+            topk_chunk_fast<true>(key, kTkChunk, k, (unsigned)(base_id + start), negate, ring + (size_t)(c % kTkStages) * kTkChunk, out,
+                                  cnt, L);
         } else {
             const int n = (int)min((long long)kTkChunk, N - start);
             topk_load_keys<false, false>(rowp + start, nullptr, n, negate, tid, key);
-            topk_chunk_fast<false>(key, n, k, (unsigned)(base_id + start), out, cnt, L);
+            topk_chunk_fast<false>(key, n, k, (unsigned)(base_id + start), negate, nullptr, out, cnt, L);
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -495,6 +520,10 @@ __device__ __forceinline__ unsigned long long warp_sort_desc64(unsigned long lon
 }
 
 constexpr int kTkSel = 1024;  // survivors the merge sorts after its selection step
+#ifndef ASP_TK_MERGE_THREADS
+#define ASP_TK_MERGE_THREADS 256
+#endif
+constexpr int kTkMergeThreads = ASP_TK_MERGE_THREADS;  // 256: cheap block barriers in the 45-stage sort, three CTAs per SM
 
 // Merge: CTA (q, grp) gathers lists [grp * group, min(nlists, (grp + 1) * group)) of query q -- list l starts at
 // lists[l * l_stride + q * q_stride] and holds counts[q * nlists + l] entries (counts == NULL: exactly k, zeros = fillers)
@@ -515,22 +544,26 @@ topk_merge_packed_kernel(const unsigned long long* __restrict__ lists, const uns
     const int q = blockIdx.x, l0 = blockIdx.y * group, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     const int nl = min(group, nlists - l0);
+    // list lengths: loaded in parallel (one dependent global load per CTA instead of nl), prefix by one thread from shared memory
+    if ((int)threadIdx.x < nl) off_s[threadIdx.x + 1] = counts ? (int)counts[(size_t)q * nlists + l0 + threadIdx.x] : k;
+    __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
+        off_s[0] = 0;
         for (int l = 0; l < nl; ++l) {
-            off_s[l] = run;
-            run += counts ? (int)counts[(size_t)q * nlists + l0 + l] : k;
+            run += off_s[l + 1];
+            off_s[l + 1] = min(run, cap);
         }
-        off_s[nl] = min(run, cap);
         n_ge = 0u;
         n_out = 0u;
     }
     __syncthreads();
     const int total = off_s[nl];
-    for (int l = 0; l < nl; ++l) {
-        const int o = off_s[l], c = min(off_s[l + 1], total) - o;
-        const unsigned long long* srcl = lists + (size_t)(l0 + l) * l_stride + (size_t)q * q_stride;
-        for (int i = threadIdx.x; i < c; i += blockDim.x) mk[o + i] = srcl[i];
+    // gather: one flat loop, every element's load independent of the others
+    for (int j = threadIdx.x; j < total; j += blockDim.x) {
+        int l = 0;
+        while (l + 1 < nl && j >= off_s[l + 1]) ++l;
+        mk[j] = lists[(size_t)(l0 + l) * l_stride + (size_t)q * q_stride + (j - off_s[l])];
     }
     __syncthreads();
     unsigned long long* sorted = mk;
@@ -715,7 +748,7 @@ extern "C" int asp_topk_ws(const float* scores, int Q, long long N, int k, long 
         const bool last = nlists <= group;
         const int ngroups = (nlists + group - 1) / group;
         const size_t cap_keys = std::min<size_t>((size_t)next_pow2(std::min(nlists, group) * stride), kTkMergeCap);
-        topk_merge_packed_kernel<<<dim3(Q, ngroups), 1024, cap_keys * 8, stream>>>(
+        topk_merge_packed_kernel<<<dim3(Q, ngroups), kTkMergeThreads, cap_keys * 8, stream>>>(
             lists, cnt, nlists, (size_t)stride, (size_t)nlists * stride, k, group, last ? out_scores : nullptr,
             last ? out_ids : nullptr, last ? out_packed : next, (int)cap_keys);
         ASP_LAUNCH_CHECK("topk_merge_packed_kernel");
@@ -744,7 +777,7 @@ extern "C" int asp_topk_merge_packed(const unsigned long long* gathered, int R, 
     if (cap_keys * 8 > 48 * 1024)
         ASP_CUDA(cudaFuncSetAttribute(topk_merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     // gathered[r][q][k]: list r of query q
-    topk_merge_packed_kernel<<<Q, 1024, cap_keys * 8, (cudaStream_t)stream>>>(gathered, nullptr, R, (size_t)Q * k, (size_t)k, k, R,
+    topk_merge_packed_kernel<<<Q, kTkMergeThreads, cap_keys * 8, (cudaStream_t)stream>>>(gathered, nullptr, R, (size_t)Q * k, (size_t)k, k, R,
                                                                              out_scores, out_ids, nullptr, (int)cap_keys);
     ASP_LAUNCH_CHECK("topk_merge_packed_kernel");
     return ASP_OK;
