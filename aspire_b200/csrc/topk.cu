@@ -356,6 +356,64 @@ __device__ __forceinline__ void topk_chunk_fast(const uint32_t (&key)[kTkPer], i
     if (tid == 0) *count_out = (total <= (unsigned)L) ? total : kTkOverflow;
 }
 
+// The chunk step for STAGED chunks (8192 scores in shared memory), in the float domain: thread maxima and the survivor
+// test are one FMNMX and one FSETP per score -- only the 8 x 32 thread maxima and the ~190 survivors are turned into keys.
+// NEG: rank by -score.  Same bound, same survivors, same lists as topk_chunk_fast on the keys (v >= key_score(tau) <=>
+// score_key(v) >= tau for every non-NaN v; NaN never survives unless the bound is 0, i.e. everything does).
+template <bool NEG>
+__device__ __forceinline__ void topk_chunk_staged(const float* stage_f, int k, unsigned int id0, unsigned long long* __restrict__ out,
+                                                  unsigned int* __restrict__ count_out, int L) {
+    __shared__ uint32_t wsel[kTkThreads / 32];
+    __shared__ unsigned int n_ge, n_out;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4* st4 = reinterpret_cast<const float4*>(stage_f);
+    float v[kTkPer];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 f = st4[tid + kTkThreads * j];
+        v[4 * j] = NEG ? -f.x : f.x; v[4 * j + 1] = NEG ? -f.y : f.y; v[4 * j + 2] = NEG ? -f.z : f.z; v[4 * j + 3] = NEG ? -f.w : f.w;
+    }
+    float mf = v[0];
+#pragma unroll
+    for (int i = 1; i < kTkPer; ++i) mf = fmaxf(mf, v[i]);  // NaNs are ignored unless every score is one
+    const uint32_t m = score_key_fast(mf, 0u);
+    __syncthreads();  // the previous chunk of this CTA is done with wsel / n_ge / n_out
+    if (tid == 0) { n_ge = 0u; n_out = 0u; }
+    const int jsel = (min(k, kTkChunk) + 7) / 8;
+    const uint32_t sorted = warp_sort_desc(m, lane);
+    if (lane == min(jsel, 32) - 1) wsel[warp] = sorted;
+    __syncthreads();
+    uint32_t tau = wsel[0];
+#pragma unroll
+    for (int w = 1; w < kTkThreads / 32; ++w) tau = min(tau, wsel[w]);
+    uint32_t gm = 0xffffffffu;
+    if (tau != 0u) {
+        const float tf = key_score(tau);
+        gm = 0u;
+#pragma unroll
+        for (int i = 0; i < kTkPer; ++i)
+            if (v[i] >= tf) gm |= 1u << i;
+    }
+    const unsigned int cge = __popc(gm);
+    unsigned int wsum = cge;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if (lane == 0 && wsum) atomicAdd(&n_ge, wsum);
+    __syncthreads();
+    const unsigned int total = n_ge;
+    if (total <= (unsigned)L) {
+        unsigned int pos = cge ? atomicAdd(&n_out, cge) : 0u;
+        while (gm) {
+            const int i = __ffs(gm) - 1;
+            gm &= gm - 1;
+            const int e = 4 * (tid + kTkThreads * (i >> 2)) + (i & 3);
+            const uint32_t ki = score_key_fast(stage_f[e], NEG ? 0x80000000u : 0u);
+            out[pos++] = ((unsigned long long)ki << 32) | (unsigned long long)(0xffffffffu - (id0 + (unsigned)e));
+        }
+    }
+    if (tid == 0) *count_out = (total <= (unsigned)L) ? total : kTkOverflow;
+}
+
 // Streaming kernel: CTA (x, row) walks `span` consecutive chunks of one row.  Whole, 16-byte-aligned chunks come in through
 // a 3-stage cp.async ring in shared memory (each thread copies exactly the 128 bytes it will read back, so the ring needs
 // no block-wide synchronisation; two chunks = 64 KB are in flight per CTA while a third is being selected from, two CTAs
@@ -398,13 +456,12 @@ topk_stream_kernel(const float* __restrict__ scores, long long N, int k, int neg
         const long long start = (long long)c * kTkChunk;
         unsigned long long* out = lists + ((size_t)row * nchunks + c) * L;
         unsigned int* cnt = counts + (size_t)row * nchunks + c;
-        uint32_t key[kTkPer];
         if (staged_ok(c)) {
-            topk_load_keys<true, true>(nullptr, reinterpret_cast<const float4*>(ring + (size_t)(c % kTkStages) * kTkChunk), kTkChunk,
-                                       negate, tid, key);
-            topk_chunk_fast<true>(key, kTkChunk, k, (unsigned)(base_id + start), negate, ring + (size_t)(c % kTkStages) * kTkChunk, out,
-                                  cnt, L);
+            const float* stage_f = ring + (size_t)(c % kTkStages) * kTkChunk;
+            if (negate) topk_chunk_staged<true>(stage_f, k, (unsigned)(base_id + start), out, cnt, L);
+            else topk_chunk_staged<false>(stage_f, k, (unsigned)(base_id + start), out, cnt, L);
         } else {
+            uint32_t key[kTkPer];
             const int n = (int)min((long long)kTkChunk, N - start);
             topk_load_keys<false, false>(rowp + start, nullptr, n, negate, tid, key);
             topk_chunk_fast<false>(key, n, k, (unsigned)(base_id + start), negate, nullptr, out, cnt, L);
