@@ -443,3 +443,46 @@ def test_allpairs_kernel_empty_documents_and_single_query():
             one = ot_scores(q[i:i + 1].contiguous(), ql[i:i + 1].cuda(), c, cl.cuda(), eps, broadcast_query=True)["dual"]
             assert rel_err(got[i].cpu().numpy(), one.cpu().numpy()).max() <= 1e-5
         assert (got[0] == 0).all() and (got[:, -1] == 0).all()
+
+
+def _structured(gen, n, S, D):
+    """SURVEY 8d "structured" distribution: low-rank signal + noise -> wider spread of distances, sharper plans."""
+    W = torch.randn(32, D, generator=torch.Generator().manual_seed(99)) / np.sqrt(32) * 4
+    return (0.3 * torch.randn(n, S, 32, generator=gen)) @ W + 0.05 * torch.randn(n, S, D, generator=gen)
+
+
+def test_tensor_core_gram_kernels_on_the_structured_distribution():
+    """The two kernels whose Gram tiles come from bf16 hi/lo tensor-core products (ot_allpairs.cu; ot_fused_tc.cu) on the
+    structured distribution -- distances from ~1 to ~40, near-degenerate plans, the regime where a cost error shows most:
+    OT distances within 1e-4 relative of the CPU oracle, and of the fp32-FMA kernel."""
+    from aspire_b200 import ot_scores, ot_scores_allpairs, epsilon_schedule, _abi
+    g = torch.Generator().manual_seed(8)
+    NQ, NC, S, D = 12, 900, 10, 768
+    q, c = _structured(g, NQ, S, D), _structured(g, NC, S, D)
+    ql = torch.randint(3, S + 1, (NQ,), generator=g).int()
+    cl = torch.randint(3, S + 1, (NC,), generator=g).int()
+    q = q * (torch.arange(S)[None, :] < ql[:, None])[:, :, None]
+    c = c * (torch.arange(S)[None, :] < cl[:, None])[:, :, None]
+    diam = float(gr.max_diameter(q.reshape(-1, D), c.reshape(-1, D)))
+    eps = epsilon_schedule(diam, 0.05, 0.9)
+    got = ot_scores_allpairs(q.cuda(), ql.cuda(), c.cuda(), cl.cuda(), eps).cpu().numpy()
+    for i in (0, 5, 11):
+        ref = ar.ot_distance(q[i:i + 1].expand(NC, -1, -1), [int(ql[i])] * NC, c, cl.tolist(), diameter=diam).numpy()
+        assert rel_err(got[i], ref).max() <= 1e-4, (i, rel_err(got[i], ref).max())
+        fma = ot_scores(q[i:i + 1].cuda(), ql[i:i + 1].cuda(), c.cuda(), cl.cuda(), eps, broadcast_query=True)["dual"].cpu().numpy()
+        assert rel_err(got[i], fma).max() <= 2e-5
+    # the pool prototype: one structured query against 9600 structured candidates
+    B = 9600
+    cb = _structured(g, B, S, D)
+    clb = torch.full((B,), S).int()
+    res = {}
+    for mode in (1, 0):
+        _abi.set_option("ot_fused_tc", mode)
+        try:
+            res[mode] = ot_scores(q[:1].cuda(), torch.tensor([S]).int().cuda(), cb.cuda(), clb.cuda(), eps, broadcast_query=True)["dual"].cpu().numpy()
+        finally:
+            _abi.set_option("ot_fused_tc", 0)
+    assert rel_err(res[1], res[0]).max() <= 5e-5   # three split terms on truncated halves: 2^-17 per element (measured 2.1e-5)
+    sub = np.arange(0, B, 40)
+    ref = ar.ot_distance(q[:1].expand(len(sub), -1, -1), [S] * len(sub), cb[sub], [S] * len(sub), diameter=diam).numpy()
+    assert rel_err(res[1][sub], ref).max() <= 1e-4
