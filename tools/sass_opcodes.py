@@ -8,7 +8,7 @@ import sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else "aspire_b200/libaspire_b200.so"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEYS = ["UTCHMMA", "UTMALDG", "UTCBAR", "LDTM", "STTM", "LDGSTS", "HMMA", "FFMA2", "FADD2", "MUFU", "SYNCS", "USETMAXREG"]
+KEYS = ["UTCHMMA", "UTMALDG", "UBLKCP", "UTCBAR", "LDTM", "STTM", "LDGSTS", "HMMA", "FFMA2", "FADD2", "MUFU", "SYNCS", "USETMAXREG"]
 cur, hist = None, collections.OrderedDict()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
