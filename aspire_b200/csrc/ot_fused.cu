@@ -36,6 +36,14 @@ constexpr int kFT = 10;        // max sentences per document on the fused path
 constexpr int kHR = kFT / 2;   // query rows per half-warp
 constexpr int kCostLd = 101;   // floats per pair in a padded cost tile (default of phase1's LD)
 constexpr int kRedVals = 64;   // 50 dot products + 5 candidate norms, padded for the 16-lane transpose-reduce
+#ifndef ASP_V7_TTABLE
+#define ASP_V7_TTABLE 1  // 1: the solvers read log2e / eps from a per-CTA table instead of dividing every step
+#endif
+#if ASP_V7_TTABLE
+#define ASP_V7_TSCHED (eps_s + ASP_MAX_EPS)
+#else
+#define ASP_V7_TSCHED nullptr
+#endif
 #ifndef ASP_V7_RING
 #define ASP_V7_RING 5
 #endif
@@ -364,11 +372,11 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 // (inlined into the Sinkhorn branch: ptxas must see them under that branch's setmaxnreg budget)
 __device__ __forceinline__ void v7_phase2(float* Cs, int ql, int cl, int b, int Sq, int Sc, const float* eps_s, int n_eps,
                                        float inv_temp, const OtOut* out) {
-    solve_pair_thread_stream<kFT, kFT, false>(Cs, ql, cl, b, Sq, Sc, eps_s, n_eps, inv_temp, *out);
+    solve_pair_thread_stream<kFT, kFT, false>(Cs, ql, cl, b, Sq, Sc, eps_s, n_eps, inv_temp, *out, ASP_V7_TSCHED);
 }
 __device__ __forceinline__ void v7_phase2_full(float* Cs, int b, const float* eps_s, int n_eps, float inv_temp,
                                             const OtOut* out) {
-    solve_pair_thread_stream<kFT, kFT, true>(Cs, kFT, kFT, b, kFT, kFT, eps_s, n_eps, inv_temp, *out);
+    solve_pair_thread_stream<kFT, kFT, true>(Cs, kFT, kFT, b, kFT, kFT, eps_s, n_eps, inv_temp, *out, ASP_V7_TSCHED);
 }
 
 // ROWS: instantiation for launches of at most one pair per Gram warp (a single query against a <= 1k pool): the
@@ -378,14 +386,17 @@ template <int DT, bool ROWS>
 __global__ void __launch_bounds__(kV7Warps * 32, 1)
 ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
     extern __shared__ float smem[];
-    __shared__ float eps_s[ASP_MAX_EPS];
+    __shared__ float eps_s[2 * ASP_MAX_EPS];  // eps[k], then log2e / eps[k] (the per-step division, done once here)
     __shared__ OtOut out_s;
     __shared__ int lut_s[128];
     __shared__ uint32_t tmem_slot;
     __shared__ uint64_t full_bar[4][kV7Slots], empty_bar[4][kV7Slots];
     __shared__ int meta_s[4][kV7Slots][4];   // base, npairs (0 = end of a Gram warp's stream), full_tile
     __shared__ unsigned int ticket_s[4];
-    for (int k = threadIdx.x; k < sched.n; k += blockDim.x) eps_s[k] = sched.eps[k];
+    for (int k = threadIdx.x; k < sched.n; k += blockDim.x) {
+        eps_s[k] = sched.eps[k];
+        eps_s[ASP_MAX_EPS + k] = kLog2e / sched.eps[k];
+    }
     if (threadIdx.x == 0) out_s = out;
     if (threadIdx.x < 4) ticket_s[threadIdx.x] = 0u;
     {
@@ -499,7 +510,7 @@ ot_fused_v7_kernel(const FusedArgs a, const EpsSched sched, const OtOut out) {
                 float* scratch = smem + 4 * kV7Slots * kV7SlotFloats + kV7Gram * kV7GramSmem + w * kV7Scratch +
                                  (active ? p : 0) * kV7Ld;
                 solved = solve_pairs_rows<kFT>(Cp, ql, cl, b, a.Sq, a.Sc, active, min(p, kV7RowSlots - 1) * kFT, r, scratch,
-                                               eps_s, sched.n, a.inv_temp, out_s);
+                                               eps_s, sched.n, a.inv_temp, out_s, ASP_V7_TSCHED);
             }
             if (!solved && l16 < my_np) {
                 float* Cs = slots + sl_mine * kV7SlotFloats + l16 * kV7Ld;

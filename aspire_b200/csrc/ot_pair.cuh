@@ -332,11 +332,11 @@ static __device__ __noinline__ void stabilised_step_mem(const float* Cs, int TQ,
 // issue, keeps POLY = false.
 template <int TQ, int TC, bool FULL, bool POLY = false>
 __device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, const float* Cs, int ql_in, int cl_in, float eps,
-                                                     float weight) {
+                                                     float t, float weight) {
+    // t = log2e / eps: from the caller's per-step table when it has one (saves the division per step), else computed there
     static_assert((TQ * TC) % 4 == 0 && TC % 2 == 0, "tile is read as float4 chunks holding whole column pairs");
     constexpr int TP = TC / 2;
     const int ql = FULL ? TQ : ql_in, cl = FULL ? TC : cl_in;
-    const float t = kLog2e / eps;
     const float scale = weight * eps * kLn2;
     const float2 t2 = dup2(t), nt2 = dup2(-t), nscale2 = dup2(-scale);
     float2 v[TP], S[TP];
@@ -421,7 +421,8 @@ __device__ __forceinline__ void sinkhorn_step_stream(PairStateS<TQ, TC>& st, con
 template <int TQ, int TC, bool FULL, bool POLY = false>
 __device__ __forceinline__ void solve_pair_thread_stream(float* Cs, int ql_in, int cl_in, int b, int Sq_in, int Sc_in,
                                                          const float* eps_sched, int n_eps, float inv_temp,
-                                                         const OtOut& out) {
+                                                         const OtOut& out, const float* t_sched = nullptr) {
+    // t_sched (optional): log2e / eps_sched[k], precomputed once per CTA with the same IEEE division the step would do
     constexpr int TP = TC / 2;
     const int ql = FULL ? TQ : ql_in, cl = FULL ? TC : cl_in, Sq = FULL ? TQ : Sq_in, Sc = FULL ? TC : Sc_in;
     PairStateS<TQ, TC> st;
@@ -484,7 +485,9 @@ __device__ __forceinline__ void solve_pair_thread_stream(float* Cs, int ql_in, i
 #pragma unroll 1
         for (int k = -1; k <= n_eps; ++k) {
             const bool plain = (k < 0) | (k == n_eps);
-            sinkhorn_step_stream<TQ, TC, FULL, POLY>(st, Cs, ql, cl, eps_sched[min(max(k, 0), n_eps - 1)], plain ? 1.0f : 0.5f);
+            const int ks = min(max(k, 0), n_eps - 1);
+            const float eps = eps_sched[ks];
+            sinkhorn_step_stream<TQ, TC, FULL, POLY>(st, Cs, ql, cl, eps, t_sched ? t_sched[ks] : kLog2e / eps, plain ? 1.0f : 0.5f);
         }
     }
 
@@ -556,7 +559,7 @@ namespace asp {
 template <int T>  // tile is T x T (T = 10), cost stride T
 __device__ __forceinline__ bool solve_pairs_rows(const float* Cs_pair, int ql, int cl, int b, int Sq, int Sc, bool active,
                                                  int group_base, int r, float* scratch, const float* eps_sched, int n_eps,
-                                                 float inv_temp, const OtOut& out) {
+                                                 float inv_temp, const OtOut& out, const float* t_sched = nullptr) {
     // `active`: this lane belongs to a pair slot that holds a pair; group_base = first lane of the slot; r = lane - base.
     // scratch: T*T floats per slot (this slot's block), visible to the slot's ten lanes.
     const unsigned full = 0xffffffffu;
@@ -598,8 +601,9 @@ __device__ __forceinline__ bool solve_pairs_rows(const float* Cs_pair, int ql, i
     if (__any_sync(full, active && ql > 0 && cl > 0)) {
 #pragma unroll 1
         for (int k = -1; k <= n_eps; ++k) {
-            const float eps = eps_sched[min(max(k, 0), n_eps - 1)];
-            const float t = kLog2e / eps;
+            const int ks = min(max(k, 0), n_eps - 1);
+            const float eps = eps_sched[ks];
+            const float t = t_sched ? t_sched[ks] : kLog2e / eps;
             const bool plain = (k < 0) | (k == n_eps);
             const float scale = (plain ? 1.0f : 0.5f) * eps * kLn2;
             const float u = fmaf(f, t, la), v_own = fmaf(g, t, lb);

@@ -36,16 +36,19 @@ def main():
             from aspire_b200 import _abi
             k, v = arg[6:].split("=")
             _abi.set_option(k, int(v))
+    shapes = [tuple(int(v) for v in a[8:].split(",")) for a in sys.argv[1:] if a.startswith("--shape=")]  # --shape=B,L
+    precs = [a[7:] for a in sys.argv[1:] if a.startswith("--prec=")] or ["bf16", "bf16x3"]
     model = seeded_bert(seed=0, num_hidden_layers=12)
     enc = B200BertEncoder(model)
     hf32 = model.cuda().float()
-    for B, L in ([(32, 256)] if quick else [(8, 256), (32, 256), (32, 512), (128, 256)]):
+    quick = quick or bool(shapes)
+    for B, L in (shapes or ([(32, 256)] if quick else [(8, 256), (32, 256), (32, 512), (128, 256)])):
         ids = torch.randint(1000, 31000, (B, L)).cuda()
         lens = torch.full((B,), L, dtype=torch.int32).cuda()
         mask = torch.ones((B, L), dtype=torch.long).cuda()
         flops = B * L * (2 * 85.05e6 + 12 * 4 * L * 768)
         out = {}
-        for prec in ("bf16", "bf16x3"):
+        for prec in precs:
             out[prec] = timeit(lambda: enc.forward(ids, lens, precision=prec))
         if not quick:
             with torch.no_grad():
