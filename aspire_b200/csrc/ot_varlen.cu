@@ -39,6 +39,9 @@
 // sleep between non-blocking barrier tests; 0 = mbarrier.try_wait with a suspend hint.  The hinted form wakes on every
 // barrier event of the CTA (measured: one retry per ~17 ns per waiting warp, 45 % of the kernel's issued instructions),
 // which takes issue slots from the Gram warp of the same scheduler; a plain sleep does not.
+#ifndef ASP_VL_QUAD_MAP
+#define ASP_VL_QUAD_MAP 1
+#endif
 #ifndef ASP_VL_IDLE_SINK
 #define ASP_VL_IDLE_SINK 0
 #endif
@@ -457,7 +460,16 @@ ot_varlen_kernel(const VlArgs a, const EpsSched sched, const OtOut out) {
         const int g = warp;
         const uint32_t ring_s = vl_smem_u32(smem + (size_t)g * kWsRingFloats);
         float* nrm = gram_misc + g * 64;
-        const int li = lane & 7, lj = lane >> 3;     // lane grid: 8 query-row groups x 4 candidate-row groups
+        // lane grid: 8 query-row groups x 4 candidate-row groups.  Which lanes share an address decides what a 128-bit
+        // broadcast load costs: 2 passes of the shared-memory pipe when every aligned group of four lanes holds at most
+        // two distinct addresses, 4 otherwise (tools/ubench3.cu, profiles/r02_3q_lds_wavefronts.txt).  li takes lane bits
+        // 0, 2, 3 and lj bits 1, 4: a quad then sees two query rows and two candidate rows (li = lane & 7 made every
+        // query-side load a 4-pass one).
+#if ASP_VL_QUAD_MAP
+        const int li = (lane & 1) | ((lane >> 1) & 6), lj = ((lane >> 1) & 1) | ((lane >> 3) & 2);
+#else
+        const int li = lane & 7, lj = lane >> 3;
+#endif
         const int r0 = lane >> 3, chunk = lane & 7;  // norm duty: the pieces the producer lane of the same index copied
         int off = 0, vpos = 0, n = 0, popped = 0, t = 0;
         for (;;) {
