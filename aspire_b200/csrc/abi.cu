@@ -74,8 +74,13 @@ extern "C" int asp_set_option(const char* key, int value) {
         asp::g_span_tma = value != 0;
         return ASP_OK;
     }
-    if (strcmp(key, "attn_tc") == 0) {  // developer switch: 1 tcgen05 attention (plain bf16, L <= 256), 0 mma.sync attention
-        ASP_REQUIRE(value >= 0 && value <= 2, "asp_set_option: attn_tc must be 0, 1 or 2");
+    if (strcmp(key, "ln_on_read") == 0) {  // developer switch: 1 inner LayerNorms leave statistics, the next residual epilogue normalises
+        ASP_REQUIRE(value == 0 || value == 1, "asp_set_option: ln_on_read must be 0 or 1");
+        asp::g_ln_on_read = value;
+        return ASP_OK;
+    }
+    if (strcmp(key, "attn_tc") == 0) {  // developer switch: tcgen05 attention (plain bf16, L <= 256) 3 / 1 / 2 (see attention_tc.cu), 0 mma.sync attention
+        ASP_REQUIRE(value >= 0 && value <= 3, "asp_set_option: attn_tc must be 0..3");
         asp::g_attn_tc = value;
         return ASP_OK;
     }

@@ -6,8 +6,9 @@
 //   TMA      Q [128 x 64], K [256 x 64], V [256 x 64] boxes straight out of the fused QKV activation [tokens, 3 * hidden]
 //            (128-byte rows, 128B swizzle); rows past the batch are zero-filled, keys past the document are masked
 //   MMA 1    S[128 x 256] = Q K^T: 4 tcgen05.mma (M 128, N 256, K 16), fp32 in 256 TMEM columns
-//   meanwhile the four warps transpose V into V^T [64 x 256] (the B operand of P V must be K-major; 8 x 8 blocks through
-//            ldmatrix.trans / stmatrix, swizzled both sides)
+//   V        is the B operand of P V as it arrived: [key][d] rows of 128 bytes with the 128B swizzle are the canonical
+//            MN-major SW128 layout (8-key groups 1 KB apart), selected by bit 16 of the instruction descriptor.  (The first
+//            version transposed V into a K-major V^T with ldmatrix.trans / stmatrix while MMA 1 ran -- kept as attn_tc=1.)
 //   softmax  one thread per query row: row max, then p = 2^((s - max) / 8 * log2 e) straight from TMEM (tcgen05.ld, 32
 //            columns at a time), row sum in fp32, P as bf16 into shared memory in the A-operand layout (it reuses the
 //            Q / K / V staging, which MMA 1 and the transposition are done with)
@@ -91,6 +92,10 @@ __device__ __forceinline__ float at_softmax_piece(const float (&v)[32], int c0, 
     return sum;
 }
 
+// VMN: V is consumed as an MN-major B operand straight from its TMA tile ([key][d], 128-byte rows, 128B swizzle: the canonical
+// MN-major SW128 layout with 8-key groups 1024 bytes apart), so the V -> V^T pass does not exist.  The tile then lands where
+// V^T would have been (P overwrites Q, K and the unused gap).
+template <bool VMN>
 __global__ void __launch_bounds__(kAtThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tkv,
                     const int32_t* __restrict__ seq_lens, int L, int H, __nv_bfloat16* __restrict__ ctx) {
@@ -125,7 +130,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         mbar_arrive_expect_tx(&bar_load, kAtQBytes + 2 * kAtKBytes);
         tma_load_2d(smem, &tq, &bar_load, head * kAtD, b * L + q0);
         tma_load_2d(smem + kAtOffK, &tkv, &bar_load, H + head * kAtD, b * L);
-        tma_load_2d(smem + kAtOffV, &tkv, &bar_load, 2 * H + head * kAtD, b * L);
+        tma_load_2d(smem + (VMN ? kAtOffVt : kAtOffV), &tkv, &bar_load, 2 * H + head * kAtD, b * L);
     }
     mbar_wait(&bar_load, 0);
     if (threadIdx.x == 0) {
@@ -138,7 +143,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     }
     __syncwarp();
     // ---- V -> V^T while MMA 1 runs: 8 x 8 blocks, four at a time (same 8 keys, four 8-wide slices of d) ----
-    {
+    if (!VMN) {
         const int mtx = lane >> 3, i = lane & 7;  // ldmatrix / stmatrix: lanes 8m..8m+7 address the rows of matrix m
 #pragma unroll 4
         for (int t = warp; t < 2 * (kAtKeys / 8); t += kAtThreads / 32) {
@@ -210,12 +215,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     __syncthreads();
     if (threadIdx.x == 0) {
         tc_fence_after_sync();
-        constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtD);
+        constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtD) | (VMN ? (1u << 16) : 0u);  // bit 16: B is MN-major
 #pragma unroll
         for (int kb = 0; kb < kAtKeys / 64; ++kb) {
-            const uint64_t pd = umma_desc_sw128(sbase + kb * kAtPBlock), vd = umma_desc_sw128(sbase + kAtOffVt + kb * kAtVtBlock);
+            const uint64_t pd = umma_desc_sw128(sbase + kb * kAtPBlock);
+            // K-major V^T: 64-key blocks of [d][key] rows, 32 bytes per K = 16 step; MN-major V: 16 keys = 16 rows = 2 KB per step
+            const uint64_t vd = umma_desc_sw128(sbase + kAtOffVt + (VMN ? kb * 64 * 128 : kb * kAtVtBlock));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, pd + 2 * kk, vd + 2 * kk, idesc, (kb | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(tmem_base, pd + 2 * kk, vd + (VMN ? (2048 >> 4) * kk : 2 * kk), idesc, (kb | kk) != 0);
         }
         umma_commit(&bar_o);
     }
@@ -447,11 +455,13 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tq, const __g
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// asp_set_option("attn_tc"): plain-bf16 attention with L <= 256 on tcgen05: 1 (default) = one tile per CTA, two CTAs per SM;
-// 2 = the persistent warp-specialised kernel (bit-identical; measured SLOWER, 2.21 vs 2.15 ms per B=32 L=256 forward,
-// profiles/r02_3h_attention_persistent_ab.txt: its eight worker warps run transposition, softmax and epilogue of a tile
-// back to back -- ~12 k clk -- where two independent CTAs overlap them); 0 = always mma.sync
-int g_attn_tc = 1;
+// asp_set_option("attn_tc"): plain-bf16 attention with L <= 256 on tcgen05: 3 (default) = one tile per CTA, two CTAs per SM, V
+// consumed as an MN-major operand straight from its TMA tile; 1 = the same with V transposed in shared memory first
+// (bit-identical, ~1 % of a forward slower: profiles/r02_3t_*); 2 = the persistent warp-specialised kernel (bit-identical;
+// measured SLOWER, 2.21 vs 2.15 ms per B=32 L=256 forward, profiles/r02_3h_attention_persistent_ab.txt: its eight worker
+// warps run transposition, softmax and epilogue of a tile back to back -- ~12 k clk -- where two independent CTAs
+// overlap them); 0 = always mma.sync
+int g_attn_tc = 3;
 
 bool attention_tc_supported(const void* qkv_lo, int L, int H, int heads) {
     return g_attn_tc && qkv_lo == nullptr && L >= 1 && L <= kAtKeys && H == heads * kAtD;
@@ -479,7 +489,8 @@ int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int 
     int dev = 0;
     ASP_CUDA(cudaGetDevice(&dev));
     if (attr_dev != dev) {
-        ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+        ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+        ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
         attr_dev = dev;
     }
     if (g_attn_tc == 2) {
@@ -495,8 +506,12 @@ int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int 
         return ASP_OK;
     }
     dim3 grid((L + kAtQ - 1) / kAtQ, heads, B);
-    ASP_CUDA(launch_pdl(attention_tc_kernel, grid, dim3(kAtThreads), (size_t)kAtSmem, stream, cache.q, cache.kv, seq_lens, L, H,
-                        (__nv_bfloat16*)ctx_hi));
+    if (g_attn_tc == 3)
+        ASP_CUDA(launch_pdl(attention_tc_kernel<true>, grid, dim3(kAtThreads), (size_t)kAtSmem, stream, cache.q, cache.kv, seq_lens,
+                            L, H, (__nv_bfloat16*)ctx_hi));
+    else
+        ASP_CUDA(launch_pdl(attention_tc_kernel<false>, grid, dim3(kAtThreads), (size_t)kAtSmem, stream, cache.q, cache.kv, seq_lens,
+                            L, H, (__nv_bfloat16*)ctx_hi));
     ASP_LAUNCH_CHECK("attention_tc_kernel");
     return ASP_OK;
 }

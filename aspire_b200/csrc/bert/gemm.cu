@@ -41,7 +41,18 @@ struct GemmArgs {
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     float* out_f32;
+    // LayerNorm on read (EPI_RESID_F32 only): `residual` then holds the PRE-LayerNorm rows and the epilogue adds
+    // (r - mean) * rstd * gamma + beta -- the expression ln_row_store evaluates -- from the per-row (mean, rstd) the
+    // LayerNorm kernel left behind, so the normalised fp32 tensor is never written to or read from memory.
+    const float2* ln_stats;
+    const float* ln_gamma;
+    const float* ln_beta;
 };
+
+__device__ __forceinline__ float4 ln_on_read(const float4& r, const float2& st, const float4& g, const float4& b) {
+    return make_float4((r.x - st.x) * st.y * g.x + b.x, (r.y - st.x) * st.y * g.y + b.y, (r.z - st.x) * st.y * g.z + b.z,
+                       (r.w - st.x) * st.y * g.w + b.w);
+}
 
 constexpr int kGemmStages = 3;
 constexpr int kBlockM = 128;
@@ -107,7 +118,10 @@ __device__ __forceinline__ void epilogue_store32(const GemmArgs& g, float (&v)[3
         for (int i = 0; i < 32; i += 4) {
             float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             if (EPI == EPI_RESID_F32) {
-                const float4 rr = __ldg(r + i / 4);
+                float4 rr = __ldg(r + i / 4);
+                if (g.ln_stats)
+                    rr = ln_on_read(rr, __ldg(g.ln_stats + off / g.N), __ldg(reinterpret_cast<const float4*>(g.ln_gamma + col + i)),
+                                    __ldg(reinterpret_cast<const float4*>(g.ln_beta + col + i)));
                 x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
             }
             o[i / 4] = x;
@@ -255,7 +269,12 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
                 if (row < g.M) {
                     const size_t off = (size_t)row * g.N + col + 16 * h + 4 * c_sub;
                     if (EPI == EPI_RESID_F32) {
-                        const float4 rr = __ldg(reinterpret_cast<const float4*>(g.residual + off));
+                        float4 rr = __ldg(reinterpret_cast<const float4*>(g.residual + off));
+                        if (g.ln_stats) {  // uniform
+                            const int c4 = col + 16 * h + 4 * c_sub;
+                            rr = ln_on_read(rr, __ldg(g.ln_stats + row), __ldg(reinterpret_cast<const float4*>(g.ln_gamma + c4)),
+                                            __ldg(reinterpret_cast<const float4*>(g.ln_beta + c4)));
+                        }
                         x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
                     }
                     *reinterpret_cast<float4*>(g.out_f32 + off) = x;
@@ -842,8 +861,11 @@ int g_pdl = 1;
 
 int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                  const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo, float* out_f32,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const LnOnRead* ln) {
     constexpr int BN = 128;
+    const float2* ln_stats = ln ? reinterpret_cast<const float2*>(ln->stats) : nullptr;
+    const float *ln_g = ln ? ln->gamma : nullptr, *ln_b = ln ? ln->beta : nullptr;
+    if (ln) ASP_REQUIRE(epilogue == EPI_RESID_F32 && ln->stats && ln->gamma && ln->beta, "gemm: LayerNorm-on-read needs the residual epilogue");
     ASP_REQUIRE(a_hi && w_hi, "gemm: NULL operand");
     ASP_REQUIRE(M >= 1 && N >= BN && (N % BN) == 0 && K >= kBlockK && (K % kBlockK) == 0,
                 "gemm: need N %% %d == 0 and K %% %d == 0 (got M=%d N=%d K=%d)", BN, kBlockK, M, N, K);
@@ -885,7 +907,7 @@ int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const voi
         if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, pbn / 2))) return rc;
         if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;
         if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, pbn / 2))) return rc;
-        GemmArgs gp{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32};
+        GemmArgs gp{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32, ln_stats, ln_g, ln_b};
         return pbn == 256 ? dispatch_pair<256>(ta_hi, ta_lo, tb_hi, tb_lo, gp, epilogue, stream)
                           : dispatch_pair<128>(ta_hi, ta_lo, tb_hi, tb_lo, gp, epilogue, stream);
     }
@@ -894,7 +916,7 @@ int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const voi
     if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, w_box))) return rc;
     if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;
     if ((rc = make_tmap_bf16(&tb_lo, w_lo ? w_lo : w_hi, N, K, w_box))) return rc;
-    GemmArgs g{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32};
+    GemmArgs g{M, N, K, a_lo ? 3 : 1, bias, residual, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, out_f32, ln_stats, ln_g, ln_b};
     if (g_gemm_kernel >= 1) {
         const int cl = bn == 192 ? 1 : g_gemm_cluster;
         if (bn == 192) return dispatch_persistent<192, 1>(ta_hi, ta_lo, tb_hi, tb_lo, g, epilogue, stream);
@@ -923,5 +945,5 @@ extern "C" int asp_gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* 
                                 const float* residual, int M, int N, int K, int epilogue, void* out_hi, void* out_lo,
                                 float* out_f32, asp_stream_t stream) {
     return asp::gemm_bf16_tn(a_hi, a_lo, w_hi, w_lo, bias, residual, M, N, K, epilogue, out_hi, out_lo, out_f32,
-                             (cudaStream_t)stream);
+                             (cudaStream_t)stream, nullptr);
 }

@@ -15,7 +15,10 @@ constexpr int kMaxHiddenPerLane = 32;  // hidden <= 32 lanes * 32 floats = 1024
 template <int VPL>  // float4 vectors per lane: hidden = 128 * VPL
 __device__ __forceinline__ void ln_row_store(float4 (&x)[VPL], int lane, const float* __restrict__ gamma,
                                              const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
-                                             __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+                                             __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                             float2* __restrict__ stats = nullptr) {
+    // out_f32 == nullptr: the fp32 row is not written -- its consumer (the residual epilogue of a GEMM) rebuilds it from
+    // the pre-LayerNorm row and *stats = (mean, rstd) with the expression below (gemm.cu: ln_on_read)
     constexpr float inv_n = 1.0f / (128 * VPL);
     float s = 0.f;
 #pragma unroll
@@ -28,6 +31,7 @@ __device__ __forceinline__ void ln_row_store(float4 (&x)[VPL], int lane, const f
         q += (a * a + b * b) + (c * c + d * d);
     }
     const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+    if (stats && lane == 0) *stats = make_float2(mean, rstd);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
         const int k4 = v * 32 + lane;
@@ -38,7 +42,7 @@ __device__ __forceinline__ void ln_row_store(float4 (&x)[VPL], int lane, const f
         y.y = (x[v].y - mean) * rstd * g.y + b.y;
         y.z = (x[v].z - mean) * rstd * g.z + b.z;
         y.w = (x[v].w - mean) * rstd * g.w + b.w;
-        reinterpret_cast<float4*>(out_f32)[k4] = y;
+        if (out_f32) reinterpret_cast<float4*>(out_f32)[k4] = y;
         const __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
         uint2 ph;
         ph.x = *reinterpret_cast<const uint32_t*>(&h0);
@@ -88,7 +92,7 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ typ
 template <int VPL>
 __global__ void __launch_bounds__(128)
 ln_kernel(const float* in, int T, const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* out_f32,
-          __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+          __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, float2* __restrict__ stats) {
     constexpr int H = 128 * VPL;
     pdl_trigger();
     pdl_wait();
@@ -99,8 +103,8 @@ ln_kernel(const float* in, int T, const float* __restrict__ gamma, const float* 
     float4 x[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) x[v] = r[v * 32 + lane];
-    ln_row_store<VPL>(x, lane, gamma, beta, eps, out_f32 + (size_t)t * H, out_hi + (size_t)t * H,
-                      out_lo ? out_lo + (size_t)t * H : nullptr);
+    ln_row_store<VPL>(x, lane, gamma, beta, eps, out_f32 ? out_f32 + (size_t)t * H : nullptr, out_hi + (size_t)t * H,
+                      out_lo ? out_lo + (size_t)t * H : nullptr, stats ? stats + t : nullptr);
 }
 
 int embed_ln_launch(const int32_t* ids, const int32_t* type_ids, int T, int L, int H, int vocab, int max_pos,
@@ -115,11 +119,12 @@ int embed_ln_launch(const int32_t* ids, const int32_t* type_ids, int T, int L, i
 }
 
 int ln_launch(const float* in, int T, int H, const float* gamma, const float* beta, float eps, float* out_f32, void* out_hi,
-              void* out_lo, cudaStream_t stream) {
+              void* out_lo, cudaStream_t stream, void* stats) {
+    ASP_REQUIRE(out_f32 || stats, "encoder: a LayerNorm without fp32 output must leave its row statistics");
     ASP_REQUIRE(H == 768, "encoder: hidden size %d not built (768 only)", H);
     const int wpb = 4, blocks = (T + wpb - 1) / wpb;
     ASP_CUDA(launch_pdl(ln_kernel<6>, dim3(blocks), dim3(wpb * 32), 0, stream, in, T, gamma, beta, eps, out_f32,
-                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo));
+                        (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, (float2*)stats));
     ASP_LAUNCH_CHECK("ln_kernel");
     return ASP_OK;
 }

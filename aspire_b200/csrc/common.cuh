@@ -69,6 +69,15 @@ extern int g_gemm_kernel;    // asp_set_option("gemm_kernel")
 extern int g_gemm_cluster;   // asp_set_option("gemm_cluster")
 extern int g_gemm_pair;      // asp_set_option("gemm_pair")
 extern int g_attn_tc;        // asp_set_option("attn_tc")
+// asp_set_option("ln_on_read"): 1 (default) = the encoder's inner LayerNorms write only the bf16 GEMM operand and per-row
+// (mean, rstd); the residual epilogue of the next GEMM normalises the pre-LayerNorm rows as it reads them.  0 = every
+// LayerNorm writes the fp32 residual stream (one 4-byte write and one read less per element and LayerNorm with 1).
+extern int g_ln_on_read;
+struct LnOnRead {
+    const void* stats;  // float2 (mean, rstd) per row
+    const float* gamma;
+    const float* beta;
+};
 extern int g_span_tma;       // asp_set_option("span_tma")
 
 // Epsilon schedule passed by value in kernel parameter space (uniform, read through the constant bank).

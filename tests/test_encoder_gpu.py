@@ -143,19 +143,50 @@ def test_tcgen05_attention_equals_mma_sync_attention(B, L, lens):
         ids[b, n:] = 0
     enc = B200BertEncoder(model)
     out = {}
-    for mode in (2, 1, 0):   # 2: persistent warp-specialised kernel, 1: one tile per CTA (default), 0: mma.sync
+    # 3: one tile per CTA with V as an MN-major operand (no V^T pass), 2: persistent warp-specialised kernel,
+    # 1: one tile per CTA, V transposed in shared memory, 0: mma.sync
+    for mode in (3, 2, 1, 0):
         _abi.set_option("attn_tc", mode)
         try:
             out[mode] = enc.forward(ids, lens, precision="bf16").clone()
             torch.cuda.synchronize()
         finally:
-            _abi.set_option("attn_tc", 1)
+            _abi.set_option("attn_tc", 3)
     ref = _hf_reference(model, ids, lens)
     valid = (torch.arange(L)[None, :] < torch.tensor(lens)[:, None]).cuda()
-    for mode in (2, 1):
+    for mode in (3, 2, 1):
         assert torch.isfinite(out[mode]).all()
         rel = ((out[mode] - out[0]).norm() / out[0].norm()).item()
         assert rel <= 6e-3, f"tcgen05 (mode {mode}) vs mma.sync attention: relative L2 {rel:.3e}"
         rel_ref = ((out[mode] - ref)[valid].norm() / ref[valid].norm()).item()
         assert rel_ref <= 3e-2, f"tcgen05 attention (mode {mode}) vs HF fp32: relative L2 {rel_ref:.3e}"
-    assert torch.equal(out[2], out[1])   # same arithmetic in the same order: the two tcgen05 kernels agree bit for bit
+    assert torch.equal(out[2], out[1])   # same arithmetic in the same order: the tcgen05 kernels agree bit for bit
+    assert torch.equal(out[3], out[1])
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
+def test_layernorm_on_read_is_bit_identical(precision):
+    """asp_set_option("ln_on_read"): with 1 (default) the inner LayerNorms write only the bf16 GEMM operand and per-row
+    (mean, rstd) and the next residual epilogue normalises the pre-LayerNorm rows as it reads them; with 0 every LayerNorm
+    writes the fp32 residual stream.  Same expression, same operands: the hidden states agree bit for bit (3 layers, so
+    both the layer-0 path -- residual = embedding LayerNorm output -- and the chained path are exercised; ragged lengths,
+    a row count that is not a multiple of the 128-row tile)."""
+    from aspire_b200 import _abi
+    from aspire_b200.encoder import B200BertEncoder
+    model = ref_shims.seeded_bert(seed=11, num_hidden_layers=3)
+    B, L, lens = 5, 77, [77, 50, 1, 33, 64]
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(1000, 31000, (B, L), generator=g)
+    for b, n in enumerate(lens):
+        ids[b, n:] = 0
+    enc = B200BertEncoder(model)
+    out = {}
+    for mode in (0, 1):
+        _abi.set_option("ln_on_read", mode)
+        try:
+            out[mode] = enc.forward(ids, lens, precision=precision).clone()
+            torch.cuda.synchronize()
+        finally:
+            _abi.set_option("ln_on_read", 1)
+    assert torch.isfinite(out[1]).all()
+    assert torch.equal(out[0], out[1])
