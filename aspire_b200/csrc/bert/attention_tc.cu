@@ -52,8 +52,10 @@ constexpr float kAtSafeExp = 100.f;  // largest exponent of 2 a probability may 
 
 // one 32-key piece of a row: p = 2^((s - m) c) into the P tile as bf16; returns the sum of the probabilities and tracks
 // the largest exponent.  nvalid = keys of the piece inside the document: 32 (no per-element test), 1..31, or 0 (zeros).
+// TM: the piece goes to 16 TMEM columns at p_tmem (A operand of P V read from tensor memory) instead of shared memory.
+template <bool TM = false>
 __device__ __forceinline__ float at_softmax_piece(const float (&v)[32], int c0, int nvalid, float sc, float off, uint8_t* smem, int r,
-                                                  float& xmax) {
+                                                  float& xmax, uint32_t p_tmem = 0u) {
     uint32_t pk[16];
     float sum = 0.f;
     if (nvalid >= 32) {  // warp-uniform
@@ -84,6 +86,10 @@ __device__ __forceinline__ float at_softmax_piece(const float (&v)[32], int c0, 
 #pragma unroll
         for (int e = 0; e < 16; ++e) pk[e] = 0u;
     }
+    if (TM) {
+        tmem_st16(p_tmem, pk);
+        return sum;
+    }
     uint8_t* prow = smem + (c0 >> 6) * kAtPBlock + (r >> 3) * 1024 + (r & 7) * 128;
     const int ch0 = (c0 & 63) >> 3;  // first 16-byte chunk (8 keys) of this 32-key piece inside its 64-key block
 #pragma unroll
@@ -95,7 +101,11 @@ __device__ __forceinline__ float at_softmax_piece(const float (&v)[32], int c0, 
 // VMN: V is consumed as an MN-major B operand straight from its TMA tile ([key][d], 128-byte rows, 128B swizzle: the canonical
 // MN-major SW128 layout with 8-key groups 1024 bytes apart), so the V -> V^T pass does not exist.  The tile then lands where
 // V^T would have been (P overwrites Q, K and the unused gap).
-template <bool VMN>
+// PT (with VMN): P never touches shared memory.  Each thread overwrites the part of S it has already consumed with its
+// probabilities as packed bf16 pairs (half h of row r: S columns 128h..128h+127 -> P columns 128h..128h+63, piece by
+// piece behind the read position), MMA 2 takes A from tensor memory and writes O to columns 64-127 (consumed S of half 0).
+// The rare exact path needs S again: MMA 1 is simply re-issued, Q and K are still in shared memory.
+template <bool VMN, bool PT = false>
 __global__ void __launch_bounds__(kAtThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tkv,
                     const int32_t* __restrict__ seq_lens, int L, int H, __nv_bfloat16* __restrict__ ctx) {
@@ -133,14 +143,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         tma_load_2d(smem + (VMN ? kAtOffVt : kAtOffV), &tkv, &bar_load, 2 * H + head * kAtD, b * L);
     }
     mbar_wait(&bar_load, 0);
-    if (threadIdx.x == 0) {
+    auto issue_s = [&]() {
         tc_fence_after_sync();
         constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtKeys);
         const uint64_t qd = umma_desc_sw128(sbase), kd = umma_desc_sw128(sbase + kAtOffK);
 #pragma unroll
         for (int kk = 0; kk < kAtD / 16; ++kk) umma_bf16(tmem_base, qd + 2 * kk, kd + 2 * kk, idesc, kk != 0);
         umma_commit(&bar_s);
-    }
+    };
+    if (threadIdx.x == 0) issue_s();
     __syncwarp();
     // ---- V -> V^T while MMA 1 runs: 8 x 8 blocks, four at a time (same 8 keys, four 8-wide slices of d) ----
     if (!VMN) {
@@ -157,7 +168,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
             at_stmatrix_x4(dst, r);
         }
     }
-    __syncthreads();  // V^T complete, nobody reads the V staging any more: P may overwrite Q / K / V
+    if (!PT) __syncthreads();  // V^T complete, nobody reads the V staging any more: P may overwrite Q / K / V
     // ---- softmax: two threads per query row (warps w and w + 4 share TMEM lane quadrant w), 128 keys each.  S is read
     //      from TMEM ONCE (64 B per clk per SM: a second pass over the 128 KB tile would cost as much as everything else):
     //      the shift m is the maximum over the FIRST 32 keys of each half, not the row maximum.  Any m within 2^100 of the
@@ -184,10 +195,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
         if (c0 != cbeg && c0 < nkeys) tmem_ld32(trow + c0, v);   // (the first piece is still in registers)
-        sum += at_softmax_piece(v, c0, min(max(nkeys - c0, 0), 32), sc, off, smem, r, xmax);  // beyond the document: zeros
+        sum += at_softmax_piece<PT>(v, c0, min(max(nkeys - c0, 0), 32), sc, off, smem, r, xmax,  // beyond the document: zeros
+                                    trow + (uint32_t)(cbeg + ((c0 - cbeg) >> 1)));
+    }
+    if (PT) {
+        tmem_wait_st();
+        tc_fence_before_sync();
     }
     if (__syncthreads_or(xmax > kAtSafeExp)) {
         // exact form (rare): row maximum over all keys first, then the probabilities again
+        if (PT) {  // S was overwritten by P: compute it again
+            if (threadIdx.x == 0) issue_s();
+            __syncwarp();
+            mbar_wait(&bar_s, 1);
+            tc_fence_after_sync();
+        }
         float me = -INFINITY;
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + 128 && c0 < nkeys; c0 += 32) {
@@ -205,12 +227,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
 #pragma unroll 1
         for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
             if (c0 < nkeys) tmem_ld32(trow + c0, v);
-            sum += at_softmax_piece(v, c0, min(max(nkeys - c0, 0), 32), sc, off, smem, r, xmax);
+            sum += at_softmax_piece<PT>(v, c0, min(max(nkeys - c0, 0), 32), sc, off, smem, r, xmax,
+                                        trow + (uint32_t)(cbeg + ((c0 - cbeg) >> 1)));
         }
+        if (PT) tmem_wait_st();
     }
     __syncthreads();
     xch[half * 128 + r] = sum;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P and V^T were written through the generic proxy
+    if (!PT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P and V^T were written through the generic proxy
     tc_fence_before_sync();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -222,8 +246,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
             // K-major V^T: 64-key blocks of [d][key] rows, 32 bytes per K = 16 step; MN-major V: 16 keys = 16 rows = 2 KB per step
             const uint64_t vd = umma_desc_sw128(sbase + kAtOffVt + (VMN ? kb * 64 * 128 : kb * kAtVtBlock));
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(tmem_base, pd + 2 * kk, vd + (VMN ? (2048 >> 4) * kk : 2 * kk), idesc, (kb | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk) {
+                if (PT)  // keys 64 kb + 16 kk .. + 15: packed P columns 128 * (kb / 2) + 32 * (kb % 2) + 8 kk
+                    umma_bf16_ts(tmem_base + 64u, tmem_base + (uint32_t)(128 * (kb >> 1) + 32 * (kb & 1) + 8 * kk),
+                                 vd + (2048 >> 4) * kk, idesc, (kb | kk) != 0);
+                else
+                    umma_bf16(tmem_base, pd + 2 * kk, vd + (VMN ? (2048 >> 4) * kk : 2 * kk), idesc, (kb | kk) != 0);
+            }
         }
         umma_commit(&bar_o);
     }
@@ -233,7 +262,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     tc_fence_after_sync();
     // ---- epilogue: the half-th 32 columns of O for row r ----
     {
-        tmem_ld32(trow + half * 32, v);
+        tmem_ld32(trow + (PT ? 64 : 0) + half * 32, v);
         if (q0 + r < L) {
             __nv_bfloat16* dst = ctx + ((size_t)b * L + q0 + r) * H + head * kAtD + half * 32;
 #pragma unroll
@@ -491,6 +520,7 @@ int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int 
     if (attr_dev != dev) {
         ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
         ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+        ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
         attr_dev = dev;
     }
     if (g_attn_tc == 2) {
@@ -506,7 +536,10 @@ int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int 
         return ASP_OK;
     }
     dim3 grid((L + kAtQ - 1) / kAtQ, heads, B);
-    if (g_attn_tc == 3)
+    if (g_attn_tc == 4)
+        ASP_CUDA(launch_pdl(attention_tc_kernel<true, true>, grid, dim3(kAtThreads), (size_t)kAtSmem, stream, cache.q, cache.kv,
+                            seq_lens, L, H, (__nv_bfloat16*)ctx_hi));
+    else if (g_attn_tc == 3)
         ASP_CUDA(launch_pdl(attention_tc_kernel<true>, grid, dim3(kAtThreads), (size_t)kAtSmem, stream, cache.q, cache.kv, seq_lens,
                             L, H, (__nv_bfloat16*)ctx_hi));
     else

@@ -143,9 +143,10 @@ def test_tcgen05_attention_equals_mma_sync_attention(B, L, lens):
         ids[b, n:] = 0
     enc = B200BertEncoder(model)
     out = {}
+    # 4: as 3 with P in tensor memory instead of shared memory,
     # 3: one tile per CTA with V as an MN-major operand (no V^T pass), 2: persistent warp-specialised kernel,
     # 1: one tile per CTA, V transposed in shared memory, 0: mma.sync
-    for mode in (3, 2, 1, 0):
+    for mode in (4, 3, 2, 1, 0):
         _abi.set_option("attn_tc", mode)
         try:
             out[mode] = enc.forward(ids, lens, precision="bf16").clone()
@@ -154,7 +155,7 @@ def test_tcgen05_attention_equals_mma_sync_attention(B, L, lens):
             _abi.set_option("attn_tc", 3)
     ref = _hf_reference(model, ids, lens)
     valid = (torch.arange(L)[None, :] < torch.tensor(lens)[:, None]).cuda()
-    for mode in (3, 2, 1):
+    for mode in (4, 3, 2, 1):
         assert torch.isfinite(out[mode]).all()
         rel = ((out[mode] - out[0]).norm() / out[0].norm()).item()
         assert rel <= 6e-3, f"tcgen05 (mode {mode}) vs mma.sync attention: relative L2 {rel:.3e}"
@@ -162,6 +163,7 @@ def test_tcgen05_attention_equals_mma_sync_attention(B, L, lens):
         assert rel_ref <= 3e-2, f"tcgen05 attention (mode {mode}) vs HF fp32: relative L2 {rel_ref:.3e}"
     assert torch.equal(out[2], out[1])   # same arithmetic in the same order: the tcgen05 kernels agree bit for bit
     assert torch.equal(out[3], out[1])
+    assert torch.equal(out[4], out[1])   # P kept in tensor memory (A operand of P V read from TMEM)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
