@@ -80,7 +80,7 @@ extern "C" int asp_set_option(const char* key, int value) {
         return ASP_OK;
     }
     if (strcmp(key, "attn_tc") == 0) {  // developer switch: tcgen05 attention (plain bf16, L <= 256) 3 / 1 / 2 (see attention_tc.cu), 0 mma.sync attention
-        ASP_REQUIRE(value >= 0 && value <= 4, "asp_set_option: attn_tc must be 0..4");
+        ASP_REQUIRE(value >= 0 && value <= 5, "asp_set_option: attn_tc must be 0..5");
         asp::g_attn_tc = value;
         return ASP_OK;
     }

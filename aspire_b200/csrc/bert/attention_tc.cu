@@ -484,13 +484,274 @@ attention_tc_persistent_kernel(const __grid_constant__ CUtensorMap tq, const __g
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// asp_set_option("attn_tc"): plain-bf16 attention with L <= 256 on tcgen05: 3 (default) = one tile per CTA, two CTAs per SM, V
-// consumed as an MN-major operand straight from its TMA tile; 1 = the same with V transposed in shared memory first
-// (bit-identical, ~1 % of a forward slower: profiles/r02_3t_*); 2 = the persistent warp-specialised kernel (bit-identical;
-// measured SLOWER, 2.21 vs 2.15 ms per B=32 L=256 forward, profiles/r02_3h_attention_persistent_ab.txt: its eight worker
-// warps run transposition, softmax and epilogue of a tile back to back -- ~12 k clk -- where two independent CTAs
-// overlap them); 0 = always mma.sync
-int g_attn_tc = 3;
+// ---- pipelined version: one CTA per SM, a producer warp and TWO worker groups -------------------------------------------
+// The one-tile-per-CTA kernel is a serial chain per tile -- prologue, load (HBM / L2 latency), MMA 1, softmax, MMA 2, store --
+// with only the second resident CTA to hide it: a fifth of the warps' time is the wait for the TMA loads, a CTA prologue is
+// paid per tile.  Here the two tiles in flight per SM (two 256-column TMEM buffers) are worked on by two groups of eight
+// warps, and a producer thread keeps the operands one tile AHEAD of both:
+//   shared memory  three Q|K slots (48 KB) + two V slots (32 KB).  Q and K of a tile are dead once MMA 1 has run and V is only
+//                  needed by MMA 2, so tile k+2's Q|K land while tiles k and k+1 are being worked on, and its V takes the slot
+//                  tile k's MMA 2 has just released.  P never touches shared memory (TMEM A operand, V MN-major: as in PT above).
+//   warp 0, lane 0 TMA loads and every tcgen05.mma: S(k+2) as soon as group k % 2 has stored O(k), P V(k) as soon as the
+//                  group has written P(k).
+//   groups 0 / 1   warps 1-8 / 9-16, tile k goes to group k % 2: softmax from TMEM (two threads per row), P back into the
+//                  consumed part of S, O / row sum -> bf16 context rows.
+// A tile whose exponents leave the safe range asks the producer to run MMA 1 again (S was overwritten by P; Q and K are still
+// in their slot) and redoes the softmax in the exact two-pass form.
+constexpr int kApThreads = 32 + 2 * 256;
+constexpr int kApQK = kAtQBytes + kAtKBytes;                     // 48 KB
+constexpr int kApOffV = 3 * kApQK;                               // 144 KB
+constexpr int kApOffX = kApOffV + 2 * kAtKBytes;                 // 208 KB: [2 groups][2 halves][128] floats
+constexpr int kApOffBar = kApOffX + 2 * 2 * 128 * 4;
+constexpr int kApSmem = kApOffBar + 256;
+
+__device__ __forceinline__ void ap_group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
+
+__global__ void __launch_bounds__(kApThreads, 1)
+attention_tc_pipe_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tkv,
+                         const int32_t* __restrict__ seq_lens, int B, int L, int H, int heads, __nv_bfloat16* __restrict__ ctx) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023u) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kApOffBar);
+    uint64_t *qk_loaded = bars, *v_loaded = bars + 3, *s_ready = bars + 5, *p_ready = bars + 7, *o_ready = bars + 9,
+             *tmem_free = bars + 11;
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 13);
+    volatile int* flag = reinterpret_cast<volatile int*>(bars + 14);  // [0..1] a row of the group's tile overflowed; [2..3] redo request
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nqb = (L + kAtQ - 1) / kAtQ;
+    const int ntiles = nqb * heads * B;  // tile t = (document, head, query block), query block fastest: neighbouring CTAs
+                                         // work on the two query blocks of one (document, head) and share its K / V in L2
+    const int n = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto tile_of = [&](int k, int& qb, int& head, int& b) {
+        const int t = blockIdx.x + k * gridDim.x;
+        const int u = t / nqb;
+        qb = t - u * nqb;
+        b = u / heads;
+        head = u - b * heads;
+    };
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tq);
+        tma_prefetch_desc(&tkv);
+        for (int i = 0; i < 3; ++i) mbar_init(&qk_loaded[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&v_loaded[i], 1);
+            mbar_init(&s_ready[i], 1);
+            mbar_init(&p_ready[i], 256);
+            mbar_init(&o_ready[i], 1);
+            mbar_init(&tmem_free[i], 256);
+        }
+        for (int i = 0; i < 4; ++i) flag[i] = 0;
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (warp == 0) {
+        if (lane == 0 && n > 0) {
+            // ------------------------------ producer: TMA + MMA issue -------------------------------------------------
+            uint32_t ph_qk = 0, ph_v = 0, ph_p = 0, ph_o = 0, ph_f = 0;  // phase bits, one per barrier
+            auto wait = [&](uint64_t* bar, uint32_t& ph, int i) {
+                mbar_wait(&bar[i], (ph >> i) & 1u);
+                ph ^= 1u << i;
+            };
+            auto load_qk = [&](int k) {
+                int qb, head, b;
+                tile_of(k, qb, head, b);
+                const int q = k % 3;
+                uint8_t* st = smem + q * kApQK;
+                mbar_arrive_expect_tx(&qk_loaded[q], kApQK);
+                tma_load_2d(st, &tq, &qk_loaded[q], head * kAtD, b * L + qb * kAtQ);
+                tma_load_2d(st + kAtQBytes, &tkv, &qk_loaded[q], H + head * kAtD, b * L);
+            };
+            auto load_v = [&](int k) {
+                int qb, head, b;
+                tile_of(k, qb, head, b);
+                const int s = k & 1;
+                mbar_arrive_expect_tx(&v_loaded[s], kAtKBytes);
+                tma_load_2d(smem + kApOffV + s * kAtKBytes, &tkv, &v_loaded[s], 2 * H + head * kAtD, b * L);
+            };
+            auto mma_s = [&](int k) {  // S(k) = Q K^T into TMEM buffer k & 1
+                const int s = k & 1;
+                tc_fence_after_sync();
+                constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtKeys);
+                const uint32_t st = sbase + (k % 3) * kApQK;
+                const uint64_t qd = umma_desc_sw128(st), kd = umma_desc_sw128(st + kAtQBytes);
+#pragma unroll
+                for (int kk = 0; kk < kAtD / 16; ++kk) umma_bf16(tmem_base + s * 256, qd + 2 * kk, kd + 2 * kk, idesc, kk != 0);
+                umma_commit(&s_ready[s]);
+            };
+            pdl_wait();  // the QKV projection has written its output
+            load_qk(0);
+            load_v(0);
+            if (n > 1) {
+                load_qk(1);
+                load_v(1);
+            }
+            if (n > 2) load_qk(2);
+            wait(qk_loaded, ph_qk, 0);
+            mma_s(0);
+            if (n > 1) {
+                wait(qk_loaded, ph_qk, 1);
+                mma_s(1);
+            }
+            for (int k = 0; k < n; ++k) {
+                const int s = k & 1;
+                wait(p_ready, ph_p, s);
+                while (flag[2 + s]) {  // the group asks for S(k) again (exact softmax): Q and K are still in their slot
+                    flag[2 + s] = 0;
+                    mma_s(k);
+                    wait(p_ready, ph_p, s);
+                }
+                wait(v_loaded, ph_v, s);
+                tc_fence_after_sync();
+                {
+                    constexpr uint32_t idesc = umma_idesc_bf16(kAtQ, kAtD) | (1u << 16);  // B = V, MN-major
+                    const uint32_t tb = tmem_base + s * 256;
+#pragma unroll
+                    for (int kb = 0; kb < kAtKeys / 64; ++kb) {
+                        const uint64_t vd = umma_desc_sw128(sbase + kApOffV + s * kAtKBytes + kb * 64 * 128);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16_ts(tb + 64u, tb + (uint32_t)(128 * (kb >> 1) + 32 * (kb & 1) + 8 * kk), vd + (2048 >> 4) * kk, idesc,
+                                         (kb | kk) != 0);
+                    }
+                    umma_commit(&o_ready[s]);
+                }
+                if (k + 3 < n) load_qk(k + 3);  // slot k % 3: S(k) is final now
+                if (k + 2 < n) {
+                    wait(o_ready, ph_o, s);     // P V(k) has read V(k): its slot takes V(k+2)
+                    load_v(k + 2);
+                    wait(tmem_free, ph_f, s);   // the group has read O(k): the TMEM buffer takes S(k+2)
+                    wait(qk_loaded, ph_qk, (k + 2) % 3);
+                    mma_s(k + 2);
+                }
+            }
+        }
+    } else {
+        // ------------------------------ worker groups: softmax, epilogue ------------------------------------------
+        const int g = (warp - 1) >> 3, wid = (warp - 1) & 7;
+        const int half = wid >> 2, quad = warp & 3;     // TMEM lane quadrant is fixed by the hardware warp id
+        const int r = quad * 32 + lane;
+        const float sc = 0.125f * kLog2e;
+        float* xch = reinterpret_cast<float*>(smem + kApOffX) + g * 256;
+        const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(quad * 32) << 16);
+        const int cbeg = half * 128;
+        uint32_t ph_s = 0, ph_o = 0;
+        // the next tile's coordinates and key count are fetched one tile ahead: a global load in front of the first use of
+        // nkeys cost every tile ~10 % of its time (long-scoreboard stall right after the wait for S)
+        int qb = 0, head = 0, b = 0, len_next = 1;
+        if (g < n) {
+            tile_of(g, qb, head, b);
+            len_next = __ldg(seq_lens + b);
+        }
+        for (int k = g; k < n; k += 2) {
+            const int q0 = qb * kAtQ, head_k = head, b_k = b;
+            const int nkeys = min(max(len_next, 1), min(L, kAtKeys));
+            if (k + 2 < n) {
+                tile_of(k + 2, qb, head, b);
+                len_next = __ldg(seq_lens + b);
+            }
+            mbar_wait(&s_ready[g], ph_s);
+            ph_s ^= 1u;
+            tc_fence_after_sync();
+            float v[32];
+            float mloc = -INFINITY;
+            if (cbeg < nkeys) {
+                tmem_ld32(trow + cbeg, v);
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (cbeg + e < nkeys) mloc = fmaxf(mloc, v[e]);
+            }
+            xch[half * 128 + r] = mloc;
+            ap_group_sync(g);
+            float m = fmaxf(xch[r], xch[128 + r]);
+            float off = m * sc, sum = 0.f, xmax = -INFINITY;
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+                if (c0 != cbeg && c0 < nkeys) tmem_ld32(trow + c0, v);
+                sum += at_softmax_piece<true>(v, c0, min(max(nkeys - c0, 0), 32), sc, off, nullptr, r, xmax,
+                                              trow + (uint32_t)(cbeg + ((c0 - cbeg) >> 1)));
+            }
+            if (xmax > kAtSafeExp) flag[g] = 1;
+            tmem_wait_st();
+            ap_group_sync(g);  // (also: every thread has read the maxima, xch may take the sums)
+            const bool redo = flag[g] != 0;  // group-uniform
+            if (redo) {
+                if (wid == 0 && lane == 0) flag[2 + g] = 1;  // published by the arrive below
+                tc_fence_before_sync();
+                mbar_arrive(&p_ready[g]);
+                mbar_wait(&s_ready[g], ph_s);  // S(k) again
+                ph_s ^= 1u;
+                tc_fence_after_sync();
+                float me = -INFINITY;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + 128 && c0 < nkeys; c0 += 32) {
+                    tmem_ld32(trow + c0, v);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c0 + e < nkeys) me = fmaxf(me, v[e]);
+                }
+                xch[half * 128 + r] = me;
+                ap_group_sync(g);
+                m = fmaxf(xch[r], xch[128 + r]);
+                off = m * sc;
+                sum = 0.f;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + 128; c0 += 32) {
+                    if (c0 < nkeys) tmem_ld32(trow + c0, v);
+                    sum += at_softmax_piece<true>(v, c0, min(max(nkeys - c0, 0), 32), sc, off, nullptr, r, xmax,
+                                                  trow + (uint32_t)(cbeg + ((c0 - cbeg) >> 1)));
+                }
+                tmem_wait_st();
+                ap_group_sync(g);
+                if (wid == 0 && lane == 0) flag[g] = 0;
+            }
+            xch[half * 128 + r] = sum;
+            tc_fence_before_sync();
+            mbar_arrive(&p_ready[g]);
+            mbar_wait(&o_ready[g], ph_o);
+            ph_o ^= 1u;
+            tc_fence_after_sync();
+            const float inv = 1.0f / (xch[r] + xch[128 + r]);  // (both halves stored their sums before arriving on p_ready)
+            tmem_ld32(trow + 64 + half * 32, v);
+            if (q0 + r < L) {
+                __nv_bfloat16* dst = ctx + ((size_t)b_k * L + q0 + r) * H + head_k * kAtD + half * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * q + 2 * e] * inv, v[8 * q + 2 * e + 1] * inv);
+                        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&tmem_free[g]);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// asp_set_option("attn_tc"): plain-bf16 attention with L <= 256 on tcgen05 -- all variants agree bit for bit:
+//   5 (default)  the pipelined kernel above: one CTA per SM, producer thread + two worker groups, P in tensor memory
+//                (64 us against 90 us for variant 3 per layer at 32768 tokens when timed alone, profiles/r02_3y_*; 1.5-3 % of
+//                a whole forward, r02_3z_*)
+//   3            one tile per CTA, two CTAs per SM, V consumed as an MN-major operand straight from its TMA tile
+//   4            as 3 with P in tensor memory (same speed as 3)
+//   1            as 3 with V transposed in shared memory first (~1 % of a forward slower: r02_3t_*)
+//   2            the first persistent kernel: eight worker warps run a tile's transposition, softmax and epilogue back to
+//                back (slower than 1: profiles/r02_3h_attention_persistent_ab.txt)
+//   0            always mma.sync (attention.cu)
+int g_attn_tc = 5;
 
 bool attention_tc_supported(const void* qkv_lo, int L, int H, int heads) {
     return g_attn_tc && qkv_lo == nullptr && L >= 1 && L <= kAtKeys && H == heads * kAtD;
@@ -522,6 +783,18 @@ int attention_tc_launch(const void* qkv_hi, const int32_t* seq_lens, int B, int 
         ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
         ASP_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
         attr_dev = dev;
+    }
+    if (g_attn_tc == 5) {
+        static thread_local int attr_dev5 = -1;
+        if (attr_dev5 != dev) {
+            ASP_CUDA(cudaFuncSetAttribute(attention_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmem));
+            attr_dev5 = dev;
+        }
+        const int ntiles = ((L + kAtQ - 1) / kAtQ) * heads * B;
+        ASP_CUDA(launch_pdl(attention_tc_pipe_kernel, dim3(std::min(ntiles, sm_count())), dim3(kApThreads), (size_t)kApSmem, stream,
+                            cache.q, cache.kv, seq_lens, B, L, H, heads, (__nv_bfloat16*)ctx_hi));
+        ASP_LAUNCH_CHECK("attention_tc_pipe_kernel");
+        return ASP_OK;
     }
     if (g_attn_tc == 2) {
         static thread_local int attr_dev2 = -1;

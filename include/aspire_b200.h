@@ -56,8 +56,9 @@ long long asp_launch_count(void);
  *   "gemm_cluster"  1 (default), 2 or 4 CTAs per cluster sharing W tiles by TMA multicast
  *   "gemm_pair"     0 (default) off, 1 / 2 CTA pairs (tcgen05 cta_group::2) with 128- / 256-wide pair tiles
  *   "pdl"           1 (default) encoder kernels use programmatic dependent launch, 0 plain stream order
- *   "attn_tc"       plain-bf16 attention, L <= 256: 3 (default) tcgen05, V as an MN-major operand; 1 tcgen05 with V
- *                   transposed in shared memory; 2 persistent tcgen05 variant; 0 mma.sync (1, 2, 3 agree bit for bit)
+ *   "attn_tc"       plain-bf16 attention, L <= 256: 5 (default) pipelined tcgen05 kernel (producer + two worker groups per
+ *                   SM, P in tensor memory); 3 / 4 / 1 / 2 earlier tcgen05 variants (one tile per CTA with V MN-major, + P in
+ *                   tensor memory, V transposed in shared memory, first persistent kernel); 0 mma.sync.  1-5 agree bit for bit
  *   "ln_on_read"    1 (default) inner LayerNorms write the bf16 GEMM operand + per-row (mean, rstd) and the next
  *                   residual epilogue normalises the pre-LayerNorm rows as it reads them; 0 every LayerNorm writes the
  *                   fp32 residual stream (bit-identical outputs)

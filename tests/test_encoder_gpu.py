@@ -143,19 +143,20 @@ def test_tcgen05_attention_equals_mma_sync_attention(B, L, lens):
         ids[b, n:] = 0
     enc = B200BertEncoder(model)
     out = {}
+    # 5: pipelined kernel (one CTA per SM, producer warp + two worker groups, operands one tile ahead),
     # 4: as 3 with P in tensor memory instead of shared memory,
     # 3: one tile per CTA with V as an MN-major operand (no V^T pass), 2: persistent warp-specialised kernel,
     # 1: one tile per CTA, V transposed in shared memory, 0: mma.sync
-    for mode in (4, 3, 2, 1, 0):
+    for mode in (5, 4, 3, 2, 1, 0):
         _abi.set_option("attn_tc", mode)
         try:
             out[mode] = enc.forward(ids, lens, precision="bf16").clone()
             torch.cuda.synchronize()
         finally:
-            _abi.set_option("attn_tc", 3)
+            _abi.set_option("attn_tc", 5)
     ref = _hf_reference(model, ids, lens)
     valid = (torch.arange(L)[None, :] < torch.tensor(lens)[:, None]).cuda()
-    for mode in (4, 3, 2, 1):
+    for mode in (5, 4, 3, 2, 1):
         assert torch.isfinite(out[mode]).all()
         rel = ((out[mode] - out[0]).norm() / out[0].norm()).item()
         assert rel <= 6e-3, f"tcgen05 (mode {mode}) vs mma.sync attention: relative L2 {rel:.3e}"
@@ -164,6 +165,7 @@ def test_tcgen05_attention_equals_mma_sync_attention(B, L, lens):
     assert torch.equal(out[2], out[1])   # same arithmetic in the same order: the tcgen05 kernels agree bit for bit
     assert torch.equal(out[3], out[1])
     assert torch.equal(out[4], out[1])   # P kept in tensor memory (A operand of P V read from TMEM)
+    assert torch.equal(out[5], out[1])   # pipelined kernel: producer warp + two worker groups
 
 
 @pytest.mark.parametrize("precision", ["bf16", "bf16x3"])
@@ -192,3 +194,38 @@ def test_layernorm_on_read_is_bit_identical(precision):
             _abi.set_option("ln_on_read", 1)
     assert torch.isfinite(out[1]).all()
     assert torch.equal(out[0], out[1])
+
+
+def test_tcgen05_attention_exact_softmax_path():
+    """The tcgen05 attention kernels read S from tensor memory once and shift by the maximum over a SUBSET of the keys; a tile
+    with an exponent more than 100 above that shift redoes the softmax in the exact two-pass form (the kernels that keep P in
+    tensor memory have to run Q K^T again for that).  Query / key projections scaled by 16 make the scores span hundreds of
+    powers of two, so nearly every tile takes that path: all tcgen05 variants still agree bit for bit, stay finite, and stay
+    close to the mma.sync kernel's online softmax."""
+    from aspire_b200 import _abi
+    from aspire_b200.encoder import B200BertEncoder
+    model = ref_shims.seeded_bert(seed=7, num_hidden_layers=2)
+    with torch.no_grad():
+        for layer in model.encoder.layer:
+            layer.attention.self.query.weight.mul_(16.0)
+            layer.attention.self.key.weight.mul_(16.0)
+    B, L, lens = 3, 256, [256, 200, 90]
+    g = torch.Generator().manual_seed(17)
+    ids = torch.randint(1000, 31000, (B, L), generator=g)
+    for b, n in enumerate(lens):
+        ids[b, n:] = 0
+    enc = B200BertEncoder(model)
+    out = {}
+    for mode in (5, 4, 3, 2, 1, 0):
+        _abi.set_option("attn_tc", mode)
+        try:
+            out[mode] = enc.forward(ids, lens, precision="bf16").clone()
+            torch.cuda.synchronize()
+        finally:
+            _abi.set_option("attn_tc", 5)
+    valid = (torch.arange(L)[None, :] < torch.tensor(lens)[:, None]).cuda()
+    for mode in (5, 4, 3, 2):
+        assert torch.isfinite(out[mode]).all()
+        assert torch.equal(out[mode], out[1]), f"attn_tc={mode} differs from attn_tc=1 on the exact-softmax path"
+    rel = ((out[1] - out[0])[valid].norm() / out[0][valid].norm()).item()
+    assert rel <= 5e-2, f"tcgen05 vs mma.sync attention on peaked softmax rows: relative L2 {rel:.3e}"

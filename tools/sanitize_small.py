@@ -61,8 +61,9 @@ from transformers import BertConfig, BertModel
 from aspire_b200.encoder import B200BertEncoder
 torch.manual_seed(0)
 enc = B200BertEncoder(BertModel(BertConfig(vocab_size=2000, num_hidden_layers=1)).eval())
-ids = torch.randint(5, 1999, (2, 150), generator=g)
-h = enc.forward(ids, [150, 31], precision="bf16")
+# 20 documents x 12 heads x 2 query blocks = 480 tiles: every CTA of the pipelined attention kernel walks 3-4 of them
+ids = torch.randint(5, 1999, (20, 150), generator=g)
+h = enc.forward(ids, [150, 31] * 10, precision="bf16")
 torch.cuda.synchronize()
 assert torch.isfinite(h).all()
 print("sanitize_small round-2 kernels ok")
