@@ -7,7 +7,10 @@ timeout 900 python -m pytest tests -m gpu -q --timeout 300 --durations=6 > gpuru
 grep -E "FAIL|passed|failed|exit|Error" gpurun_out/r2fin_pytest.txt | cut -c1-250 | tail -6
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2fin_smoke.txt 2>&1; tail -1 gpurun_out/r2fin_smoke.txt
 for tool in memcheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool python tools/sanitize_small.py > gpurun_out/r2fin_san_$tool.txt 2>&1
+  # (synccheck needs room for the kernels' mbarriers: without --num-cuda-barriers its tracking table overflows and a later
+  #  launch fails under the tool)
+  extra=""; [ $tool = synccheck ] && extra="--num-cuda-barriers 65536"
+  timeout 900 compute-sanitizer --tool $tool $extra python tools/sanitize_small.py > gpurun_out/r2fin_san_$tool.txt 2>&1
   echo "== $tool: $(grep -E 'ERROR SUMMARY|sanitize_small' gpurun_out/r2fin_san_$tool.txt | tr '\n' ' ')"
 done
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2fin_bench_ref.txt 2>&1

@@ -1,4 +1,5 @@
 """Small fused-kernel invocations for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -24,8 +25,12 @@ q = (0.3 * torch.randn(50, 20, 128, generator=g)).cuda()
 c = (0.3 * torch.randn(50, 27, 128, generator=g)).cuda()
 ql = torch.randint(1, 21, (50,), generator=g).int().cuda()
 cl = torch.randint(1, 28, (50,), generator=g).int().cuda()
-ot_scores(q, ql, c, cl, eps, want=("dual",))
-l2max_scores(q, ql, c, cl)
+# ASP_SAN_SKIP_VARLEN=1: synccheck reports "Missing init" for two of the var-len kernel's mbarriers (it does not model
+# cp.async.mbarrier.arrive.noinc) and then aborts the process at the next launch; with the switch the rest of the
+# script (every other kernel) still runs under that tool
+if os.environ.get("ASP_SAN_SKIP_VARLEN") != "1":
+    ot_scores(q, ql, c, cl, eps, want=("dual",))
+    l2max_scores(q, ql, c, cl)
 pair_heads(q, ql, c, cl, want=("top2", "att"))
 torch.cuda.synchronize()
 print("sanitize_small ok")
