@@ -229,3 +229,32 @@ def test_tcgen05_attention_exact_softmax_path():
         assert torch.equal(out[mode], out[1]), f"attn_tc={mode} differs from attn_tc=1 on the exact-softmax path"
     rel = ((out[1] - out[0])[valid].norm() / out[0][valid].norm()).item()
     assert rel <= 5e-2, f"tcgen05 vs mma.sync attention on peaked softmax rows: relative L2 {rel:.3e}"
+
+
+@pytest.mark.parametrize("B,L", [(40, 256), (30, 100), (26, 131)])
+def test_pipelined_attention_many_tiles_per_cta(B, L):
+    """The pipelined attention kernel walks several tiles per CTA (operand slots, TMEM buffers and barrier phases are reused):
+    960 / 360 / 624 tiles on 148 SMs, ragged lengths incl. 1 and L, one and two query blocks per document.  Bit-identical
+    to the one-tile-per-CTA kernels, within bf16 round-off of the mma.sync kernel."""
+    from aspire_b200 import _abi
+    from aspire_b200.encoder import B200BertEncoder
+    model = ref_shims.seeded_bert(seed=23, num_hidden_layers=2)
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    lens = torch.randint(1, L + 1, (B,), generator=g).tolist()
+    lens[0], lens[1] = L, 1
+    ids = torch.randint(1000, 31000, (B, L), generator=g)
+    for b, n in enumerate(lens):
+        ids[b, n:] = 0
+    enc = B200BertEncoder(model)
+    out = {}
+    for mode in (5, 3, 1, 0):
+        _abi.set_option("attn_tc", mode)
+        try:
+            out[mode] = enc.forward(ids, lens, precision="bf16").clone()
+            torch.cuda.synchronize()
+        finally:
+            _abi.set_option("attn_tc", 5)
+    assert torch.isfinite(out[5]).all()
+    assert torch.equal(out[5], out[1]) and torch.equal(out[3], out[1])
+    rel = ((out[5] - out[0]).norm() / out[0].norm()).item()
+    assert rel <= 6e-3, f"pipelined tcgen05 vs mma.sync attention: relative L2 {rel:.3e}"
