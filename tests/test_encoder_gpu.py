@@ -196,7 +196,8 @@ def test_layernorm_on_read_is_bit_identical(precision):
     assert torch.equal(out[0], out[1])
 
 
-def test_tcgen05_attention_exact_softmax_path():
+@pytest.mark.parametrize("B", [3, 30])
+def test_tcgen05_attention_exact_softmax_path(B):
     """The tcgen05 attention kernels read S from tensor memory once and shift by the maximum over a SUBSET of the keys; a tile
     with an exponent more than 100 above that shift redoes the softmax in the exact two-pass form (the kernels that keep P in
     tensor memory have to run Q K^T again for that).  Query / key projections scaled by 16 make the scores span hundreds of
@@ -209,7 +210,8 @@ def test_tcgen05_attention_exact_softmax_path():
         for layer in model.encoder.layer:
             layer.attention.self.query.weight.mul_(16.0)
             layer.attention.self.key.weight.mul_(16.0)
-    B, L, lens = 3, 256, [256, 200, 90]
+    L = 256
+    lens = ([256, 200, 90] * 10)[:B]   # B = 30: ~5 tiles per CTA of the pipelined kernel, most of them redone
     g = torch.Generator().manual_seed(17)
     ids = torch.randint(1000, 31000, (B, L), generator=g)
     for b, n in enumerate(lens):
