@@ -233,9 +233,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 constexpr int kEpiPitch = 80;
 constexpr int kEpiBytesPerWarp = 32 * kEpiPitch;
 
+// ln_st: the (mean, rstd) of this lane's four rows (row0 + 8 i + lane / 4) when the caller has already fetched them -- the
+// persistent kernel does, once per tile and before it waits for the accumulator -- else nullptr.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float (&v)[32], uint8_t* stage, int lane, int row0,
-                                                        int col) {
+                                                        int col, const float2* ln_st = nullptr) {
     if (g.bias) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -255,8 +257,28 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
     uint8_t* wr = stage + lane * kEpiPitch;
     const uint8_t* rd = stage + r_sub * kEpiPitch + c_sub * 16;
     if (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+        // LayerNorm on read: the statistics of this lane's four rows once per chunk, gamma / beta of its columns once per half
+        const bool lnr = EPI == EPI_RESID_F32 && g.ln_stats != nullptr;  // uniform
+        float2 st[4];
+        if (lnr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) st[i] = ln_st ? ln_st[i] : __ldg(g.ln_stats + min(row0 + 8 * i + r_sub, g.M - 1));
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            // the residual loads go out before the chunk is turned through the staging buffer
+            float4 rr[4], gm, bt;
+            if (EPI == EPI_RESID_F32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = min(row0 + 8 * i + r_sub, g.M - 1);
+                    rr[i] = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.N + col + 16 * h + 4 * c_sub));
+                }
+                if (lnr) {
+                    gm = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + col + 16 * h + 4 * c_sub));
+                    bt = __ldg(reinterpret_cast<const float4*>(g.ln_beta + col + 16 * h + 4 * c_sub));
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<float4*>(wr + 16 * j) =
@@ -269,13 +291,8 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
                 if (row < g.M) {
                     const size_t off = (size_t)row * g.N + col + 16 * h + 4 * c_sub;
                     if (EPI == EPI_RESID_F32) {
-                        float4 rr = __ldg(reinterpret_cast<const float4*>(g.residual + off));
-                        if (g.ln_stats) {  // uniform
-                            const int c4 = col + 16 * h + 4 * c_sub;
-                            rr = ln_on_read(rr, __ldg(g.ln_stats + row), __ldg(reinterpret_cast<const float4*>(g.ln_gamma + c4)),
-                                            __ldg(reinterpret_cast<const float4*>(g.ln_beta + c4)));
-                        }
-                        x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                        const float4 r4 = lnr ? ln_on_read(rr[i], st[i], gm, bt) : rr[i];
+                        x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
                     }
                     *reinterpret_cast<float4*>(g.out_f32 + off) = x;
                 }
@@ -445,6 +462,11 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
             const int buf = t & 1;
             const int row0 = ((tile / n_tiles) * CL + rank) * kBlockM + quad * 32;
             const int n0 = (tile % n_tiles) * BLOCK_N + half * kCols;
+            float2 ln_st[4];  // LayerNorm on read: row statistics of this lane's rows, fetched under the wait for the accumulator
+            if (EPI == EPI_RESID_F32 && g.ln_stats) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ln_st[i] = __ldg(g.ln_stats + min(row0 + 8 * i + (lane >> 2), g.M - 1));
+            }
             mbar_wait(&tmem_full[buf], (t >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N + half * kCols);
@@ -465,14 +487,14 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
                     tmem_ld32_issue(acc + (uint32_t)(c0 + 32), vb);
                 else
                     release();
-                epilogue_store32_staged<EPI>(g, va, stage, lane, row0, n0 + c0);
+                epilogue_store32_staged<EPI>(g, va, stage, lane, row0, n0 + c0, ln_st);
                 if (second) {
                     tmem_ld32_wait(vb);
                     if (c0 + 64 < kCols)
                         tmem_ld32_issue(acc + (uint32_t)(c0 + 64), va);
                     else
                         release();
-                    epilogue_store32_staged<EPI>(g, vb, stage, lane, row0, n0 + c0 + 32);
+                    epilogue_store32_staged<EPI>(g, vb, stage, lane, row0, n0 + c0 + 32, ln_st);
                 }
             }
         }
