@@ -264,21 +264,25 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
 #pragma unroll
             for (int i = 0; i < 4; ++i) st[i] = ln_st ? ln_st[i] : __ldg(g.ln_stats + min(row0 + 8 * i + r_sub, g.M - 1));
         }
+        // the residual loads of BOTH halves go out before the chunk is turned through the staging buffer: one L2 round trip
+        // per chunk instead of one per half (the epilogue of the K = 768 residual GEMM is a chain of such round trips)
+        float4 rr[8], gm[2], bt[2];
+        if (EPI == EPI_RESID_F32) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            // the residual loads go out before the chunk is turned through the staging buffer
-            float4 rr[4], gm, bt;
-            if (EPI == EPI_RESID_F32) {
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = min(row0 + 8 * i + r_sub, g.M - 1);
-                    rr[i] = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.N + col + 16 * h + 4 * c_sub));
+                    rr[4 * h + i] = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.N + col + 16 * h + 4 * c_sub));
                 }
                 if (lnr) {
-                    gm = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + col + 16 * h + 4 * c_sub));
-                    bt = __ldg(reinterpret_cast<const float4*>(g.ln_beta + col + 16 * h + 4 * c_sub));
+                    gm[h] = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + col + 16 * h + 4 * c_sub));
+                    bt[h] = __ldg(reinterpret_cast<const float4*>(g.ln_beta + col + 16 * h + 4 * c_sub));
                 }
             }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 *reinterpret_cast<float4*>(wr + 16 * j) =
@@ -291,7 +295,7 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
                 if (row < g.M) {
                     const size_t off = (size_t)row * g.N + col + 16 * h + 4 * c_sub;
                     if (EPI == EPI_RESID_F32) {
-                        const float4 r4 = lnr ? ln_on_read(rr[i], st[i], gm, bt) : rr[i];
+                        const float4 r4 = lnr ? ln_on_read(rr[4 * h + i], st[i], gm[h], bt[h]) : rr[4 * h + i];
                         x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
                     }
                     *reinterpret_cast<float4*>(g.out_f32 + off) = x;
