@@ -194,6 +194,15 @@ def test_layernorm_on_read_is_bit_identical(precision):
             _abi.set_option("ln_on_read", 1)
     assert torch.isfinite(out[1]).all()
     assert torch.equal(out[0], out[1])
+    # the other GEMM kernels carry the same epilogue: one tile per CTA (row-per-lane stores) and CTA pairs
+    for key, val in (("gemm_kernel", 0), ("gemm_pair", 1)):
+        _abi.set_option(key, val)
+        try:
+            alt = enc.forward(ids, lens, precision=precision).clone()
+            torch.cuda.synchronize()
+        finally:
+            _abi.set_option(key, 3 if key == "gemm_kernel" else 0)
+        assert torch.equal(alt, out[1]), f"{key}={val} with LayerNorm on read differs"
 
 
 @pytest.mark.parametrize("B", [3, 30])
