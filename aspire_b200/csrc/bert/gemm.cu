@@ -233,11 +233,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant_
 constexpr int kEpiPitch = 80;
 constexpr int kEpiBytesPerWarp = 32 * kEpiPitch;
 
+// The residual values a lane adds to one 32-column chunk: rows row0 + 8 i + lane / 4, columns col + 16 h + 4 (lane % 4) ..+3.
+__device__ __forceinline__ void epilogue_load_residual(const GemmArgs& g, int lane, int row0, int col, float4 (&rr)[8]) {
+    const int r_sub = lane >> 2, c_sub = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = min(row0 + 8 * i + r_sub, g.M - 1);
+            rr[4 * h + i] = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.N + col + 16 * h + 4 * c_sub));
+        }
+}
+
 // ln_st: the (mean, rstd) of this lane's four rows (row0 + 8 i + lane / 4) when the caller has already fetched them -- the
 // persistent kernel does, once per tile and before it waits for the accumulator -- else nullptr.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float (&v)[32], uint8_t* stage, int lane, int row0,
-                                                        int col, const float2* ln_st = nullptr) {
+                                                        int col, const float2* ln_st = nullptr, const float4* rr_pre = nullptr) {
     if (g.bias) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -273,7 +285,8 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = min(row0 + 8 * i + r_sub, g.M - 1);
-                    rr[4 * h + i] = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.N + col + 16 * h + 4 * c_sub));
+                    rr[4 * h + i] = rr_pre ? rr_pre[4 * h + i]
+                                           : __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)row * g.N + col + 16 * h + 4 * c_sub));
                 }
                 if (lnr) {
                     gm[h] = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + col + 16 * h + 4 * c_sub));
@@ -344,6 +357,9 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
 //                        column half (w - 2) / 4 of the tile.
 // The one-tile-per-CTA kernel above pays TMEM allocation, barrier set-up, a cold TMA pipeline and a serial epilogue per
 // tile; here they are paid once per SM.  192 KB of operand ring per SM (6 x 32 KB or 4 x 48 KB).
+#ifndef ASP_GEMM_RESID_AHEAD
+#define ASP_GEMM_RESID_AHEAD 1
+#endif
 constexpr int kPersistEpiWarps = 8;
 constexpr int kPersistThreads = 64 + 32 * kPersistEpiWarps;
 
@@ -481,7 +497,23 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap ta_hi, const __gri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[buf]);
             };
-            float va[32], vb[32];
+            float va[32];
+            if (EPI == EPI_RESID_F32 && ASP_GEMM_RESID_AHEAD) {
+                // Residual epilogue: what it waits for is the residual rows (a global load, ~1 us under load), not tensor
+                // memory.  The register budget (168) holds ONE accumulator chunk and TWO chunks of residual values: the next
+                // chunk's residual loads are in flight while this chunk is added, staged and stored.
+                float4 ra[8], rb[8];
+                epilogue_load_residual(g, lane, row0, n0, ra);
+#pragma unroll
+                for (int c = 0; c < kCols / 32; ++c) {
+                    tmem_ld32(acc + (uint32_t)(32 * c), va);
+                    if (c + 1 == kCols / 32) release();
+                    if (c + 1 < kCols / 32) epilogue_load_residual(g, lane, row0, n0 + 32 * (c + 1), (c & 1) ? ra : rb);
+                    epilogue_store32_staged<EPI>(g, va, stage, lane, row0, n0 + 32 * c, ln_st, (c & 1) ? rb : ra);
+                }
+                continue;
+            }
+            float vb[32];
             tmem_ld32_issue(acc, va);
 #pragma unroll 1
             for (int c0 = 0; c0 < kCols; c0 += 64) {
