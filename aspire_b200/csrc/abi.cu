@@ -99,7 +99,7 @@ extern "C" int asp_set_option(const char* key, int value) {
         return ASP_OK;
     }
     if (strcmp(key, "gemm_pair") == 0) {
-        ASP_REQUIRE(value >= 0 && value <= 2, "asp_set_option: gemm_pair must be 0, 1 or 2");
+        ASP_REQUIRE(value >= -1 && value <= 2, "asp_set_option: gemm_pair must be -1 (auto), 0, 1 or 2");
         asp::g_gemm_pair = value;
         return ASP_OK;
     }

@@ -914,7 +914,12 @@ static int dispatch_pair(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
 int g_gemm_kernel = 3;
 constexpr int kCost192 = 520;  // (FFN2 - attention-output time at 192 columns) / (36 K blocks x 2 rounds)
 int g_gemm_cluster = 1;
-int g_gemm_pair = 0;
+// -1 (default): CTA pairs with 256-wide pair tiles for the bf16-output GEMMs (QKV, FFN1) of >= 16384 rows.  The 1-CTA MMA reads
+// A (4 KB) and B (8 KB) from shared memory for every M 128 x N 256 x K 16 instruction -- 96 B/clk of a 128 B/clk pipe, which is
+// the ~75 % "practical" tensor rate; a pair splits B between two SMs (64 B/clk each).  At 8192 rows the pair kernel gains nothing
+// (round 1), at 32768 rows the forward is 2 % faster (profiles/r02_4o_gemm_pair_32k.txt).  The residual GEMMs stay on the
+// one-CTA kernel, whose epilogue prefetches the residual.  0 = never, 1 / 2 = always (128- / 256-wide pair tiles).
+int g_gemm_pair = -1;
 int g_pdl = 1;
 
 int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
@@ -959,8 +964,10 @@ int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const voi
             }
         }
     }
-    if (g_gemm_pair && g_gemm_kernel >= 1) {
-        const int pbn = (g_gemm_pair == 2 && (N % 256) == 0) ? 256 : 128;
+    const bool pair_auto = g_gemm_pair < 0 && g_gemm_kernel == 3 && g_gemm_cluster == 1 && (N % 256) == 0 && M >= 16384 &&
+                           (epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16);
+    if ((g_gemm_pair > 0 || pair_auto) && g_gemm_kernel >= 1) {
+        const int pbn = ((g_gemm_pair == 2 || pair_auto) && (N % 256) == 0) ? 256 : 128;
         if ((rc = make_tmap_bf16(&ta_hi, a_hi, M, K, kBlockM))) return rc;
         if ((rc = make_tmap_bf16(&tb_hi, w_hi, N, K, pbn / 2))) return rc;
         if ((rc = make_tmap_bf16(&ta_lo, a_lo ? a_lo : a_hi, M, K, kBlockM))) return rc;

@@ -121,4 +121,26 @@ def test_gemm_kernel_variants_agree(epi):
     finally:
         _abi.set_option("gemm_kernel", 3)
         _abi.set_option("gemm_cluster", 1)
-        _abi.set_option("gemm_pair", 0)
+        _abi.set_option("gemm_pair", -1)
+
+
+def test_gemm_pair_auto_rule_large_m():
+    """gemm_pair = -1 (default) sends bf16-output GEMMs of >= 16384 rows to the CTA-pair kernel (256-wide pair tiles); an odd
+    number of 128-row blocks (16500 rows = 129 blocks) leaves the last pair half empty.  Bit-identical to the one-CTA kernel."""
+    from aspire_b200 import _abi
+    M, N, K = 16500, 768, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    a_hi, _ = _split(a)
+    w_hi, _ = _split(w)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = {}
+    try:
+        for pair in (-1, 0):
+            _abi.set_option("gemm_pair", pair)
+            out[pair] = [t.clone() for t in _gemm(a_hi, None, w_hi, None, bias, None, EPI_GELU, want_lo=False) if t is not None]
+    finally:
+        _abi.set_option("gemm_pair", -1)
+    for x, y in zip(out[-1], out[0]):
+        assert torch.equal(x, y)
