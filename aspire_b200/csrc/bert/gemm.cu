@@ -357,6 +357,9 @@ __device__ __forceinline__ void epilogue_store32_staged(const GemmArgs& g, float
 //                        column half (w - 2) / 4 of the tile.
 // The one-tile-per-CTA kernel above pays TMEM allocation, barrier set-up, a cold TMA pipeline and a serial epilogue per
 // tile; here they are paid once per SM.  192 KB of operand ring per SM (6 x 32 KB or 4 x 48 KB).
+#ifndef ASP_GEMM_PAIR_FFN2
+#define ASP_GEMM_PAIR_FFN2 1
+#endif
 #ifndef ASP_GEMM_RESID_AHEAD
 #define ASP_GEMM_RESID_AHEAD 1
 #endif
@@ -659,7 +662,24 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_cons
             mbar_wait(&tmem_full[buf], (t >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BLOCK_N + half * kCols);
-            float va[32], vb[32];
+            float va[32];
+            if (EPI == EPI_RESID_F32 && ASP_GEMM_RESID_AHEAD) {  // as in the one-CTA kernel: the double buffer is on the residual loads
+                float4 ra[8], rb[8];
+                epilogue_load_residual(g, lane, row0, n0, ra);
+#pragma unroll
+                for (int c = 0; c < kCols / 32; ++c) {
+                    tmem_ld32(acc + (uint32_t)(32 * c), va);
+                    if (c + 1 == kCols / 32) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tmem_empty[buf], 0);
+                    }
+                    if (c + 1 < kCols / 32) epilogue_load_residual(g, lane, row0, n0 + 32 * (c + 1), (c & 1) ? ra : rb);
+                    epilogue_store32_staged<EPI>(g, va, stage, lane, row0, n0 + 32 * c, nullptr, (c & 1) ? rb : ra);
+                }
+                continue;
+            }
+            float vb[32];
             tmem_ld32_issue(acc, va);
 #pragma unroll 1
             for (int c0 = 0; c0 < kCols; c0 += 64) {
@@ -914,11 +934,12 @@ static int dispatch_pair(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
 int g_gemm_kernel = 3;
 constexpr int kCost192 = 520;  // (FFN2 - attention-output time at 192 columns) / (36 K blocks x 2 rounds)
 int g_gemm_cluster = 1;
-// -1 (default): CTA pairs with 256-wide pair tiles for the bf16-output GEMMs (QKV, FFN1) of >= 16384 rows.  The 1-CTA MMA reads
+// -1 (default): CTA pairs with 256-wide pair tiles for the GEMMs of >= 16384 rows whose main loop is what is left to gain -- the
+// bf16-output ones (QKV, FFN1) and the K >= 2048 residual one (FFN2); attn-out (K = 768, epilogue-bound) stays on one CTA.  The 1-CTA MMA reads
 // A (4 KB) and B (8 KB) from shared memory for every M 128 x N 256 x K 16 instruction -- 96 B/clk of a 128 B/clk pipe, which is
 // the ~75 % "practical" tensor rate; a pair splits B between two SMs (64 B/clk each).  At 8192 rows the pair kernel gains nothing
-// (round 1), at 32768 rows the forward is 2 % faster (profiles/r02_4o_gemm_pair_32k.txt).  The residual GEMMs stay on the
-// one-CTA kernel, whose epilogue prefetches the residual.  0 = never, 1 / 2 = always (128- / 256-wide pair tiles).
+// (round 1), at 32768 rows the forward is 6 % faster (profiles/r02_4o_gemm_pair_32k.txt).
+// 0 = never, 1 / 2 = always (128- / 256-wide pair tiles).
 int g_gemm_pair = -1;
 int g_pdl = 1;
 
@@ -965,7 +986,7 @@ int gemm_bf16_tn(const void* a_hi, const void* a_lo, const void* w_hi, const voi
         }
     }
     const bool pair_auto = g_gemm_pair < 0 && g_gemm_kernel == 3 && g_gemm_cluster == 1 && (N % 256) == 0 && M >= 16384 &&
-                           (epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16);
+                           (epilogue == EPI_BF16 || epilogue == EPI_GELU_BF16 || (ASP_GEMM_PAIR_FFN2 && epilogue == EPI_RESID_F32 && K >= 2048));
     if ((g_gemm_pair > 0 || pair_auto) && g_gemm_kernel >= 1) {
         const int pbn = ((g_gemm_pair == 2 || pair_auto) && (N % 256) == 0) ? 256 : 128;
         if ((rc = make_tmap_bf16(&ta_hi, a_hi, M, K, kBlockM))) return rc;

@@ -54,7 +54,7 @@ long long asp_launch_count(void);
  *   "gemm_kernel"   encoder GEMM: 3 persistent kernel, tile width picked per shape (default); 1 / 4 / 2 force 128- /
  *                   192- / 256-wide tiles; 0 one tile per CTA
  *   "gemm_cluster"  1 (default), 2 or 4 CTAs per cluster sharing W tiles by TMA multicast
- *   "gemm_pair"     CTA pairs (tcgen05 cta_group::2): -1 (default) 256-wide pair tiles for the bf16-output GEMMs of >= 16384
+ *   "gemm_pair"     CTA pairs (tcgen05 cta_group::2): -1 (default) 256-wide pair tiles for QKV, FFN1 and FFN2 at >= 16384
  *                   rows, 0 never, 1 / 2 always with 128- / 256-wide pair tiles
  *   "pdl"           1 (default) encoder kernels use programmatic dependent launch, 0 plain stream order
  *   "attn_tc"       plain-bf16 attention, L <= 256: 5 (default) pipelined tcgen05 kernel (producer + two worker groups per
