@@ -124,22 +124,25 @@ def test_gemm_kernel_variants_agree(epi):
         _abi.set_option("gemm_pair", -1)
 
 
-def test_gemm_pair_auto_rule_large_m():
-    """gemm_pair = -1 (default) sends bf16-output GEMMs of >= 16384 rows to the CTA-pair kernel (256-wide pair tiles); an odd
-    number of 128-row blocks (16500 rows = 129 blocks) leaves the last pair half empty.  Bit-identical to the one-CTA kernel."""
+@pytest.mark.parametrize("epi,K", [(EPI_GELU, 256), (EPI_RESID, 2048)])
+def test_gemm_pair_auto_rule_large_m(epi, K):
+    """gemm_pair = -1 (default) sends the bf16-output GEMMs and the K >= 2048 residual GEMM of >= 16384 rows to the CTA-pair kernel
+    (256-wide pair tiles); an odd number of 128-row blocks (16500 rows = 129 blocks) leaves the last pair half empty.
+    Bit-identical to the one-CTA kernel."""
     from aspire_b200 import _abi
-    M, N, K = 16500, 768, 256
+    M, N = 16500, 768
     g = torch.Generator(device="cuda").manual_seed(5)
     a = torch.randn(M, K, device="cuda", generator=g)
     w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
     a_hi, _ = _split(a)
     w_hi, _ = _split(w)
     bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g) if epi == EPI_RESID else None
     out = {}
     try:
         for pair in (-1, 0):
             _abi.set_option("gemm_pair", pair)
-            out[pair] = [t.clone() for t in _gemm(a_hi, None, w_hi, None, bias, None, EPI_GELU, want_lo=False) if t is not None]
+            out[pair] = [t.clone() for t in _gemm(a_hi, None, w_hi, None, bias, resid, epi, want_lo=False) if t is not None]
     finally:
         _abi.set_option("gemm_pair", -1)
     for x, y in zip(out[-1], out[0]):
