@@ -71,7 +71,8 @@ extern "C" int asp_set_option(const char* key, int value) {
         return ASP_OK;
     }
     if (strcmp(key, "span_tma") == 0) {  // developer switch: 1 span pooling staged by cp.async.bulk, 0 streaming loads
-        asp::g_span_tma = value != 0;
+        ASP_REQUIRE(value == 0 || value == 1, "asp_set_option: span_tma must be 0 or 1");
+        asp::g_span_tma = value;
         return ASP_OK;
     }
     if (strcmp(key, "ln_on_read") == 0) {  // developer switch: 1 inner LayerNorms leave statistics, the next residual epilogue normalises

@@ -36,6 +36,13 @@ def test_argument_validation_without_gpu():
     assert rc == -1
     rc = L.asp_set_option(b"no_such_option", 1)
     assert rc == -1 and b"unknown key" in L.asp_last_error()
+    # every documented switch accepts its documented values (and its default leaves the process as it was) and rejects the next one
+    for key, ok, bad, default in ((b"attn_tc", (0, 1, 2, 3, 4, 5), 6, 5), (b"ln_on_read", (0, 1), 2, 1), (b"gemm_pair", (-1, 0, 1, 2), 3, -1),
+                                  (b"span_tma", (0, 1), 2, 1), (b"oa_warps", (8, 12), 10, 12)):
+        for v in ok:
+            assert L.asp_set_option(key, v) == 0, (key, v)
+        assert L.asp_set_option(key, bad) == -1, (key, bad)
+        assert L.asp_set_option(key, default) == 0
 
 
 def test_no_cpu_fallback():
